@@ -1,0 +1,654 @@
+// fp32 SIMT kernels: the parity path (LFMQ_PREC_FP32) and every HBM-bound piece of the step
+// (batcher gather, BN/dropout, head + loss, clip + optimizer + MaxNorm).  sm_100a.
+//
+// Reference call sites are cited per kernel (paths relative to /root/reference/scripts).
+#include "kernels.h"
+
+#include <math.h>
+
+namespace lfmq {
+
+thread_local char g_err[512] = {0};
+long long g_launches = 0;
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// =============================================================================================
+// Generic strided SGEMM, 64x64x16 tiles, 4x4 micro-tiles, deterministic split-K.
+// =============================================================================================
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool A_M_CONTIG, bool B_N_CONTIG>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long sAm,
+                                                    long sAk, const float* __restrict__ B, long sBk, long sBn,
+                                                    float* __restrict__ C, long ldc, float beta, int kchunk,
+                                                    float* __restrict__ partial) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + 256 * r;
+      int m, k;
+      if (A_M_CONTIG) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < kend) ? __ldg(A + (long)gm * sAm + (long)gk * sAk) : 0.f;
+      int n, kb;
+      if (B_N_CONTIG) { n = idx & 63; kb = idx >> 6; } else { kb = idx & 15; n = idx >> 4; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < N && gkb < kend) ? __ldg(B + (long)gkb * sBk + (long)gn * sBn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      if (partial) {
+        partial[((long)blockIdx.z * M + gm) * N + gn] = acc[i][j];
+      } else {
+        float* c = C + (long)gm * ldc + gn;
+        *c = (beta == 0.f) ? acc[i][j] : fmaf(beta, *c, acc[i][j]);
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(int M, int N, int S, const float* __restrict__ partial, float* __restrict__ C,
+                                     long ldc, float beta) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[(long)z * M * N + i];
+  float* c = C + (i / N) * ldc + (i % N);
+  *c = (beta == 0.f) ? s : fmaf(beta, *c, s);
+}
+
+int sgemm(cudaStream_t s, int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk,
+          long sBn, float* C, long ldc, float beta, float* scratch, size_t scratch_elems) {
+  if (M <= 0 || N <= 0) return 0;
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  int S = 1;
+  if (K >= 2048 && tiles < 296 && scratch) {
+    S = min(cdiv(K, 512), max(1, 592 / tiles));
+    while (S > 1 && (size_t)S * M * N > scratch_elems) --S;
+  }
+  int kchunk = cdiv(cdiv(K, S), BK) * BK;
+  if (kchunk <= 0) kchunk = BK;
+  S = max(1, cdiv(K, kchunk));
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), S);
+  float* partial = (S > 1) ? scratch : nullptr;
+  const bool am = (sAm == 1), bn = (sBn == 1);
+  if (am && bn)
+    sgemm_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, kchunk, partial);
+  else if (am && !bn)
+    sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, kchunk, partial);
+  else if (!am && bn)
+    sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, kchunk, partial);
+  else
+    sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, kchunk, partial);
+  LFMQ_LAUNCH_CHECK();
+  if (S > 1) {
+    splitk_reduce_kernel<<<cdiv((long)M * N, 256), 256, 0, s>>>(M, N, S, partial, C, ldc, beta);
+    LFMQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// =============================================================================================
+// LSTM cell, pointwise halves of one time step (Keras LSTM implementation=2,
+// models/point_estimate/rnn_point_estimate.py:80-87).
+// =============================================================================================
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void lstm_pointwise_fwd_kernel(int B, int T, int H, int t, const float* __restrict__ z,
+                                          const float* __restrict__ bias, float* __restrict__ gates,
+                                          float* __restrict__ c, float* __restrict__ h,
+                                          const float* __restrict__ rmask, float* __restrict__ hm) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const float* zr = z + (long)b * 4 * H;
+  const float gi = sigmoid_f(zr[j] + bias[j]);
+  const float gf = sigmoid_f(zr[H + j] + bias[H + j]);
+  const float gg = tanhf(zr[2 * H + j] + bias[2 * H + j]);
+  const float go = sigmoid_f(zr[3 * H + j] + bias[3 * H + j]);
+  const long o = ((long)b * T + t) * H + j;
+  const float cp = (t > 0) ? c[o - H] : 0.f;
+  const float cn = fmaf(gf, cp, gi * gg);
+  const float hn = go * tanhf(cn);
+  c[o] = cn;
+  h[o] = hn;
+  if (gates) {
+    float* g = gates + ((long)b * T + t) * 4 * H;
+    g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
+  }
+  if (hm) hm[idx] = rmask ? hn * rmask[idx] : hn;
+}
+
+int lstm_pointwise_fwd(cudaStream_t s, int B, int T, int H, int t, const float* z, const float* bias, float* gates,
+                       float* c, float* h, const float* rmask, float* hm) {
+  lstm_pointwise_fwd_kernel<<<cdiv((long)B * H, 256), 256, 0, s>>>(B, T, H, t, z, bias, gates, c, h, rmask, hm);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// dz_t from (dh_out_t + dh_rec), saved gates and cell states; dc carried in place.
+__global__ void lstm_pointwise_bwd_kernel(int B, int T, int H, int t, const float* __restrict__ gates,
+                                          const float* __restrict__ c, const float* __restrict__ dh_out,
+                                          const float* __restrict__ dh_rec, const float* __restrict__ rmask,
+                                          float* __restrict__ dc, float* __restrict__ dz) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const long o = ((long)b * T + t) * H + j;
+  const float* g = gates + ((long)b * T + t) * 4 * H;
+  const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+  float dh = dh_out[o];
+  if (dh_rec) dh += rmask ? dh_rec[idx] * rmask[idx] : dh_rec[idx];
+  const float tc = tanhf(c[o]);
+  const float cp = (t > 0) ? c[o - H] : 0.f;
+  const float d_o = dh * tc;
+  const float dcn = ((t < T - 1) ? dc[idx] : 0.f) + dh * go * (1.f - tc * tc);
+  const float di = dcn * gg, dg = dcn * gi, df = dcn * cp;
+  dc[idx] = dcn * gf;
+  float* d = dz + ((long)b * T + t) * 4 * H;
+  d[j] = di * gi * (1.f - gi);
+  d[H + j] = df * gf * (1.f - gf);
+  d[2 * H + j] = dg * (1.f - gg * gg);
+  d[3 * H + j] = d_o * go * (1.f - go);
+}
+
+int lstm_pointwise_bwd(cudaStream_t s, int B, int T, int H, int t, const float* gates, const float* c,
+                       const float* dh_out, const float* dh_rec, const float* rmask, float* dc, float* dz) {
+  lstm_pointwise_bwd_kernel<<<cdiv((long)B * H, 256), 256, 0, s>>>(B, T, H, t, gates, c, dh_out, dh_rec, rmask, dc,
+                                                                   dz);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// recurrent_dropout mask [B,H], one per call, shared by all T steps (rnn_point_estimate.py:86).
+__global__ void gen_row_mask_kernel(int B, int H, DropoutKey key, int64_t row0, float* __restrict__ rmask) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = H / 4;
+  if (q >= (long)B * nq) return;
+  const long b = q / nq;
+  float m[4];
+  dropout_quad(key, (uint64_t)(row0 + b) * nq + (q % nq), m);
+  *reinterpret_cast<float4*>(rmask + q * 4) = make_float4(m[0], m[1], m[2], m[3]);
+}
+
+int gen_row_mask(cudaStream_t s, int B, int H, DropoutKey key, int64_t row0, float* rmask) {
+  gen_row_mask_kernel<<<cdiv((long)B * H / 4, 256), 256, 0, s>>>(B, H, key, row0, rmask);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// hp[b,t,:] = (t > 0 ? h[b,t-1,:] : 0) * rmask[b,:]  -- the operand of dU = hp^T dz (App. A.4).
+__global__ void shift_mask_kernel(int B, int T, int H, const float* __restrict__ h, const float* __restrict__ rmask,
+                                  float* __restrict__ hp) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * T * H) return;
+  const int j = (int)(idx % H);
+  const long bt = idx / H;
+  const int t = (int)(bt % T);
+  const long b = bt / T;
+  float v = (t > 0) ? h[idx - H] : 0.f;
+  if (rmask) v *= rmask[b * H + j];
+  hp[idx] = v;
+}
+
+int shift_mask(cudaStream_t s, int B, int T, int H, const float* h, const float* rmask, float* hp) {
+  shift_mask_kernel<<<cdiv((long)B * T * H, 256), 256, 0, s>>>(B, T, H, h, rmask, hp);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// BatchNormalization (inference-mode affine) + Dropout
+// (rnn_point_estimate.py:88-89).
+// =============================================================================================
+__global__ void bn_dropout_fwd_kernel(long nquads, int T, int H, const float* __restrict__ h,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                      bool use_dropout, DropoutKey key, int64_t row0, float* __restrict__ y) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nquads) return;
+  const int nq = H / 4;
+  const int j = (int)(q % nq) * 4;
+  const float4 hv = *reinterpret_cast<const float4*>(h + q * 4);
+  float m[4] = {1.f, 1.f, 1.f, 1.f};
+  if (use_dropout) dropout_quad(key, (uint64_t)row0 * T * nq + q, m);
+  const float hin[4] = {hv.x, hv.y, hv.z, hv.w};
+  float out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float inv = 1.0f / sqrtf(var[j + i] + eps);
+    out[i] = (gamma[j + i] * (hin[i] - mean[j + i]) * inv + beta[j + i]) * m[i];
+  }
+  *reinterpret_cast<float4*>(y + q * 4) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+int bn_dropout_fwd(cudaStream_t s, int B, int T, int H, const float* h, const float* gamma, const float* beta,
+                   const float* mean, const float* var, float eps, bool use_dropout, DropoutKey key, int64_t row0,
+                   float* y) {
+  const long nquads = (long)B * T * H / 4;
+  bn_dropout_fwd_kernel<<<cdiv(nquads, 256), 256, 0, s>>>(nquads, T, H, h, gamma, beta, mean, var, eps, use_dropout,
+                                                          key, row0, y);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// dh_out = dy * d * gamma * inv ; per-block partial column sums of dgamma, dbeta -> scratch[blk][2H].
+constexpr int BN_ROWS_PER_BLOCK = 128;
+
+__global__ void bn_dropout_bwd_kernel(long rows, int T, int H, const float* __restrict__ dy,
+                                      const float* __restrict__ h, const float* __restrict__ gamma,
+                                      const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                      bool use_dropout, DropoutKey key, int64_t row0, float* __restrict__ dh_out,
+                                      float* __restrict__ partial) {
+  extern __shared__ float red[];  // [RL][2*H]
+  const int nq = H / 4;
+  const int RL = blockDim.x / nq;
+  const int qc = threadIdx.x % nq, rl = threadIdx.x / nq;
+  const int j = qc * 4;
+  float g[4], mu[4], inv[4], sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g[i] = gamma[j + i];
+    mu[i] = mean[j + i];
+    inv[i] = 1.0f / sqrtf(var[j + i] + eps);
+  }
+  const long r0 = (long)blockIdx.x * BN_ROWS_PER_BLOCK;
+  const long r1 = min(rows, r0 + BN_ROWS_PER_BLOCK);
+  if (rl < RL) {
+    for (long r = r0 + rl; r < r1; r += RL) {
+      const long q = r * nq + qc;
+      const float4 dv = *reinterpret_cast<const float4*>(dy + q * 4);
+      const float4 hv = *reinterpret_cast<const float4*>(h + q * 4);
+      float m[4] = {1.f, 1.f, 1.f, 1.f};
+      if (use_dropout) dropout_quad(key, (uint64_t)row0 * T * nq + q, m);
+      const float d[4] = {dv.x * m[0], dv.y * m[1], dv.z * m[2], dv.w * m[3]};
+      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sg[i] += d[i] * (hh[i] - mu[i]) * inv[i];
+        sb[i] += d[i];
+        o[i] = d[i] * g[i] * inv[i];
+      }
+      *reinterpret_cast<float4*>(dh_out + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red[(long)rl * 2 * H + j + i] = sg[i];
+      red[(long)rl * 2 * H + H + j + i] = sb[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < RL; ++r) sum += red[(long)r * 2 * H + c];
+    partial[(long)blockIdx.x * 2 * H + c] = sum;
+  }
+}
+
+__global__ void colsum_partial_kernel(long rows, int N, long rows_per_block, const float* __restrict__ A,
+                                      float* __restrict__ partial) {
+  const long r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = min(rows, r0 + rows_per_block);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s = 0.f;
+    for (long r = r0; r < r1; ++r) s += A[r * N + n];
+    partial[(long)blockIdx.x * N + n] = s;
+  }
+}
+
+int colsum(cudaStream_t s, long rows, int N, const float* A, float* out, float* scratch, size_t scratch_elems) {
+  long nblk = min((long)1024, max((long)1, rows / 64));
+  while (nblk > 1 && (size_t)nblk * N > scratch_elems) nblk /= 2;
+  if (nblk <= 1) {
+    colsum_partial_kernel<<<1, 256, 0, s>>>(rows, N, rows, A, out);
+    LFMQ_LAUNCH_CHECK();
+    return 0;
+  }
+  const long rpb = (rows + nblk - 1) / nblk;
+  nblk = (rows + rpb - 1) / rpb;
+  colsum_partial_kernel<<<(int)nblk, 256, 0, s>>>(rows, N, rpb, A, scratch);
+  LFMQ_LAUNCH_CHECK();
+  colsum_partial_kernel<<<1, 256, 0, s>>>(nblk, N, nblk, scratch, out);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int bn_dropout_bwd(cudaStream_t s, int B, int T, int H, const float* dy, const float* h, const float* gamma,
+                   const float* mean, const float* var, float eps, bool use_dropout, DropoutKey key, int64_t row0,
+                   float* dh_out, float* dgamma, float* dbeta, float* scratch, size_t scratch_elems) {
+  if (dbeta != dgamma + H) {
+    LFMQ_SET_ERR("bn_dropout_bwd: dgamma/dbeta must be adjacent");
+    return 1;
+  }
+  const long rows = (long)B * T;
+  const int nq = H / 4;
+  if (nq > 256) {
+    LFMQ_SET_ERR("bn_dropout_bwd: num_hidden > 1024 unsupported");
+    return 3;
+  }
+  const int RL = max(1, 256 / nq);
+  const int nblk = cdiv(rows, BN_ROWS_PER_BLOCK);
+  const size_t need = (size_t)nblk * 2 * H + (size_t)1024 * 2 * H;
+  if (need > scratch_elems) {
+    LFMQ_SET_ERR("bn_dropout_bwd: scratch too small (%zu > %zu)", need, scratch_elems);
+    return 4;
+  }
+  bn_dropout_bwd_kernel<<<nblk, nq * RL, (size_t)RL * 2 * H * sizeof(float), s>>>(
+      rows, T, H, dy, h, gamma, mean, var, eps, use_dropout, key, row0, dh_out, scratch);
+  LFMQ_LAUNCH_CHECK();
+  return colsum(s, nblk, 2 * H, scratch, dgamma, scratch + (size_t)nblk * 2 * H, (size_t)1024 * 2 * H);
+}
+
+__global__ void add_bias_rows_kernel(long n, int N, float* __restrict__ C, const float* __restrict__ bias) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) C[i] += bias[i % N];
+}
+
+int add_bias_rows(cudaStream_t s, long rows, int N, float* C, const float* bias) {
+  add_bias_rows_kernel<<<cdiv(rows * N, 256), 256, 0, s>>>(rows * N, N, C, bias);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fill_kernel(float* p, long n, float v) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int fill(cudaStream_t s, float* p, long n, float v) {
+  if (n <= 0) return 0;
+  fill_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, n, v);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Loss (model_utils/losses.py:55-98,121-135), one thread per [b,t] row.
+// =============================================================================================
+constexpr int LOSS_BLOCKS = 296;
+
+__device__ __forceinline__ void block_reduce4(double v[4], double* out4) {
+  __shared__ double sm[4][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = warp_sum(v[i]);
+    if (lane == 0) sm[i][w] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sm[threadIdx.x][k];
+    out4[threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_rows_kernel(int B, int T, int O, const float* __restrict__ pred,
+                                                        const float* __restrict__ y,
+                                                        const float* __restrict__ denom, int target_idx, float p1,
+                                                        float p2, float* __restrict__ dpred,
+                                                        double* __restrict__ partial) {
+  double acc[4] = {0, 0, 0, 0};  // s0, s1, s2, mask count
+  float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
+  if (dpred) {
+    const float Bg = denom[0], Mg = denom[1];
+    c_all = (1.f - p1) * (1.f - p2) / ((float)O * Mg);
+    c_last = (1.f - p1) * p2 / (Bg * (float)O);
+    c_tar = p1 / Bg;
+  }
+  const long rows = (long)B * T;
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long)gridDim.x * blockDim.x) {
+    const float* yr = y + r * O;
+    const float* pr = pred ? pred + r * O : nullptr;
+    bool any = false;
+    for (int k = 0; k < O; ++k) any |= (yr[k] != 0.0f);          // losses.py:72
+    const float m = any ? 1.f : 0.f;
+    acc[3] += m;
+    if (!pr) continue;
+    const bool last = ((int)(r % T) == T - 1);
+    for (int k = 0; k < O; ++k) {
+      const float d = pr[k] * m - yr[k];                           // losses.py:75
+      const float d2 = d * d;
+      acc[2] += d2;
+      float coef = c_all;
+      if (last) {
+        acc[1] += d2;
+        coef += c_last;
+        if (k == target_idx) { acc[0] += d2; coef += c_tar; }
+      }
+      if (dpred) dpred[r * O + k] = 2.f * d * coef * m;
+    }
+  }
+  block_reduce4(acc, partial + (long)blockIdx.x * 4);
+}
+
+// mode 0: maskout = {B, mask_count};  mode 1: out = {loss, mse_0} (+ maskout when given)
+__global__ void loss_final_kernel(int nblk, const double* __restrict__ partial, const float* __restrict__ denom,
+                                  int B, int O, float p1, float p2, int mode, float* __restrict__ out,
+                                  float* __restrict__ maskout) {
+  if (threadIdx.x != 0) return;
+  double s[4] = {0, 0, 0, 0};
+  for (int b = 0; b < nblk; ++b)
+    for (int i = 0; i < 4; ++i) s[i] += partial[(long)b * 4 + i];
+  if (maskout) {
+    maskout[0] = (float)B;
+    maskout[1] = (float)s[3];
+  }
+  if (mode == 0) return;
+  const double Bg = denom ? (double)denom[0] : (double)B;
+  const double Mg = denom ? (double)denom[1] : s[3];
+  const double mse0 = s[0] / Bg, mse1 = s[1] / (Bg * O), mse2 = s[2] / (Mg * O);
+  out[0] = (float)(p1 * mse0 + (1.0 - p1) * (p2 * mse1 + (1.0 - p2) * mse2));
+  out[1] = (float)mse0;
+}
+
+int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, float* scratch) {
+  double* partial = reinterpret_cast<double*>(scratch);
+  loss_rows_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(B, T, O, nullptr, y, nullptr, 0, 0.f, 0.f, nullptr, partial);
+  LFMQ_LAUNCH_CHECK();
+  loss_final_kernel<<<1, 32, 0, s>>>(LOSS_BLOCKS, partial, nullptr, B, O, 0.f, 0.f, 0, nullptr, out2);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const float* y, const float* denom,
+              int target_idx, float p1, float p2, float* dpred, float* out2, float* maskout2, float* scratch) {
+  double* partial = reinterpret_cast<double*>(scratch);
+  loss_rows_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(B, T, O, pred, y, denom, target_idx, p1, p2, dpred, partial);
+  LFMQ_LAUNCH_CHECK();
+  loss_final_kernel<<<1, 32, 0, s>>>(LOSS_BLOCKS, partial, denom, B, O, p1, p2, 1, out2, maskout2);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// clip_by_global_norm + optimizer + MaxNorm (train.py:195-198, model_utils/optimizers.py:21-27,
+// rnn_point_estimate.py:85).
+// =============================================================================================
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(long n, const float* __restrict__ g,
+                                                            double* __restrict__ partial) {
+  double acc[4] = {0, 0, 0, 0};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double v = g[i];
+    acc[0] += v * v;
+  }
+  block_reduce4(acc, partial + (long)blockIdx.x * 4);
+}
+
+__global__ void norm_final_kernel(int nblk, const double* __restrict__ partial, float clip,
+                                  float* __restrict__ scalars) {
+  if (threadIdx.x != 0) return;
+  double s = 0;
+  for (int b = 0; b < nblk; ++b) s += partial[(long)b * 4];
+  const float gn = (float)sqrt(s);
+  scalars[0] = gn;
+  scalars[1] = (clip > 0.f) ? clip / fmaxf(gn, clip) : 1.0f;
+}
+
+int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* scalars, float* scratch) {
+  double* partial = reinterpret_cast<double*>(scratch);
+  const int nblk = (int)min((long)148, max((long)1, n / 2048));
+  sumsq_partial_kernel<<<nblk, 256, 0, s>>>(n, g, partial);
+  LFMQ_LAUNCH_CHECK();
+  norm_final_kernel<<<1, 32, 0, s>>>(nblk, partial, clip, scalars);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void opt_update_kernel(int opt, long n, float* __restrict__ p, const float* __restrict__ g,
+                                  float* __restrict__ s0, float* __restrict__ s1,
+                                  const float* __restrict__ scalars, float lr, float momentum) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gr = g[i] * scalars[1];
+  float w = p[i];
+  if (opt == 0) {            // Adadelta rho=.95 eps=1e-7
+    const float rho = 0.95f, eps = 1e-7f;
+    const float a = rho * s0[i] + (1.f - rho) * gr * gr;
+    const float upd = sqrtf(s1[i] + eps) / sqrtf(a + eps) * gr;
+    s0[i] = a;
+    s1[i] = rho * s1[i] + (1.f - rho) * upd * upd;
+    w -= lr * upd;
+  } else if (opt == 1) {     // Adam, lr already bias-corrected on the host
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f;
+    const float m = b1 * s0[i] + (1.f - b1) * gr;
+    const float v = b2 * s1[i] + (1.f - b2) * gr * gr;
+    s0[i] = m;
+    s1[i] = v;
+    w -= lr * m / (sqrtf(v) + eps);
+  } else if (opt == 2) {     // RMSprop rho=.9 eps=1e-7
+    const float rho = 0.9f, eps = 1e-7f;
+    const float v = rho * s0[i] + (1.f - rho) * gr * gr;
+    s0[i] = v;
+    w -= lr * gr / (sqrtf(v) + eps);
+  } else {                   // SGD (+ momentum)
+    if (momentum > 0.f) {
+      const float m = momentum * s0[i] - lr * gr;
+      s0[i] = m;
+      w += m;
+    } else {
+      w -= lr * gr;
+    }
+  }
+  p[i] = w;
+}
+
+int opt_update(cudaStream_t s, int opt, long n, float* p, const float* g, float* slot0, float* slot1,
+               const float* scalars, float lr, float, float, float momentum) {
+  opt_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(opt, n, p, g, slot0, slot1, scalars, lr, momentum);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// keras.constraints.MaxNorm(max_value, axis=0) on W[I,N]: one thread per column.
+__global__ void maxnorm_cols_kernel(int I, int N, float* __restrict__ W, float max_norm) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float ss = 0.f;
+  for (int i = 0; i < I; ++i) {
+    const float v = W[(long)i * N + n];
+    ss = fmaf(v, v, ss);
+  }
+  const float nr = sqrtf(ss);
+  const float f = fminf(fmaxf(nr, 0.f), max_norm) / (1e-7f + nr);
+  for (int i = 0; i < I; ++i) W[(long)i * N + n] *= f;
+}
+
+int maxnorm_cols(cudaStream_t s, int I, int N, float* W, float max_norm) {
+  maxnorm_cols_kernel<<<cdiv(N, 128), 128, 0, s>>>(I, N, W, max_norm);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Sliding-window batcher (data_processing.py:307-368, 370-449, 600-609).
+// One CTA per window; fp64 arithmetic then cast to fp32, as the reference.
+// =============================================================================================
+__device__ __forceinline__ double squash(double v) {
+  // np.sign(v) * np.log1p(np.abs(v)); NaN propagates
+  const double sg = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : ((v == 0.0) ? 0.0 : v));
+  return sg * log1p(fabs(v));
+}
+
+__global__ void __launch_bounds__(128) gather_batch_kernel(GatherArgs a) {
+  const int b = blockIdx.x;
+  const int is = a.inp_idx[b * 3 + 0], ipad = a.inp_idx[b * 3 + 2];
+  const int ts = a.tar_idx[b * 3 + 0], te = a.tar_idx[b * 3 + 1], tpad = a.tar_idx[b * 3 + 2];
+  double norm = 1.0;
+  if (a.seq_norm_col >= 0) {
+    // data_processing.py:393-396: max(seq[-1, idx], 10) with Python max() NaN semantics
+    const long rl = (long)is + (long)(a.T - 1 - ipad) * a.stride;
+    const double v = a.table[rl * a.n_cols + a.seq_norm_col];
+    norm = (10.0 > v) ? 10.0 : v;
+  }
+  if (threadIdx.x == 0) a.seq_norm[b] = norm;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int e = threadIdx.x; e < a.T * a.F; e += blockDim.x) {
+    const int t = e / a.F, f = e % a.F;
+    double v = 0.0;
+    if (t >= ipad) v = a.table[((long)is + (long)(t - ipad) * a.stride) * a.n_cols + a.inp_cols[f]];
+    if (f < a.O) {
+      v /= norm;
+      if (a.log_squasher) v = squash(v);
+    }
+    if (a.scale_flag[f]) v = (v - a.center[f]) / a.scale[f];
+    if (a.aux_masking && a.aux_flag[f] && t < a.T - 1) v = 0.0;
+    a.x[((long)b * a.T + t) * a.F + f] = (float)v;
+  }
+  for (int e = threadIdx.x; e < a.T * a.O; e += blockDim.x) {
+    const int t = e / a.O, k = e % a.O;
+    double v = 0.0;
+    if (t >= tpad) {
+      const long r = (long)ts + (long)(t - tpad) * a.stride;
+      v = (r <= te && r < a.n_rows) ? a.table[r * a.n_cols + a.fin_cols[k]] : qnan;  // :427-435
+    }
+    v /= norm;
+    if (a.log_squasher) v = squash(v);
+    v = (v - a.center[k]) / a.scale[k];
+    a.y[((long)b * a.T + t) * a.O + k] = (float)v;
+  }
+}
+
+int gather_batch(cudaStream_t s, const GatherArgs& a) {
+  if (a.B <= 0) return 0;
+  gather_batch_kernel<<<a.B, 128, 0, s>>>(a);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace lfmq

@@ -1,0 +1,239 @@
+"""Thin Python owner of one native forecaster instance (one per process / GPU).
+
+PyTorch is used for device allocation, streams and torch.distributed only; every piece of arithmetic
+happens in lfm_quant_b200/_lfmq.so through the C-ABI of include/lfmq.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ForecasterEngine(object):
+    """fwd / loss / BPTT / clip / optimizer / MaxNorm for RNNPointEstimate on one B200.
+
+    Mirrors what the reference builds in RNNPointEstimate._build_model
+    (scripts/models/point_estimate/rnn_point_estimate.py:40-107) plus the step body of
+    Train._train_step_point (scripts/train.py:178-199).
+    """
+
+    def __init__(self, *, max_batch, seq_len, n_inputs, n_outputs, num_hidden, num_layers=1, target_idx=0,
+                 train=True, precision='fp32', optimizer='Adadelta', dropout=0.0, recurrent_dropout=0.0,
+                 target_lambda=0.5, rnn_lambda=0.7, max_grad_norm=50.0, max_norm=3.0, sgd_momentum=0.0,
+                 seed=521, forward_only=False, device=None):
+        if not torch.cuda.is_available():
+            raise N.LfmqError('ForecasterEngine needs a CUDA device (no CPU fallback)')
+        self.lib = N.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if optimizer not in N.OPTIMIZERS:
+            raise ValueError("%s optimizer not found in tf.keras.optimizers" % optimizer)
+        cfg = N.LfmqConfig()
+        cfg.struct_size = C.sizeof(N.LfmqConfig)
+        cfg.max_batch, cfg.seq_len, cfg.n_inputs, cfg.n_outputs = max_batch, seq_len, n_inputs, n_outputs
+        cfg.num_hidden, cfg.num_layers, cfg.target_idx = num_hidden, num_layers, target_idx
+        cfg.train = 1 if train else 0
+        cfg.precision = {'fp32': N.PREC_FP32, 'bf16': N.PREC_BF16}[precision]
+        cfg.optimizer = N.OPTIMIZERS[optimizer]
+        cfg.forward_only = 1 if forward_only else 0
+        cfg.dropout, cfg.recurrent_dropout = dropout, recurrent_dropout
+        cfg.target_lambda, cfg.rnn_lambda = target_lambda, rnn_lambda
+        cfg.max_grad_norm, cfg.max_norm, cfg.sgd_momentum = max_grad_norm, max_norm, sgd_momentum
+        cfg.bn_epsilon = 1e-3
+        cfg.seed = seed
+        self.cfg = cfg
+        self.precision = precision
+        self.T, self.F, self.O, self.H, self.L = seq_len, n_inputs, n_outputs, num_hidden, num_layers
+        nbytes = C.c_uint64(0)
+        N.check(self.lib.lfmq_workspace_bytes(C.byref(cfg), C.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            self.handle = C.c_void_p(0)
+            N.check(self.lib.lfmq_create(C.byref(cfg), _ptr(self.workspace), nbytes, C.byref(self.handle)))
+        nt, ntr, ntot = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        N.check(self.lib.lfmq_param_count(self.handle, C.byref(nt), C.byref(ntr), C.byref(ntot)))
+        self.n_trainable, self.n_total = ntr.value, ntot.value
+        self.specs = []
+        for i in range(nt.value):
+            name = C.create_string_buffer(96)
+            ndim, off, tr = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+            shape = (C.c_int64 * 2)()
+            N.check(self.lib.lfmq_param_spec(self.handle, i, name, 96, C.byref(ndim), shape, C.byref(off),
+                                             C.byref(tr)))
+            shp = (shape[0], shape[1]) if ndim.value == 2 else (shape[0],)
+            self.specs.append((name.value.decode(), shp, off.value, bool(tr.value)))
+        self.params = self._view('lfmq_params_ptr', self.n_total)
+        self.grads = self._view('lfmq_grads_ptr', self.n_trainable + 4)
+        self._denom = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def _view(self, fn, n):
+        p = C.c_void_p(0)
+        N.check(getattr(self.lib, fn)(self.handle, C.byref(p)))
+        off = p.value - self.workspace.data_ptr()
+        return self.workspace[off:off + 4 * n].view(torch.float32)
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle.value:
+            self.lib.lfmq_destroy(self.handle)
+            self.handle = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------------
+    @property
+    def trainable_specs(self):
+        return [s for s in self.specs if s[3]]
+
+    def set_flat(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.shape == (self.n_total,)
+        N.check(self.lib.lfmq_set_params(self.handle, flat.ctypes.data_as(C.c_void_p), self.n_total, _stream()))
+
+    def get_flat(self):
+        out = np.empty(self.n_total, dtype=np.float32)
+        N.check(self.lib.lfmq_get_params(self.handle, out.ctypes.data_as(C.c_void_p), self.n_total, _stream()))
+        return out
+
+    def set_weights(self, weights, bn_stats=None):
+        """weights: arrays in Keras trainable_variables order; bn_stats: optional [(mean, var)] per layer."""
+        flat = self.get_flat()
+        tr = self.trainable_specs
+        assert len(weights) == len(tr), (len(weights), len(tr))
+        for w, (name, shp, off, _) in zip(weights, tr):
+            w = np.asarray(w, dtype=np.float32)
+            assert tuple(w.shape) == tuple(shp), (name, w.shape, shp)
+            flat[off:off + w.size] = w.ravel()
+        if bn_stats is not None:
+            nontr = [s for s in self.specs if not s[3]]
+            for l, (m, v) in enumerate(bn_stats):
+                for arr, (name, shp, off, _) in zip((m, v), nontr[2 * l:2 * l + 2]):
+                    flat[off:off + shp[0]] = np.asarray(arr, dtype=np.float32)
+        self.set_flat(flat)
+
+    def get_weights(self, trainable_only=True):
+        flat = self.get_flat()
+        out = []
+        for name, shp, off, tr in self.specs:
+            if trainable_only and not tr:
+                continue
+            out.append(flat[off:off + int(np.prod(shp))].reshape(shp).copy())
+        return out
+
+    def grads_list(self):
+        g = self.grads.detach().cpu().numpy()
+        return [g[off:off + int(np.prod(shp))].reshape(shp).copy() for name, shp, off, tr in self.specs if tr]
+
+    # ---- compute -------------------------------------------------------------------------------
+    def _check_x(self, x):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(), 'x must be a contiguous CUDA fp32 tensor'
+        assert x.dim() == 3 and x.shape[1] == self.T and x.shape[2] == self.F, tuple(x.shape)
+        return x.shape[0]
+
+    def forward(self, x, step=0, row0=0, out=None):
+        B = self._check_x(x)
+        if out is None:
+            out = torch.empty(B, self.T, self.O, dtype=torch.float32, device=x.device)
+        N.check(self.lib.lfmq_forward(self.handle, _ptr(x), B, row0, step, _ptr(out), _stream()))
+        return out
+
+    def loss(self, preds, y):
+        out = torch.empty(2, dtype=torch.float32, device=preds.device)
+        N.check(self.lib.lfmq_loss(self.handle, _ptr(preds.contiguous()), _ptr(y.contiguous()), preds.shape[0],
+                                   _ptr(out), _stream()))
+        return out
+
+    def mask_count(self, y):
+        out = torch.empty(2, dtype=torch.float32, device=y.device)
+        N.check(self.lib.lfmq_mask_count(self.handle, _ptr(y), y.shape[0], _ptr(out), _stream()))
+        return out
+
+    def backward(self, x, y, step=0, row0=0, denom=None):
+        B = self._check_x(x)
+        assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == (B, self.T, self.O)
+        N.check(self.lib.lfmq_backward(self.handle, _ptr(x), _ptr(y), B, row0, step, _ptr(denom), _stream()))
+
+    def apply(self, lr, iteration):
+        N.check(self.lib.lfmq_apply(self.handle, float(lr), int(iteration), _stream()))
+
+    def train_step(self, x, y, step, lr, out=None):
+        """One Train._train_step_point on this GPU; returns a device tensor {loss, mse_0} (no host sync)."""
+        B = self._check_x(x)
+        if out is None:
+            out = torch.empty(2, dtype=torch.float32, device=x.device)
+        N.check(self.lib.lfmq_train_step(self.handle, _ptr(x), _ptr(y), B, 0, step, float(lr), _ptr(out), _stream()))
+        return out
+
+    def train_step_dp(self, x, y, step, lr, row0, denom_global):
+        """Data-parallel step: local BPTT with global denominators, ONE NCCL all-reduce over the flat
+        gradient (+ loss/mse tail), then the replicated clip + optimizer."""
+        import torch.distributed as dist
+        self.backward(x, y, step=step, row0=row0, denom=denom_global)
+        dist.all_reduce(self.grads[:self.n_trainable + 2], op=dist.ReduceOp.SUM)
+        self.apply(lr, step)
+        return self.grads[self.n_trainable:self.n_trainable + 2]
+
+    REGIONS = ('fwd', 'head', 'bwd', 'wgrad', 'opt')
+
+    def profile(self, enable=True):
+        N.check(self.lib.lfmq_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{region: (total_ms, count)} of the event-bracketed regions since profile(True)."""
+        out = {}
+        for r, name in enumerate(self.REGIONS):
+            ms, n = C.c_float(0), C.c_int32(0)
+            N.check(self.lib.lfmq_profile_read(self.handle, r, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.lib.lfmq_launch_count())
+
+
+def gather_batch(table, inp_idx, tar_idx, *, seq_len, stride, inp_cols, fin_cols, seq_norm_col, center, scale,
+                 scale_flag, aux_flag, log_squasher=True, aux_masking=False):
+    """Device batcher: Dataset.get_batch (scripts/data_processing.py:307-368) over a CUDA-resident fp64 table.
+
+    All array arguments are CUDA tensors: table f64 [n_rows, n_cols]; inp_idx/tar_idx int32 [B,3];
+    inp_cols/fin_cols int32; center/scale f64; scale_flag/aux_flag uint8 [F].
+    Returns (x f32 [B,T,F], y f32 [B,T,O], seq_norm f64 [B]).
+    """
+    lib = N.load()
+    B = inp_idx.shape[0]
+    F, O = inp_cols.numel(), fin_cols.numel()
+    dev = table.device
+    x = torch.empty(B, seq_len, F, dtype=torch.float32, device=dev)
+    y = torch.empty(B, seq_len, O, dtype=torch.float32, device=dev)
+    sn = torch.empty(B, dtype=torch.float64, device=dev)
+    a = N.LfmqGatherArgs()
+    a.struct_size = C.sizeof(N.LfmqGatherArgs)
+    a.n_rows, a.n_cols, a.B, a.T, a.F, a.O = table.shape[0], table.shape[1], B, seq_len, F, O
+    a.stride = stride
+    a.seq_norm_col = -1 if not seq_norm_col else int(seq_norm_col)
+    a.log_squasher, a.aux_masking = int(bool(log_squasher)), int(bool(aux_masking))
+    for name, t, dt in (('table', table, torch.float64), ('inp_idx', inp_idx, torch.int32),
+                        ('tar_idx', tar_idx, torch.int32), ('inp_cols', inp_cols, torch.int32),
+                        ('fin_cols', fin_cols, torch.int32), ('center', center, torch.float64),
+                        ('scale', scale, torch.float64), ('scale_flag', scale_flag, torch.uint8),
+                        ('aux_flag', aux_flag, torch.uint8)):
+        assert t.is_cuda and t.dtype == dt and t.is_contiguous(), name
+        setattr(a, name, t.data_ptr())
+    a.x, a.y, a.seq_norm = x.data_ptr(), y.data_ptr(), sn.data_ptr()
+    N.check(lib.lfmq_gather_batch(C.byref(a), _stream()))
+    return x, y, sn

@@ -108,20 +108,20 @@ def reverse_log_squasher(x):
 def _get_seq(table, start, end, pad, stride, seq_len, nan_fill):
     """data_processing.py:370-398 (_get_train_seq) and :400-449 (_get_pred_seq, nan_fill=True).
 
-    Returns the [seq_len, n_cols] float64 slab (first ``pad`` rows zero).  In the prediction
-    variant rows whose index falls beyond the table are NaN (the reference would raise an
-    IndexError only when it runs off the end of the file; rows that exist are copied).
+    Returns the [seq_len, n_cols] float64 slab (first ``pad`` rows zero).  Training windows always
+    have exactly seq_len - pad rows in start..end.  In the prediction variant with a missing target
+    (tar_key != inp_key) the reference fills the slab with NaN and copies only the rows
+    range(start, end + stride, stride) that exist (:428-435); ``end`` was not advanced by
+    forecast_n for such windows (:276-279), so the tail rows stay NaN.
     """
     n_cols = table.shape[1]
     seq = np.zeros((seq_len, n_cols), dtype=np.float64)
-    rows = np.arange(start, end + stride, stride)
-    assert rows.shape[0] == seq_len - pad, (rows.shape, seq_len, pad)
-    if nan_fill:
-        body = np.full((seq_len - pad, n_cols), np.nan)
-        ok = rows < table.shape[0]
-        body[ok] = table[rows[ok]]
-    else:
-        body = table[rows]
+    rows = start + stride * np.arange(seq_len - pad)
+    ok = (rows <= end) & (rows < table.shape[0])
+    if not nan_fill:
+        assert ok.all(), (start, end, pad, stride, seq_len)
+    body = np.full((seq_len - pad, n_cols), np.nan)
+    body[ok] = table[rows[ok]]
     seq[pad:] = body
     return seq
 
