@@ -17,3 +17,7 @@ $(LIB): $(OBJS)
 
 clean:
 	rm -f $(OBJS) $(LIB)
+
+tools: tools/tc_probe
+tools/tc_probe: tools/tc_probe.cu $(CSRC)/sm100.cuh
+	$(NVCC) -O3 -std=c++17 -lineinfo $(ARCH) -o $@ $<
