@@ -1,0 +1,54 @@
+"""Losses(config, target_idx).weight_adjusted_mse (reference: scripts/model_utils/losses.py:19-135), evaluated by
+the native loss kernel (lfmq_loss).  Only the RNN point-estimate branch with forecast_steps == 1 is built; the
+MLP / Huber / UQ branches belong to other model families."""
+from __future__ import absolute_import, division, print_function
+
+import numpy as np
+
+
+class _Scalar(object):
+    """Device scalar with the ``.numpy()`` the drivers call (train.py:199,336)."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def numpy(self):
+        return float(self._t.item()) if hasattr(self._t, 'item') else float(self._t)
+
+    def __float__(self):
+        return self.numpy()
+
+
+class Losses(object):
+
+    def __init__(self, config, target_idx, engine=None):
+        self.config = config
+        self.target_idx = target_idx
+        self.engine = engine
+
+    def bind(self, engine):
+        self.engine = engine
+
+    def weight_adjusted_mse(self, y_true, y_pred, is_validation=False):
+        assert self.config.forecast_steps > 0, 'forecasts_steps should be a positive integer. %i was provided' % \
+            self.config.forecast_steps
+        assert isinstance(y_true, (list, tuple)), \
+            'arguments to loss function need to be a list [y_true], [y_true1, y_true2, ..]'
+        assert isinstance(y_pred, (list, tuple)), \
+            'arguments to loss function need to be a list [y_pred], [y_pred1, y_pred2, ..]'
+        if self.config.forecast_steps != 1 or 'RNN' not in self.config.nn_type:
+            raise NotImplementedError('only RNN point estimates with forecast_steps=1 are built on this path')
+        if len(self.config.forecast_steps_weights) == 1:
+            self.config.forecast_steps_weights = [1.0]           # losses.py:44-45
+        loss, mse = self._get_loss_point_estimate(y_true[0], y_pred[0], is_validation)
+        return loss, mse
+
+    def _get_loss_point_estimate(self, y_true, y_pred, is_validation=False):
+        import torch
+        assert self.engine is not None, 'Losses is not bound to a native engine'
+        dev = self.engine.device
+        to = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        yt = to(y_true).to(dev, torch.float32).contiguous()
+        yp = to(y_pred).to(dev, torch.float32).contiguous()
+        out = self.engine.loss(yp, yt)
+        return _Scalar(out[0]), _Scalar(out[1])

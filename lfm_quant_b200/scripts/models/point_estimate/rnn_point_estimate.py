@@ -1,0 +1,143 @@
+"""RNNPointEstimate (reference: scripts/models/point_estimate/rnn_point_estimate.py:17-154).
+
+Same constructor ``RNNPointEstimate(config, dataset)`` and ``.model`` attribute; the Keras functional graph is
+replaced by ``NativeForecaster``: n_layers x [LSTM -> BatchNormalization(inference affine) -> Dropout] -> Dense,
+executed by hand-written sm_100a CUDA behind the C-ABI of include/lfmq.h.
+"""
+from __future__ import absolute_import, division, print_function
+
+import os
+
+import numpy as np
+
+from ..model_base_class import BaseModelClass
+from ...model_utils.initializers import Initializer
+from ...model_utils.optimizers import Optimizers
+
+
+class _Variable(object):
+    """The slice of tf.Variable the drivers touch: name, shape, numpy()."""
+
+    def __init__(self, model, index, name, shape):
+        self._model, self._index, self.name, self.shape = model, index, name + ':0', tuple(shape)
+
+    def numpy(self):
+        return self._model.engine.get_weights()[self._index]
+
+
+class NativeForecaster(object):
+    """Keras-subset model object: __call__, predict, trainable_variables, save/load_weights,
+    reset_states, summary -- plus ``train_step`` (the fused native Train._train_step_point)."""
+
+    def __init__(self, config, seq_len, n_inputs, n_outputs, target_idx):
+        from ....engine import ForecasterEngine
+        self.config = config
+        if config.rnn_cell != 'lstm':
+            raise NotImplementedError('rnn_cell=%s: only the LSTM cell is built (GRU is a "next" row)' % config.rnn_cell)
+        if config.forecast_steps != 1:
+            raise NotImplementedError('forecast_steps > 1 is a "next" row of the scope table')
+        self.engine = ForecasterEngine(
+            max_batch=config.batch_size, seq_len=seq_len, n_inputs=n_inputs, n_outputs=n_outputs,
+            num_hidden=config.num_hidden, num_layers=config.num_layers, target_idx=target_idx,
+            train=bool(config.train), precision=getattr(config, 'precision', 'fp32'), optimizer=config.optimizer,
+            dropout=config.dropout, recurrent_dropout=config.recurrent_dropout, target_lambda=config.target_lambda,
+            rnn_lambda=config.rnn_lambda, max_grad_norm=config.max_grad_norm, max_norm=float(config.max_norm),
+            sgd_momentum=config.sgd_momentum, seed=config.seed, forward_only=not config.train)
+        specs = [(n, s) for (n, s, _, tr) in self.engine.specs if tr]
+        self.engine.set_weights(Initializer(config).initial_weights(specs))
+        self.trainable_variables = [_Variable(self, i, n, s) for i, (n, s) in enumerate(specs)]
+        self._calls = 0
+
+    # -- forward ---------------------------------------------------------------------------------------
+    def _to_device(self, inp):
+        import torch
+        if isinstance(inp, torch.Tensor):
+            return inp.to(self.engine.device, torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(inp, dtype=np.float32)).to(self.engine.device)
+
+    def __call__(self, inp, training=None):
+        """model(inp) (train.py:182): preds [B,T,O] on the device; dropout follows config.train."""
+        self._calls += 1
+        return self.engine.forward(self._to_device(inp), step=self._calls)
+
+    def predict(self, inp, batch_size=None):
+        """model.predict(inp) (train.py:289, predict.py:129): ndarray [B,T,O]."""
+        x = self._to_device(inp)
+        B = x.shape[0]
+        mb = self.engine.cfg.max_batch
+        outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls).cpu().numpy() for s in range(0, B, mb)]
+        return np.concatenate(outs, axis=0)
+
+    def train_step(self, inp, targets, lr, iteration):
+        """Fused fwd + loss + BPTT + clip + optimizer + MaxNorm; returns a device tensor {loss, mse_0}."""
+        return self.engine.train_step(self._to_device(inp), self._to_device(targets), iteration, lr)
+
+    # -- Keras API surface -------------------------------------------------------------------------------
+    def reset_states(self):
+        return None                                      # layers are stateless (train.py:105)
+
+    def count_params(self):
+        return self.engine.n_total
+
+    def summary(self):
+        lines = ['Model: "RNNPointEstimate" (native sm_100a, precision=%s)' % self.engine.precision,
+                 '%-44s %-16s %10s' % ('Variable', 'Shape', 'Param #'), '=' * 72]
+        for name, shape, _, tr in self.engine.specs:
+            lines.append('%-44s %-16s %10d%s' % (name, str(tuple(shape)), int(np.prod(shape)), '' if tr else '  (non-trainable)'))
+        lines += ['=' * 72, 'Total params: %d' % self.engine.n_total, 'Trainable params: %d' % self.engine.n_trainable]
+        return '\n'.join(lines)
+
+    @staticmethod
+    def _weights_path(prefix):
+        return prefix + '.lfmq.npz'
+
+    def save_weights(self, prefix):
+        """model.save_weights(<model_dir>/chkpts/chkpt) (train.py:99,171): Keras-style names in one .npz."""
+        flat = self.engine.get_flat()
+        arrs = {name: flat[off:off + int(np.prod(shp))].reshape(shp) for name, shp, off, _ in self.engine.specs}
+        os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+        with open(self._weights_path(prefix), 'wb') as fh:
+            np.savez(fh, **arrs)
+
+    def load_weights(self, prefix):
+        """model.load_weights(prefix) (train.py:87, predict.py:93)."""
+        path = self._weights_path(prefix)
+        if not os.path.isfile(path):
+            raise FileNotFoundError('no native checkpoint at %s' % path)
+        data = np.load(path)
+        flat = self.engine.get_flat()
+        for name, shp, off, _ in self.engine.specs:
+            w = data[name]
+            assert tuple(w.shape) == tuple(shp), (name, w.shape, shp)
+            flat[off:off + w.size] = w.ravel()
+        self.engine.set_flat(flat)
+
+    def get_weights(self):
+        return self.engine.get_weights(trainable_only=False)
+
+    def set_weights(self, weights):
+        n_tr = len(self.trainable_variables)
+        L = self.config.num_layers
+        bn = [(weights[n_tr + 2 * l], weights[n_tr + 2 * l + 1]) for l in range(L)] if len(weights) > n_tr else None
+        self.engine.set_weights(weights[:n_tr], bn)
+
+
+class RNNPointEstimate(BaseModelClass):
+    """Builds the native recurrent forecaster with the architecture defined in the configs."""
+
+    def __init__(self, config, dataset):
+        self.config = config
+        self.dataset = dataset
+        self.seq_len = self.dataset.seq_len
+        self.n_inputs = self.dataset.n_inputs
+        self.n_outputs = self.dataset.n_outputs
+        self.forecast_steps = self.config.forecast_steps
+        self.n_layers = self.config.num_layers
+        self.n_hidden_units = self.config.num_hidden
+        self.opt = Optimizers(self.config)
+        self.initializer = Initializer(self.config)
+        super(RNNPointEstimate, self).__init__(self.seq_len, self.n_inputs, self.n_outputs)
+        self.model = self._build_model()
+
+    def _build_model(self):
+        return NativeForecaster(self.config, self.seq_len, self.n_inputs, self.n_outputs, self.dataset.target_index)
