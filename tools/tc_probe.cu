@@ -332,6 +332,224 @@ __global__ void __launch_bounds__(128, 1) probe_mufu_kernel(int iters, long long
   sink[threadIdx.x] = s;
 }
 
+// ------------------------------------------------------------------------------------------
+// v2 probes
+// ------------------------------------------------------------------------------------------
+// DSMEM exchange with the bulk-copy engine: every CTA stages its 16 KB slice locally, then ONE thread pushes it
+// to the 3 peers with cp.async.bulk.shared::cluster; arrival is counted in bytes on the receivers' mbarriers.
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1) probe_dsmem_bulk_kernel(int iters,
+                                                                                              long long* cycles,
+                                                                                              int* errors) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint8_t* mine = buf + rank * 16384;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t v = (uint32_t)(it * 131 + rank * 17 + tid * 3 + c);
+      *reinterpret_cast<uint4*>(mine + tid * 128 + c * 16) = make_uint4(v, v + 1, v + 2, v + 3);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, 3 * 16384);
+      for (uint32_t d = 1; d < 4; ++d) {
+        const uint32_t dst = (rank + d) & 3;
+        bulk_copy_s2c(mapa_u32(smem_u32(mine), dst), smem_u32(mine), 16384, mapa_u32(smem_u32(&bar), dst));
+      }
+    }
+    mbar_wait_cluster(&bar, it & 1);
+    if (it == iters - 1) {
+      for (uint32_t src = 0; src < 4; ++src) {
+        const uint32_t got = *reinterpret_cast<uint32_t*>(buf + src * 16384 + tid * 128 + 5 * 16);
+        if (got != (uint32_t)(it * 131 + src * 17 + tid * 3 + 5)) atomicAdd(errors, 1);
+      }
+    }
+    cluster_sync_all();
+  }
+  long long t1 = clock64();
+  if (tid == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// st.shared::cluster with lane-consecutive 16-byte chunks (fully coalesced remote stores)
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1) probe_dsmem_coal_kernel(int iters,
+                                                                                              long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 4 * 128);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    for (uint32_t dst = 0; dst < 4; ++dst) {
+      const uint32_t remote = mapa_u32(smem_u32(buf + rank * 16384), dst);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) st_cluster_v4(remote + (c * 128 + tid) * 16, it, tid, c, dst);
+      mbar_arrive_cluster(mapa_u32(smem_u32(&bar), dst));
+    }
+    mbar_wait_cluster(&bar, it & 1);
+    cluster_sync_all();
+  }
+  long long t1 = clock64();
+  if (tid == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// TMA multicast from global/L2: every CTA of the cluster fetches one 16 KB k-block of a [128 x 256] bf16 tile
+// and multicasts it to all 4 CTAs (64 KB lands in each SM).
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
+    probe_mcast_kernel(int iters, long long* cycles, const __grid_constant__ CUtensorMap tm, int* errors) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x / 4;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, 65536);
+      tma_load_2d_mcast(buf + rank * 16384, &tm, &bar, rank * 64, tile * 128, 0xF);
+    }
+    mbar_wait_cluster(&bar, it & 1);
+    cluster_sync_all();
+  }
+  long long t1 = clock64();
+  if (tid == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  // element (row=tid, k = 64*kb + 0) of the tile is at swizzled chunk (0 ^ (tid&7))
+  for (int kb = 0; kb < 4; ++kb) {
+    const __nv_bfloat16 v = *reinterpret_cast<__nv_bfloat16*>(buf + kb * 16384 + tid * 128 + ((0 ^ (tid & 7)) << 4));
+    const float want = (float)(((tile * 128 + tid) * 7 + (kb * 64) * 3) % 61);
+    if (__bfloat162float(v) != want) atomicAdd(errors, 1);
+  }
+}
+
+// tcgen05.ld variants
+template <int MODE>   // 0: 4 warps, 4 x (x16) per wait ; 1: 8 warps (2 per lane quadrant), 4 x (x16) per wait
+__global__ void __launch_bounds__(256, 1) probe_tmem_ld2_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const int nw = (MODE == 0) ? 4 : 8;
+  const uint32_t tmem = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  float acc = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  if (warp < nw) {
+    const int cbeg = (MODE == 0) ? 0 : (warp >> 2) * 128;
+    const int cend = (MODE == 0) ? 256 : cbeg + 128;
+    for (int it = 0; it < iters; ++it) {
+      for (int c0 = cbeg; c0 < cend; c0 += 64) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x16(tmem + c0 + q * 16, v[q]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc += __uint_as_float(v[q][j] & 0x3fffffffu);
+      }
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  sink[threadIdx.x] = acc;
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 256);
+}
+
+// MMA issue->completion for the per-step gate GEMM: NK x (M128 N256 K16), operands = whatever is in smem.
+__global__ void __launch_bounds__(128, 1) probe_mma_lat_kernel(int nk, int reps, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (64 + 128) * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, 256, false, false);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int k = 0; k < nk; ++k) {
+        const uint32_t kb = (k / 4) % 4, k16 = k % 4;
+        const uint64_t da = make_smem_desc(smem_u32(smem + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+        const uint64_t db = make_smem_desc(smem_u32(smem + 65536 + kb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
+        umma_f16(tmem_base_s + (r & 1) * 256, da, db, idesc, k > 0);
+      }
+      umma_commit(&bar);
+      mbar_wait(&bar, r & 1);
+    }
+    long long t1 = clock64();
+    cycles[0] = t1 - t0;
+    // throughput: issue everything, wait once
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < nk; ++k) {
+        const uint32_t kb = (k / 4) % 4, k16 = k % 4;
+        const uint64_t da = make_smem_desc(smem_u32(smem + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+        const uint64_t db = make_smem_desc(smem_u32(smem + 65536 + kb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
+        umma_f16(tmem_base_s + (r & 1) * 256, da, db, idesc, k > 0);
+      }
+    umma_commit(&bar);
+    mbar_wait(&bar, reps & 1);
+    t1 = clock64();
+    cycles[1] = t1 - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+__global__ void __launch_bounds__(128, 1) probe_mufu2_kernel(int iters, long long* cycles, float* sink) {
+  uint32_t a[8];
+  for (int j = 0; j < 8; ++j) a[j] = pack_bf16x2(0.01f * (threadIdx.x + j), 0.02f * j);
+  const uint32_t q = pack_bf16x2(0.25f, 0.25f), one = pack_bf16x2(1.f, 1.f);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = tanh_bf16x2(fma_bf16x2(a[j], one, q));
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  float s = 0;
+  for (int j = 0; j < 8; ++j) s += bf16_lo(a[j]) + bf16_hi(a[j]);
+  sink[threadIdx.x] = s;
+}
+
 static bool want(int argc, char** argv, const char* name) {
   if (argc <= 1) return true;
   for (int i = 1; i < argc; ++i)
@@ -396,6 +614,81 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
     printf("[mufu] tanh.approx: %.2f per cycle per SM (128 threads, 8-way ILP)\n",
            128.0 * 8 * iters / (double)cy[0]);
+  }
+  if (want(argc, argv, "dsmem_bulk")) {
+    const int iters = 200;
+    CK(cudaMemset(derr, 0, 4));
+    CK(cudaFuncSetAttribute(probe_dsmem_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 + 2048));
+    probe_dsmem_bulk_kernel<<<4 * 32, 128, 4 * 16384 + 2048>>>(iters, dcy, derr);
+    CK(cudaDeviceSynchronize());
+    int herr;
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+    const double per = (double)cy[0] / iters;
+    printf("[dsmem_bulk] round (local 16 KB stage + 3 x 16 KB cp.async.bulk s2c + wait + cluster.sync) = %.0f cyc "
+           "(minus ~406 sync) -> %.1f B/cyc/SM outgoing, errors=%d\n", per, 49152.0 / (per - 406), herr);
+    ok &= (herr == 0);
+  }
+  if (want(argc, argv, "dsmem_coal")) {
+    const int iters = 200;
+    CK(cudaFuncSetAttribute(probe_dsmem_coal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 + 2048));
+    probe_dsmem_coal_kernel<<<4 * 32, 128, 4 * 16384 + 2048>>>(iters, dcy);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    const double per = (double)cy[0] / iters;
+    printf("[dsmem_coal] lane-consecutive st.shared::cluster.v4: round = %.0f cyc -> %.1f B/cyc/SM outgoing\n", per,
+           49152.0 / (per - 406));
+  }
+  if (want(argc, argv, "mcast")) {
+    const int iters = 200, tiles = 32;
+    std::vector<__nv_bfloat16> hh((size_t)tiles * 128 * 256);
+    for (int r = 0; r < tiles * 128; ++r)
+      for (int k = 0; k < 256; ++k) hh[(size_t)r * 256 + k] = __float2bfloat16((float)((r * 7 + k * 3) % 61));
+    __nv_bfloat16* dh;
+    CK(cudaMalloc(&dh, hh.size() * 2));
+    CK(cudaMemcpy(dh, hh.data(), hh.size() * 2, cudaMemcpyHostToDevice));
+    CUtensorMap tm = make_map_2d(dh, 256, tiles * 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    CK(cudaMemset(derr, 0, 4));
+    CK(cudaFuncSetAttribute(probe_mcast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 + 2048));
+    probe_mcast_kernel<<<4 * tiles, 128, 4 * 16384 + 2048>>>(iters, dcy, tm, derr);
+    CK(cudaDeviceSynchronize());
+    int herr;
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+    printf("[mcast] 4 x 16 KB TMA multicast (L2 -> 4 CTAs, 64 KB per SM): round = %.0f cyc (incl ~406 sync), errors=%d\n",
+           (double)cy[0] / iters, herr);
+    ok &= (herr == 0);
+    cudaFree(dh);
+  }
+  if (want(argc, argv, "tmem_ld2")) {
+    const int iters = 200;
+    probe_tmem_ld2_kernel<0><<<148, 256>>>(iters, dcy, dsink);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    printf("[tmem_ld2] 4 warps, 4 x x16 per wait: %.0f cyc per 128x256 tile\n", (double)cy[0] / iters);
+    probe_tmem_ld2_kernel<1><<<148, 256>>>(iters, dcy, dsink);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    printf("[tmem_ld2] 8 warps, 4 x x16 per wait: %.0f cyc per 128x256 tile\n", (double)cy[0] / iters);
+  }
+  if (want(argc, argv, "mma_lat")) {
+    const int reps = 20;
+    CK(cudaFuncSetAttribute(probe_mma_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int nk : {2, 16, 18}) {
+      probe_mma_lat_kernel<<<148, 128, 200 * 1024>>>(nk, reps, dcy);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(cy, dcy, 16, cudaMemcpyDeviceToHost));
+      printf("[mma_lat] %2d x (M128 N256 K16): issue->commit->wait %.0f cyc per batch; back-to-back %.0f cyc per batch "
+             "(%.1f cyc/MMA)\n", nk, (double)cy[0] / reps, (double)cy[1] / reps, (double)cy[1] / reps / nk);
+    }
+  }
+  if (want(argc, argv, "mufu2")) {
+    const int iters = 1000;
+    probe_mufu2_kernel<<<148, 128>>>(iters, dcy, dsink);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(cy, dcy, 8, cudaMemcpyDeviceToHost));
+    printf("[mufu2] tanh.approx.bf16x2 (+1 HFMA2): %.2f instr = %.2f tanh per cycle per SM\n",
+           128.0 * 8 * iters / (double)cy[0], 2 * 128.0 * 8 * iters / (double)cy[0]);
   }
   printf("%s\n", ok ? "PROBE ALL OK" : "PROBE HAD MISMATCHES");
   return ok ? 0 : 1;
