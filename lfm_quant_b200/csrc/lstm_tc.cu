@@ -1,23 +1,829 @@
+// LFMQ_PREC_BF16: the gate GEMMs on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 cell
+// state), everything else as fused HBM-streaming kernels.  sm_100a only.
+//
+// Data layout in HBM (all carved from the caller's workspace, see tc_layout):
+//   xh    bf16 [maxB][T+1][384]   row (b,t): cols 0..255 = h_{t-1} (zero at t=0), 256..287 = x_t, 288 = 1.0 (t<T),
+//                                 rest 0.  One buffer serves: the A operand of the forward recurrence (K-major
+//                                 tiles via TMA), the head (h_t = row t+1) and the weight-gradient GEMM (MN-major).
+//   gates bf16 [maxB][T][4H]      post-activation i|f|g|o, saved for BPTT
+//   cst   f32  [maxB][T][H]       cell states
+//   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
+//   dhout bf16 [maxB][T][H]       dLoss/dh from the head (after BN/dropout backward)
+//
+// Forward recurrence = ONE persistent kernel (lstm_fwd_tc_kernel): clusters of 8 CTAs, CTA r keeps the weight
+// slice of hidden units [32r, 32r+32) (all four gates, 128 gate columns) resident in shared memory for the whole
+// unroll; two independent 128-row batch tiles ("chains") per cluster are in flight so that one chain's
+// tensor-core work hides the other's pointwise tail and h exchange.  h_t is exchanged through global memory
+// (it is an output anyway) and comes back as the next step's A operand via TMA multicast -- measured on B200
+// (profiles/r01_tc_probe.txt) that path moves 64 KB into every SM of a cluster in ~1500 cycles while DSMEM stores
+// or bulk copies manage only 9-13 B/cycle/SM.
 #include "lstm_tc.h"
 
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+#include "sm100.cuh"
+
 namespace lfmq {
-void tc_layout(TcState&, const lfmq_config&, char*, size_t&) {}
-int tc_init(TcState&, const lfmq_config& cfg) {
-  if (cfg.precision == LFMQ_PREC_BF16) {
-    LFMQ_SET_ERR("LFMQ_PREC_BF16 not built yet");
-    return LFMQ_ERR_UNSUPPORTED;
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TC_H = 256;          // hidden units (bf16 path is specialised for H = 256)
+constexpr int TC_NC = 8;           // CTAs per cluster
+constexpr int TC_HS = 32;          // hidden units per CTA
+constexpr int TC_NSL = 128;        // gate columns per CTA
+constexpr int TC_NCH = 2;          // batch chains per cluster
+constexpr int TC_XH_LD = 384;      // elements per xh row
+constexpr int TC_XOFF = 256;       // first x column inside an xh row
+constexpr int TC_ONE = 288;        // the constant-one column (db falls out of the weight-gradient GEMM)
+constexpr int TC_OPAD = 16;        // head handles n_outputs <= 16
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  static PFN_encodeTiled enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    LFMQ_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    enc = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (!enc) {
+      LFMQ_SET_ERR("cuTensorMapEncodeTiled not available");
+      return LFMQ_ERR_CUDA;
+    }
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    LFMQ_SET_ERR("cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu box %u x %u)", (int)r,
+                 (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+    return LFMQ_ERR_CUDA;
   }
   return 0;
 }
-void tc_destroy(TcState&) {}
-int tc_forward(TcState&, const lfmq_config&, const float*, const float*, int, int64_t, int64_t, float*, bool,
-               cudaStream_t) {
-  LFMQ_SET_ERR("LFMQ_PREC_BF16 not built yet");
-  return LFMQ_ERR_UNSUPPORTED;
+
+}  // namespace
+
+struct TcImpl {
+  bool enabled = false;
+  int maxB = 0, T = 0, I = 0, O = 0;
+  // parameter offsets in the flat fp32 vector (L = 1)
+  int64_t oW, oU, ob, ogamma, obeta, oWo, obo, omean, ovar;
+  // workspace
+  __nv_bfloat16 *xh, *gates, *dz, *dhout, *Up, *Wp, *Ub;
+  float *cst, *biasp, *head_part, *wg_part, *dc;
+  size_t head_part_elems, wg_part_elems;
+  CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
+  CUtensorMap tm_dz_k, tm_ub;                  // backward step (K-major)
+  CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
+  int max_clusters = 0;
+  int head_ctas = 0;
+};
+
+// =============================================================================================
+// Small packing / cast kernels
+// =============================================================================================
+// x f32 [B,T,F] -> xh[b][t][256 .. 256+F), plus the constant-one column.
+__global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ x, __nv_bfloat16* __restrict__ xh) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (b,t)
+  if (idx >= (long)B * T) return;
+  const long b = idx / T;
+  const int t = (int)(idx % T);
+  const float* xr = x + idx * F;
+  __nv_bfloat16* dst = xh + (b * (T + 1) + t) * TC_XH_LD + TC_XOFF;
+  for (int f = 0; f < 32; ++f) dst[f] = __float2bfloat16(f < F ? xr[f] : 0.f);
+  dst[TC_ONE - TC_XOFF] = __float2bfloat16(1.0f);
 }
-int tc_backward(TcState&, const lfmq_config&, const float*, float*, const float*, const float*, int, int64_t, int64_t,
-                const float*, float*, cudaStream_t) {
-  LFMQ_SET_ERR("LFMQ_PREC_BF16 not built yet");
+
+// Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 32r+j is row n = 32g+j of
+// slice r; the three sigmoid gates are pre-scaled by 0.5 (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
+__global__ void pack_weights_kernel(int I, const float* __restrict__ W, const float* __restrict__ U,
+                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ Up,
+                                    __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp,
+                                    __nv_bfloat16* __restrict__ Ub) {
+  const int H = TC_H;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (long)4 * H * H) {          // Up: [8][128][256]
+    const int k = (int)(idx % H);
+    const int n = (int)((idx / H) % TC_NSL);
+    const int r = (int)(idx / ((long)H * TC_NSL));
+    const int g = n / TC_HS, j = n % TC_HS;
+    const float sc = (g == 2) ? 1.0f : 0.5f;
+    Up[idx] = __float2bfloat16(sc * U[(long)k * 4 * H + g * H + r * TC_HS + j]);
+    // Ub: plain bf16 copy of U [H][4H] (B operand of the backward recurrence)
+    Ub[idx] = __float2bfloat16(U[idx]);
+  }
+  if (idx < (long)4 * H * 32) {         // Wp: [8][128][32]
+    const int k = (int)(idx % 32);
+    const int n = (int)((idx / 32) % TC_NSL);
+    const int r = (int)(idx / (32 * TC_NSL));
+    const int g = n / TC_HS, j = n % TC_HS;
+    const float sc = (g == 2) ? 1.0f : 0.5f;
+    Wp[idx] = __float2bfloat16(k < I ? sc * W[(long)k * 4 * H + g * H + r * TC_HS + j] : 0.f);
+  }
+  if (idx < 4 * H) {                    // biasp: [8][128]
+    const int n = (int)(idx % TC_NSL), r = (int)(idx / TC_NSL);
+    const int g = n / TC_HS, j = n % TC_HS;
+    biasp[idx] = ((g == 2) ? 1.0f : 0.5f) * bias[g * H + r * TC_HS + j];
+  }
+}
+
+// =============================================================================================
+// Persistent forward recurrence
+// =============================================================================================
+struct FwdParams {
+  int B, T, n_iters, n_clusters, k16_x;
+  __nv_bfloat16* xh;
+  __nv_bfloat16* gates;   // null: do not save
+  float* cst;             // null: do not save
+  const float* biasp;
+};
+
+constexpr int FWD_THREADS = 32 * (3 + 4 * TC_NCH);   // 2 producers + 1 MMA + 8 epilogue warps = 352
+constexpr uint32_t SM_U = 0;
+constexpr uint32_t SM_W = 65536;
+constexpr uint32_t SM_H0 = 73728;            // hbuf[c] = SM_H0 + c * 65536
+constexpr uint32_t SM_X0 = 204800;           // xbuf[c] = SM_X0 + c * 8192
+constexpr uint32_t SM_BIAS = 221184;
+constexpr uint32_t SM_BARS = 221696;
+constexpr uint32_t FWD_SMEM = SM_BARS + 256 + 1024;   // + alignment slack
+
+struct FwdBars {
+  uint64_t w_full;
+  uint64_t x_full[TC_NCH], x_empty[TC_NCH], h_full[TC_NCH], h_written[TC_NCH];
+  uint64_t acc_full[TC_NCH][2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+    lstm_fwd_tc_kernel(FwdParams p, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_x,
+                       const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FwdBars* bars = reinterpret_cast<FwdBars*>(smem + SM_BARS);
+  float* bias_s = reinterpret_cast<float*>(smem + SM_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x / TC_NC;
+
+  if (tid == 0) {
+    mbar_init(&bars->w_full, 1);
+    for (int c = 0; c < TC_NCH; ++c) {
+      mbar_init(&bars->x_full[c], 1);
+      mbar_init(&bars->x_empty[c], 1);
+      mbar_init(&bars->h_full[c], 1);
+      mbar_init(&bars->h_written[c], TC_NC);
+      mbar_init(&bars->acc_full[c][0], 1);
+      mbar_init(&bars->acc_full[c][1], 1);
+    }
+    fence_mbar_init();
+  }
+  if (tid < TC_NSL) bias_s[tid] = p.biasp[rank * TC_NSL + tid];
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peers' barriers are initialised before anyone multicasts / arrives remotely
+  tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const int T = p.T;
+
+  if (warp < TC_NCH) {
+    // ===================== TMA producer of chain `warp` =====================
+    if (lane == 0) {
+      const int c = warp;
+      if (c == 0) {
+        mbar_arrive_expect_tx(&bars->w_full, 65536 + 8192);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SM_U + kb * 16384, &tm_u, &bars->w_full, kb * 64, rank * TC_NSL);
+        tma_load_2d(smem + SM_W, &tm_w, &bars->w_full, 0, rank * TC_NSL);
+      }
+      uint8_t* hbuf = smem + SM_H0 + c * 65536;
+      uint8_t* xbuf = smem + SM_X0 + c * 8192;
+      uint32_t n_hw = 0, n_xe = 0;
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int b0 = ((it * p.n_clusters + cid) * TC_NCH + c) * 128;
+        for (int t = 0; t < T; ++t) {
+          if (it > 0 || t > 0) mbar_wait(&bars->x_empty[c], (n_xe++) & 1);
+          mbar_arrive_expect_tx(&bars->x_full[c], 8192);
+          tma_load_2d(xbuf, &tm_x, &bars->x_full[c], t * TC_XH_LD + TC_XOFF, b0);
+          if (t >= 1) {
+            mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);   // all 8 slices of h_{t-1} are in global memory
+            fence_proxy_async_all();
+            mbar_arrive_expect_tx(&bars->h_full[c], 65536);
+            for (int kb = 0; kb < 4; ++kb)
+              tma_load_2d_mcast(hbuf + kb * 16384 + rank * 2048, &tm_h, &bars->h_full[c], t * TC_XH_LD + kb * 64,
+                                b0 + 16 * (int)rank, 0xFF);
+          }
+        }
+        mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);       // phase of step T-1 (keeps parities aligned)
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, TC_NSL, false, false);
+      mbar_wait(&bars->w_full, 0);
+      uint32_t n_xf[TC_NCH] = {0, 0}, n_hf[TC_NCH] = {0, 0};
+      for (int it = 0; it < p.n_iters; ++it) {
+        for (int t = 0; t < T; ++t) {
+          const uint32_t g = (uint32_t)(it * T + t);
+          for (int c = 0; c < TC_NCH; ++c) {
+            const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
+            mbar_wait(&bars->x_full[c], (n_xf[c]++) & 1);
+            tcgen05_fence_after();
+            for (int k16 = 0; k16 < p.k16_x; ++k16) {
+              const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0 + c * 8192) + k16 * 32, 0, 512, LAYOUT_SW64);
+              const uint64_t db = make_smem_desc(smem_u32(smem + SM_W) + k16 * 32, 0, 512, LAYOUT_SW64);
+              umma_f16(acc, da, db, idesc, k16 > 0);
+            }
+            umma_commit(&bars->x_empty[c]);
+            if (t == 0) umma_commit(&bars->acc_full[c][g & 1]);
+          }
+          if (t > 0) {
+            for (int c = 0; c < TC_NCH; ++c) {
+              const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
+              mbar_wait(&bars->h_full[c], (n_hf[c]++) & 1);
+              tcgen05_fence_after();
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  const uint64_t da = make_smem_desc(smem_u32(smem + SM_H0 + c * 65536 + kb * 16384) + k16 * 32, 0,
+                                                     1024, LAYOUT_SW128);
+                  const uint64_t db =
+                      make_smem_desc(smem_u32(smem + SM_U + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+                  umma_f16(acc, da, db, idesc, 1);
+                }
+              umma_commit(&bars->acc_full[c][g & 1]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: gates, cell update, h exchange =====================
+    const int c = (warp - 3) / 4;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int m = q * 32 + lane;            // row of the 128-row tile
+    const bool leader = ((warp - 3) % 4 == 0) && lane == 0;
+    float cstate[TC_HS];
+    for (int it = 0; it < p.n_iters; ++it) {
+      const long b = (long)((it * p.n_clusters + cid) * TC_NCH + c) * 128 + m;
+      const bool valid = b < p.B;
+#pragma unroll
+      for (int j = 0; j < TC_HS; ++j) cstate[j] = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const uint32_t g = (uint32_t)(it * T + t);
+        mbar_wait(&bars->acc_full[c][g & 1], (g >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 256 + (g & 1) * 128;
+        __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + rank * TC_HS;
+        __nv_bfloat16* grow = p.gates ? p.gates + (b * T + t) * 4 * TC_H + rank * TC_HS : nullptr;
+        float* crow = p.cst ? p.cst + (b * T + t) * TC_H + rank * TC_HS : nullptr;
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) {
+          uint32_t vi[16], vf[16], vg[16], vo[16];
+          tmem_ld_32x32b_x16(taddr + 0 * TC_HS + jb * 16, vi);
+          tmem_ld_32x32b_x16(taddr + 1 * TC_HS + jb * 16, vf);
+          tmem_ld_32x32b_x16(taddr + 2 * TC_HS + jb * 16, vg);
+          tmem_ld_32x32b_x16(taddr + 3 * TC_HS + jb * 16, vo);
+          tmem_ld_wait();
+          uint32_t ph[8], pi[8], pf[8], pg[8], po[8];
+          float cn[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            float hv[2], iv[2], fv[2], gv[2], ov[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = jb * 16 + jj + u;
+              const float gi = fmaf(0.5f, tanh_approx(__uint_as_float(vi[jj + u]) + bias_s[j]), 0.5f);
+              const float gf = fmaf(0.5f, tanh_approx(__uint_as_float(vf[jj + u]) + bias_s[TC_HS + j]), 0.5f);
+              const float gg = tanh_approx(__uint_as_float(vg[jj + u]) + bias_s[2 * TC_HS + j]);
+              const float go = fmaf(0.5f, tanh_approx(__uint_as_float(vo[jj + u]) + bias_s[3 * TC_HS + j]), 0.5f);
+              const float cc = fmaf(gf, cstate[j], gi * gg);
+              cstate[j] = cc;
+              cn[jj + u] = cc;
+              hv[u] = go * tanh_approx(cc);
+              iv[u] = gi; fv[u] = gf; gv[u] = gg; ov[u] = go;
+            }
+            ph[jj / 2] = pack_bf16x2(hv[0], hv[1]);
+            pi[jj / 2] = pack_bf16x2(iv[0], iv[1]);
+            pf[jj / 2] = pack_bf16x2(fv[0], fv[1]);
+            pg[jj / 2] = pack_bf16x2(gv[0], gv[1]);
+            po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
+          }
+          if (valid) {
+            uint4* hd = reinterpret_cast<uint4*>(hrow + jb * 16);
+            hd[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            hd[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            if (grow) {
+              uint4* gd = reinterpret_cast<uint4*>(grow + jb * 16);
+              gd[0] = make_uint4(pi[0], pi[1], pi[2], pi[3]);
+              gd[1] = make_uint4(pi[4], pi[5], pi[6], pi[7]);
+              gd = reinterpret_cast<uint4*>(grow + TC_H + jb * 16);
+              gd[0] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+              gd[1] = make_uint4(pf[4], pf[5], pf[6], pf[7]);
+              gd = reinterpret_cast<uint4*>(grow + 2 * TC_H + jb * 16);
+              gd[0] = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+              gd[1] = make_uint4(pg[4], pg[5], pg[6], pg[7]);
+              gd = reinterpret_cast<uint4*>(grow + 3 * TC_H + jb * 16);
+              gd[0] = make_uint4(po[0], po[1], po[2], po[3]);
+              gd[1] = make_uint4(po[4], po[5], po[6], po[7]);
+            }
+            if (crow) {
+              float4* cd = reinterpret_cast<float4*>(crow + jb * 16);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) cd[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __threadfence();                       // h slice visible at gpu scope ...
+        fence_proxy_async_all();               // ... and to the async proxy (peers read it with TMA)
+        named_bar_sync(1 + c, 128);
+        if (leader) {
+          const uint32_t bar = smem_u32(&bars->h_written[c]);
+#pragma unroll
+          for (uint32_t dst = 0; dst < TC_NC; ++dst) mbar_arrive_cluster(mapa_u32(bar, dst));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();          // nobody leaves while peers may still multicast into / arrive on this CTA
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// Fused head: BN(inference affine) -> Dropout -> Dense -> weighted-MSE loss -> (training) all head gradients
+// and dLoss/dh.  One warp per [b,t] row, H = 256 (8 hidden units per lane), n_outputs <= 16.
+// (models/point_estimate/rnn_point_estimate.py:88-89,105; model_utils/losses.py:55-135)
+// =============================================================================================
+struct HeadParams {
+  int B, T, O, target_idx, train;
+  const __nv_bfloat16* xh;
+  const float *gamma, *beta, *mean, *var;
+  float eps;
+  const float *Wo, *bo;
+  const float* y;
+  const float* denom;
+  float p1, p2;
+  int use_dropout;
+  DropoutKey key;
+  int64_t row0;
+  float* preds;
+  __nv_bfloat16* dhout;
+  float* partial;       // [gridDim.x][HEAD_PART]
+};
+
+constexpr int HEAD_PART = TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 16;   // dWo | dgamma | dbeta | dbo | s0 s1 s2
+constexpr int HEAD_THREADS = 256;
+
+__global__ void __launch_bounds__(HEAD_THREADS, 1) head_fused_kernel(HeadParams p) {
+  __shared__ __align__(16) float Wo_s[TC_H * TC_OPAD];
+  __shared__ float red_s[HEAD_PART];
+  __shared__ __align__(16) float bn_s[4][TC_H];      // gamma*inv | beta - gamma*mean*inv | mean | inv
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < TC_H; j += HEAD_THREADS) {
+    const float iv = 1.0f / sqrtf(p.var[j] + p.eps);
+    bn_s[0][j] = p.gamma[j] * iv;
+    bn_s[1][j] = p.beta[j] - p.gamma[j] * p.mean[j] * iv;
+    bn_s[2][j] = p.mean[j];
+    bn_s[3][j] = iv;
+  }
+  for (int i = tid; i < TC_H * TC_OPAD; i += HEAD_THREADS) {
+    const int j = i / TC_OPAD, k = i % TC_OPAD;
+    Wo_s[i] = (k < p.O) ? p.Wo[j * p.O + k] : 0.f;
+  }
+  for (int i = tid; i < HEAD_PART; i += HEAD_THREADS) red_s[i] = 0.f;
+  __syncthreads();
+
+  const int j0 = lane * 8;
+  // which output this lane owns after the butterfly: lane bit4 -> k bit3, bit3 -> bit2, bit2 -> bit1, bit1 -> bit0
+  const int kown = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  const bool owner = (lane & 1) == 0;
+  const float bo_k = (kown < p.O) ? p.bo[kown] : 0.f;
+  float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
+  if (p.train) {
+    const float Bg = p.denom[0], Mg = p.denom[1];
+    c_all = (1.f - p.p1) * (1.f - p.p2) / ((float)p.O * Mg);
+    c_last = (1.f - p.p1) * p.p2 / (Bg * (float)p.O);
+    c_tar = p.p1 / Bg;
+  }
+  float accW[8][TC_OPAD];
+  float accG[8], accB[8];
+  float accbo = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    accG[i] = 0.f;
+    accB[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) accW[i][k] = 0.f;
+  }
+  const long rows = (long)p.B * p.T;
+  const int nq = TC_H / 4;
+  for (long r = (long)blockIdx.x * (HEAD_THREADS / 32) + warp; r < rows; r += (long)gridDim.x * (HEAD_THREADS / 32)) {
+    const long b = r / p.T;
+    const int t = (int)(r % p.T);
+    const uint4 hraw = *reinterpret_cast<const uint4*>(p.xh + (b * (p.T + 1) + t + 1) * TC_XH_LD + j0);
+    const uint32_t hw[4] = {hraw.x, hraw.y, hraw.z, hraw.w};
+    float hv[8], dm[8], yv[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hv[2 * i] = bf16_lo(hw[i]);
+      hv[2 * i + 1] = bf16_hi(hw[i]);
+    }
+    if (p.use_dropout) {
+      const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + lane * 2;
+      dropout_quad(p.key, qbase, dm);
+      dropout_quad(p.key, qbase + 1, dm + 4);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dm[i] = 1.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yv[i] = fmaf(bn_s[0][j0 + i], hv[i], bn_s[1][j0 + i]) * dm[i];
+    float pr[TC_OPAD];
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) pr[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w = w4[kk];
+        pr[4 * kk + 0] = fmaf(yv[i], w.x, pr[4 * kk + 0]);
+        pr[4 * kk + 1] = fmaf(yv[i], w.y, pr[4 * kk + 1]);
+        pr[4 * kk + 2] = fmaf(yv[i], w.z, pr[4 * kk + 2]);
+        pr[4 * kk + 3] = fmaf(yv[i], w.w, pr[4 * kk + 3]);
+      }
+    }
+    // reduce-scatter butterfly: 16 partial sums over 32 lanes with 8+4+2+1+1 shuffles
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool up = (lane & 16) != 0;
+      const float send = up ? pr[i] : pr[i + 8];
+      const float keep = up ? pr[i + 8] : pr[i];
+      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool up = (lane & 8) != 0;
+      const float send = up ? pr[i] : pr[i + 4];
+      const float keep = up ? pr[i + 4] : pr[i];
+      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool up = (lane & 4) != 0;
+      const float send = up ? pr[i] : pr[i + 2];
+      const float keep = up ? pr[i + 2] : pr[i];
+      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+      const bool up = (lane & 2) != 0;
+      const float send = up ? pr[0] : pr[1];
+      const float keep = up ? pr[1] : pr[0];
+      pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    float pred = pr[0] + __shfl_xor_sync(0xffffffffu, pr[0], 1) + bo_k;
+    if (p.preds && owner && kown < p.O) p.preds[r * p.O + kown] = pred;
+    if (!p.y) continue;
+    const float yt = (kown < p.O) ? p.y[r * p.O + kown] : 0.f;
+    const bool any = __ballot_sync(0xffffffffu, yt != 0.0f) != 0u;      // losses.py:72
+    const float mk = any ? 1.f : 0.f;
+    const float d = (kown < p.O) ? (pred * mk - yt) : 0.f;               // losses.py:75
+    const bool last = (t == p.T - 1);
+    float coef = c_all;
+    if (owner) {
+      const float d2 = d * d;
+      s2 += d2;
+      if (last) {
+        s1 += d2;
+        if (kown == p.target_idx) s0 += d2;
+      }
+    }
+    if (!p.train) continue;
+    if (last) coef += c_last + ((kown == p.target_idx) ? c_tar : 0.f);
+    const float dp_own = 2.f * d * coef * mk;
+    if (owner) accbo += dp_own;
+    float dp[TC_OPAD];
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) {
+      const int src = ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2;
+      dp[k] = __shfl_sync(0xffffffffu, dp_own, src);
+    }
+    float dyv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
+      float s = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w = w4[kk];
+        s = fmaf(dp[4 * kk + 0], w.x, s);
+        s = fmaf(dp[4 * kk + 1], w.y, s);
+        s = fmaf(dp[4 * kk + 2], w.z, s);
+        s = fmaf(dp[4 * kk + 3], w.w, s);
+        accW[i][4 * kk + 0] = fmaf(yv[i], dp[4 * kk + 0], accW[i][4 * kk + 0]);
+        accW[i][4 * kk + 1] = fmaf(yv[i], dp[4 * kk + 1], accW[i][4 * kk + 1]);
+        accW[i][4 * kk + 2] = fmaf(yv[i], dp[4 * kk + 2], accW[i][4 * kk + 2]);
+        accW[i][4 * kk + 3] = fmaf(yv[i], dp[4 * kk + 3], accW[i][4 * kk + 3]);
+      }
+      const float dd = s * dm[i];                       // through Dropout
+      accG[i] = fmaf(dd, (hv[i] - bn_s[2][j0 + i]) * bn_s[3][j0 + i], accG[i]);
+      accB[i] += dd;
+      dyv[i] = dd * bn_s[0][j0 + i];                    // through BN -> dLoss/dh
+    }
+    uint4 o;
+    o.x = pack_bf16x2(dyv[0], dyv[1]);
+    o.y = pack_bf16x2(dyv[2], dyv[3]);
+    o.z = pack_bf16x2(dyv[4], dyv[5]);
+    o.w = pack_bf16x2(dyv[6], dyv[7]);
+    *reinterpret_cast<uint4*>(p.dhout + r * TC_H + j0) = o;
+  }
+  // CTA-level reduction of the per-warp accumulators (shared atomics: 8 warps, short)
+  if (p.y) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) atomicAdd(&red_s[(j0 + i) * TC_OPAD + k], accW[i][k]);
+      atomicAdd(&red_s[TC_H * TC_OPAD + j0 + i], accG[i]);
+      atomicAdd(&red_s[TC_H * TC_OPAD + TC_H + j0 + i], accB[i]);
+    }
+    if (owner) {
+      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + kown], accbo);
+      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 0], s0);
+      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 1], s1);
+      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 2], s2);
+    }
+    __syncthreads();
+    for (int i = tid; i < HEAD_PART; i += HEAD_THREADS) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
+  }
+}
+
+// Sums the per-CTA head partials in a fixed order and scatters them into the flat gradient vector / loss tail.
+__global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial, int O, int B, const float* denom,
+                                   float p1, float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
+                                   float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HEAD_PART) return;
+  double s = 0.0;
+  for (int c = 0; c < n_cta; ++c) s += partial[(long)c * HEAD_PART + i];
+  if (i < TC_H * TC_OPAD) {
+    const int j = i / TC_OPAD, k = i % TC_OPAD;
+    if (train && k < O) gWo[j * O + k] = (float)s;
+  } else if (i < TC_H * TC_OPAD + TC_H) {
+    if (train) ggamma[i - TC_H * TC_OPAD] = (float)s;
+  } else if (i < TC_H * TC_OPAD + 2 * TC_H) {
+    if (train) gbeta[i - TC_H * TC_OPAD - TC_H] = (float)s;
+  } else if (i < TC_H * TC_OPAD + 2 * TC_H + TC_OPAD) {
+    const int k = i - TC_H * TC_OPAD - 2 * TC_H;
+    if (train && k < O) gbo[k] = (float)s;
+  } else if (i == TC_H * TC_OPAD + 2 * TC_H + TC_OPAD) {
+    // the three loss sums live in consecutive slots; one thread finishes the loss (losses.py:87-98)
+    double s0 = s, s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < n_cta; ++c) {
+      s1 += partial[(long)c * HEAD_PART + i + 1];
+      s2 += partial[(long)c * HEAD_PART + i + 2];
+    }
+    const double Bg = denom[0], Mg = denom[1];
+    const double mse0 = s0 / Bg, mse1 = s1 / (Bg * O), mse2 = s2 / (Mg * O);
+    out2[0] = (float)(p1 * mse0 + (1.0 - p1) * (p2 * mse1 + (1.0 - p2) * mse2));
+    out2[1] = (float)mse0;
+  }
+}
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+static bool tc_supported(const lfmq_config& c, char* why, size_t n) {
+  if (c.num_hidden != TC_H) { snprintf(why, n, "num_hidden must be 256 (got %d)", c.num_hidden); return false; }
+  if (c.num_layers != 1) { snprintf(why, n, "num_layers must be 1 (got %d)", c.num_layers); return false; }
+  if (c.n_inputs > 32) { snprintf(why, n, "n_inputs must be <= 32 (got %d)", c.n_inputs); return false; }
+  if (c.n_outputs > TC_OPAD) { snprintf(why, n, "n_outputs must be <= 16 (got %d)", c.n_outputs); return false; }
+  if (c.recurrent_dropout > 0.f) { snprintf(why, n, "recurrent_dropout is not built on the bf16 path"); return false; }
+  return true;
+}
+
+void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
+  if (c.precision != LFMQ_PREC_BF16) return;
+  char why[128];
+  if (!tc_supported(c, why, sizeof(why))) return;   // tc_init reports the error
+  if (!st.impl) st.impl = new TcImpl;
+  TcImpl& m = *st.impl;
+  auto take = [&](size_t bytes) -> char* {
+    char* p = base ? base + off : nullptr;
+    off = (off + bytes + 1023) / 1024 * 1024;
+    return p;
+  };
+  const size_t B = (size_t)c.max_batch, T = (size_t)c.seq_len, H = TC_H;
+  m.maxB = c.max_batch; m.T = c.seq_len; m.I = c.n_inputs; m.O = c.n_outputs;
+  m.xh = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * TC_XH_LD * 2));
+  m.Up = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
+  m.Wp = reinterpret_cast<__nv_bfloat16*>(take(4 * H * 32 * 2));
+  m.Ub = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
+  m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
+  m.head_ctas = 148;
+  m.head_part_elems = (size_t)m.head_ctas * HEAD_PART;
+  m.head_part = reinterpret_cast<float*>(take(m.head_part_elems * 4));
+  if (!c.forward_only) {
+    m.gates = reinterpret_cast<__nv_bfloat16*>(take(B * T * 4 * H * 2));
+    m.cst = reinterpret_cast<float*>(take(B * T * H * 4));
+    m.dz = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * 4 * H * 2));
+    m.dhout = reinterpret_cast<__nv_bfloat16*>(take(B * T * H * 2));
+    m.dc = reinterpret_cast<float*>(take(B * H * 4));
+    m.wg_part_elems = (size_t)64 * 384 * 1024;
+    m.wg_part = reinterpret_cast<float*>(take(m.wg_part_elems * 4));
+  } else {
+    m.gates = nullptr; m.cst = nullptr; m.dz = nullptr; m.dhout = nullptr; m.dc = nullptr; m.wg_part = nullptr;
+    m.wg_part_elems = 0;
+  }
+  const int64_t I = c.n_inputs, O = c.n_outputs;
+  m.oW = 0; m.oU = I * 4 * H; m.ob = m.oU + H * 4 * H; m.ogamma = m.ob + 4 * H; m.obeta = m.ogamma + H;
+  m.oWo = m.obeta + H; m.obo = m.oWo + H * O; m.omean = m.obo + O; m.ovar = m.omean + H;
+}
+
+int tc_init(TcState& st, const lfmq_config& c) {
+  if (c.precision != LFMQ_PREC_BF16) return 0;
+  char why[128];
+  if (!tc_supported(c, why, sizeof(why))) {
+    LFMQ_SET_ERR("LFMQ_PREC_BF16 supports the H=256 single-layer forecaster only: %s; use LFMQ_PREC_FP32", why);
+    return LFMQ_ERR_UNSUPPORTED;
+  }
+  TcImpl& m = *st.impl;
+  const size_t B = (size_t)m.maxB, T = (size_t)m.T;
+  LFMQ_CUDA_CHECK(cudaMemset(m.xh, 0, B * (T + 1) * TC_XH_LD * 2));
+  if (m.dz) LFMQ_CUDA_CHECK(cudaMemset(m.dz, 0, B * (T + 1) * 4 * TC_H * 2));
+  const uint64_t xh_row = (uint64_t)(T + 1) * TC_XH_LD;     // elements per batch row of the 2-D view
+  int rc;
+  if ((rc = make_map_2d(&m.tm_h, m.xh, xh_row, B, xh_row * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  // how many 8-CTA clusters can be co-resident (one CTA per SM because of shared memory)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TC_NC * 18);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = FWD_SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TC_NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nclusters, lstm_fwd_tc_kernel, &cfg));
+  if (nclusters < 1) {
+    LFMQ_SET_ERR("no 8-CTA cluster of the forward kernel fits on this device");
+    return LFMQ_ERR_UNSUPPORTED;
+  }
+  m.max_clusters = nclusters;
+  m.enabled = true;
+  st.weights_dirty = 1;
+  return 0;
+}
+
+void tc_destroy(TcState& st) {
+  delete st.impl;
+  st.impl = nullptr;
+}
+
+static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
+  TcImpl& m = *st.impl;
+  if (!st.weights_dirty) return 0;
+  const long n = (long)4 * TC_H * TC_H;
+  pack_weights_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(m.I, params + m.oW, params + m.oU, params + m.ob, m.Up,
+                                                           m.Wp, m.biasp, m.Ub);
+  LFMQ_LAUNCH_CHECK();
+  st.weights_dirty = 0;
+  return 0;
+}
+
+static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cudaStream_t s) {
+  TcImpl& m = *st.impl;
+  const long bt = (long)B * m.T;
+  xh_fill_x_kernel<<<(int)((bt + 255) / 256), 256, 0, s>>>(B, m.T, m.I, x, m.xh);
+  LFMQ_LAUNCH_CHECK();
+  const int n_tiles = (B + 127) / 128;
+  const int n_pairs = (n_tiles + TC_NCH - 1) / TC_NCH;
+  FwdParams p;
+  p.B = B; p.T = m.T;
+  p.n_clusters = n_pairs < m.max_clusters ? n_pairs : m.max_clusters;
+  p.n_iters = (n_pairs + p.n_clusters - 1) / p.n_clusters;
+  p.k16_x = (m.I + 15) / 16;
+  p.xh = m.xh;
+  p.gates = save ? m.gates : nullptr;
+  p.cst = save ? m.cst : nullptr;
+  p.biasp = m.biasp;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TC_NC * p.n_clusters);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = FWD_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TC_NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
+  g_launches++;
+  return 0;
+}
+
+static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, float* grads, const float* y, int B,
+                       int64_t row0, int64_t step, const float* denom, float* preds, float* out2, bool train,
+                       cudaStream_t s) {
+  TcImpl& m = *st.impl;
+  HeadParams h;
+  h.B = B; h.T = m.T; h.O = m.O; h.target_idx = c.target_idx; h.train = train ? 1 : 0;
+  h.xh = m.xh;
+  h.gamma = params + m.ogamma; h.beta = params + m.obeta; h.mean = params + m.omean; h.var = params + m.ovar;
+  h.eps = c.bn_epsilon;
+  h.Wo = params + m.oWo; h.bo = params + m.obo;
+  h.y = y; h.denom = denom; h.p1 = c.target_lambda; h.p2 = c.rnn_lambda;
+  h.use_dropout = (c.train && c.dropout > 0.f) ? 1 : 0;
+  h.key.k0 = (uint32_t)(c.seed & 0xffffffffu);
+  h.key.k1 = (uint32_t)(c.seed >> 32);
+  h.key.stream = 0;
+  h.key.step = (uint32_t)(step & 0xffffffff);
+  h.key.thr = (uint32_t)((double)c.dropout * 16777216.0);
+  h.key.scale = 1.0f / (1.0f - c.dropout);
+  h.row0 = row0;
+  h.preds = preds;
+  h.dhout = train ? m.dhout : nullptr;
+  h.partial = m.head_part;
+  head_fused_kernel<<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
+  LFMQ_LAUNCH_CHECK();
+  if (y) {
+    head_reduce_kernel<<<(HEAD_PART + 255) / 256, 256, 0, s>>>(
+        m.head_ctas, m.head_part, m.O, B, denom, c.target_lambda, c.rnn_lambda, train ? 1 : 0,
+        grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr, grads ? grads + m.ogamma : nullptr,
+        grads ? grads + m.obeta : nullptr, out2);
+    LFMQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int tc_forward(TcState& st, const lfmq_config& c, const float* params, const float* x, int B, int64_t row0,
+               int64_t step, float* preds, bool save, cudaStream_t s) {
+  if (!st.impl || !st.impl->enabled) {
+    LFMQ_SET_ERR("bf16 path not initialised");
+    return LFMQ_ERR_UNSUPPORTED;
+  }
+  int rc;
+  if ((rc = tc_pack_weights(st, params, s))) return rc;
+  st.prof->begin(LFMQ_REGION_FWD, s);
+  if ((rc = tc_run_recurrence(st, x, B, save, s))) return rc;
+  st.prof->end(LFMQ_REGION_FWD, s);
+  if (preds) {
+    st.prof->begin(LFMQ_REGION_HEAD, s);
+    if ((rc = tc_run_head(st, c, params, nullptr, nullptr, B, row0, step, nullptr, preds, nullptr, false, s))) return rc;
+    st.prof->end(LFMQ_REGION_HEAD, s);
+  }
+  return 0;
+}
+
+int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, cudaStream_t s);
+
+int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* grads, const float* x, const float* y,
+                int B, int64_t row0, int64_t step, const float* denom, float* tail, cudaStream_t s) {
+  if (!st.impl || !st.impl->enabled) {
+    LFMQ_SET_ERR("bf16 path not initialised");
+    return LFMQ_ERR_UNSUPPORTED;
+  }
+  int rc;
+  if ((rc = tc_pack_weights(st, params, s))) return rc;
+  st.prof->begin(LFMQ_REGION_FWD, s);
+  if ((rc = tc_run_recurrence(st, x, B, true, s))) return rc;
+  st.prof->end(LFMQ_REGION_FWD, s);
+  st.prof->begin(LFMQ_REGION_HEAD, s);
+  if ((rc = tc_run_head(st, c, params, grads, y, B, row0, step, denom, nullptr, tail, true, s))) return rc;
+  st.prof->end(LFMQ_REGION_HEAD, s);
+  return tc_backward_impl(st, c, params, grads, B, s);
+}
+
+}  // namespace lfmq
+
+namespace lfmq {
+// TEMPORARY until the backward kernels land
+int tc_backward_impl(TcState&, const lfmq_config&, const float*, float*, int, cudaStream_t) {
+  LFMQ_SET_ERR("bf16 backward not built yet");
   return LFMQ_ERR_UNSUPPORTED;
 }
 }  // namespace lfmq

@@ -1,9 +1,12 @@
-// bf16 tensor-core path (LFMQ_PREC_BF16): persistent tcgen05 LSTM kernels + fused head.  See lstm_tc.cu.
+// bf16 tensor-core path (LFMQ_PREC_BF16): persistent tcgen05 LSTM forward, per-step tcgen05 backward, tcgen05
+// weight-gradient GEMM and the fused HBM-bound head.  See lstm_tc.cu / DESIGN.md.
 #pragma once
 #include "../../include/lfmq.h"
 #include "common.cuh"
 
 namespace lfmq {
+
+struct TcImpl;
 
 struct TcState {
   // bookkeeping shared with the fp32 path
@@ -11,14 +14,14 @@ struct TcState {
   int64_t last_row0 = 0;
   int weights_dirty = 1;
   Profiler* prof = nullptr;
-  // bf16-path workspace (carved by tc_layout) and launch state; opaque to lfmq_api.cu
-  void* impl = nullptr;
+  TcImpl* impl = nullptr;
 };
 
 // Extends the workspace carve (base may be null when only sizing); `off` is advanced.
 void tc_layout(TcState& st, const lfmq_config& cfg, char* base, size_t& off);
 int tc_init(TcState& st, const lfmq_config& cfg);
 void tc_destroy(TcState& st);
+// preds may be null (training: the head is fused with the loss in tc_backward)
 int tc_forward(TcState& st, const lfmq_config& cfg, const float* params, const float* x, int B, int64_t row0,
                int64_t step, float* preds, bool save, cudaStream_t s);
 int tc_backward(TcState& st, const lfmq_config& cfg, const float* params, float* grads, const float* x,
