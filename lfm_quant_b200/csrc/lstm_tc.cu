@@ -672,6 +672,11 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if (m.dz) {
+    const uint64_t dz_row = (uint64_t)(T + 1) * 4 * TC_H;
+    if ((rc = make_map_2d(&m.tm_dz_k, m.dz, dz_row, B, dz_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&m.tm_ub, m.Ub, 4 * TC_H, TC_H, 4 * TC_H * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   // how many 8-CTA clusters can be co-resident (one CTA per SM because of shared memory)
   cudaLaunchConfig_t cfg = {};
@@ -820,10 +825,353 @@ int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* g
 
 }  // namespace lfmq
 
+// =============================================================================================
+// Backward recurrence, one launch per time step (reverse t):
+//   dh_rec[128 x 64] = dz_{t+1}[128 x 1024] * U[64 slice][1024]^T      tcgen05, TMA ring over K
+//   dz_t = gate-gradient(dh_out_t + dh_rec, saved gates, c_t, c_{t-1}, dc)   fused epilogue
+// grid = (H/64, row tiles).  A = dz rows of step t+1 (K-major, the [B, T+1, 4H] buffer), B = bf16 copy of U.
+// =============================================================================================
 namespace lfmq {
-// TEMPORARY until the backward kernels land
-int tc_backward_impl(TcState&, const lfmq_config&, const float*, float*, int, cudaStream_t) {
-  LFMQ_SET_ERR("bf16 backward not built yet");
-  return LFMQ_ERR_UNSUPPORTED;
+
+struct BwdStepParams {
+  int B, T, t;
+  const __nv_bfloat16* gates;
+  const float* cst;
+  const __nv_bfloat16* dhout;
+  float* dc;
+  __nv_bfloat16* dz;
+};
+
+constexpr int BWD_THREADS = 192;
+constexpr int BWD_STAGES = 6;
+constexpr uint32_t BWD_STAGE_BYTES = 16384 + 8192;
+constexpr uint32_t BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+    lstm_bwd_step_tc_kernel(BwdStepParams p, const __grid_constant__ CUtensorMap tm_dz,
+                            const __grid_constant__ CUtensorMap tm_ub) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + BWD_STAGES * BWD_STAGE_BYTES);
+  uint64_t* empty = full + BWD_STAGES;
+  uint64_t* acc_full = empty + BWD_STAGES;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * 64;            // hidden slice
+  const int b0 = blockIdx.y * 128;
+  const bool has_gemm = p.t < p.T - 1;
+  constexpr int NKB = 4 * TC_H / 64;         // 16 k-blocks over the 1024 gate columns
+
+  if (tid == 0) {
+    for (int s = 0; s < BWD_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, 64);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0 && has_gemm) {
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb % BWD_STAGES;
+        if (kb >= BWD_STAGES) mbar_wait(&empty[s], ((kb / BWD_STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&full[s], BWD_STAGE_BYTES);
+        tma_load_2d(smem + s * BWD_STAGE_BYTES, &tm_dz, &full[s], (p.t + 1) * 4 * TC_H + kb * 64, b0);
+        tma_load_2d(smem + s * BWD_STAGE_BYTES + 16384, &tm_ub, &full[s], kb * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_gemm) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb % BWD_STAGES;
+        mbar_wait(&full[s], (kb / BWD_STAGES) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint64_t da = make_smem_desc(smem_u32(smem + s * BWD_STAGE_BYTES) + k16 * 32, 0, 1024, LAYOUT_SW128);
+          const uint64_t db =
+              make_smem_desc(smem_u32(smem + s * BWD_STAGE_BYTES + 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+          umma_f16(tmem, da, db, idesc, (kb | k16) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const long b = (long)b0 + m;
+    const bool valid = b < p.B;
+    if (has_gemm) {
+      mbar_wait(acc_full, 0);
+      tcgen05_fence_after();
+    }
+    const long rt = b * p.T + p.t;                       // row index in [B,T,*] buffers
+    const __nv_bfloat16* grow = p.gates + rt * 4 * TC_H + n0;
+    const float* crow = p.cst + rt * TC_H + n0;
+    const __nv_bfloat16* dhrow = p.dhout + rt * TC_H + n0;
+    float* dcrow = p.dc + b * TC_H + n0;
+    __nv_bfloat16* dzrow = p.dz + (b * (p.T + 1) + p.t) * 4 * TC_H + n0;
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+      uint32_t vr[16];
+      if (has_gemm) {
+        tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + jb * 16, vr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vr[j] = 0u;
+      }
+      if (!valid) continue;
+      uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
+      {
+        const uint4* s4 = reinterpret_cast<const uint4*>(grow + jb * 16);
+        uint4 a = s4[0], bq = s4[1];
+        gi[0] = a.x; gi[1] = a.y; gi[2] = a.z; gi[3] = a.w; gi[4] = bq.x; gi[5] = bq.y; gi[6] = bq.z; gi[7] = bq.w;
+        s4 = reinterpret_cast<const uint4*>(grow + TC_H + jb * 16);
+        a = s4[0]; bq = s4[1];
+        gf[0] = a.x; gf[1] = a.y; gf[2] = a.z; gf[3] = a.w; gf[4] = bq.x; gf[5] = bq.y; gf[6] = bq.z; gf[7] = bq.w;
+        s4 = reinterpret_cast<const uint4*>(grow + 2 * TC_H + jb * 16);
+        a = s4[0]; bq = s4[1];
+        gg[0] = a.x; gg[1] = a.y; gg[2] = a.z; gg[3] = a.w; gg[4] = bq.x; gg[5] = bq.y; gg[6] = bq.z; gg[7] = bq.w;
+        s4 = reinterpret_cast<const uint4*>(grow + 3 * TC_H + jb * 16);
+        a = s4[0]; bq = s4[1];
+        go[0] = a.x; go[1] = a.y; go[2] = a.z; go[3] = a.w; go[4] = bq.x; go[5] = bq.y; go[6] = bq.z; go[7] = bq.w;
+        s4 = reinterpret_cast<const uint4*>(dhrow + jb * 16);
+        a = s4[0]; bq = s4[1];
+        dhp[0] = a.x; dhp[1] = a.y; dhp[2] = a.z; dhp[3] = a.w; dhp[4] = bq.x; dhp[5] = bq.y; dhp[6] = bq.z;
+        dhp[7] = bq.w;
+      }
+      float ct[16], cp[16], dcv[16];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 c4 = reinterpret_cast<const float4*>(crow + jb * 16)[v];
+        ct[4 * v] = c4.x; ct[4 * v + 1] = c4.y; ct[4 * v + 2] = c4.z; ct[4 * v + 3] = c4.w;
+        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.t > 0) p4 = reinterpret_cast<const float4*>(crow - TC_H + jb * 16)[v];
+        cp[4 * v] = p4.x; cp[4 * v + 1] = p4.y; cp[4 * v + 2] = p4.z; cp[4 * v + 3] = p4.w;
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_gemm) d4 = reinterpret_cast<const float4*>(dcrow + jb * 16)[v];
+        dcv[4 * v] = d4.x; dcv[4 * v + 1] = d4.y; dcv[4 * v + 2] = d4.z; dcv[4 * v + 3] = d4.w;
+      }
+      uint32_t zi[8], zf[8], zg[8], zo[8];
+      float dcn_out[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; jj += 2) {
+        float ri[2], rf[2], rg[2], ro[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = jj + u;
+          const float i_ = u ? bf16_hi(gi[jj / 2]) : bf16_lo(gi[jj / 2]);
+          const float f_ = u ? bf16_hi(gf[jj / 2]) : bf16_lo(gf[jj / 2]);
+          const float g_ = u ? bf16_hi(gg[jj / 2]) : bf16_lo(gg[jj / 2]);
+          const float o_ = u ? bf16_hi(go[jj / 2]) : bf16_lo(go[jj / 2]);
+          const float dh = (u ? bf16_hi(dhp[jj / 2]) : bf16_lo(dhp[jj / 2])) + __uint_as_float(vr[j]);
+          const float tc = tanh_approx(ct[j]);
+          const float d_o = dh * tc;
+          const float dcn = dcv[j] + dh * o_ * (1.f - tc * tc);
+          ri[u] = dcn * g_ * i_ * (1.f - i_);
+          rf[u] = dcn * cp[j] * f_ * (1.f - f_);
+          rg[u] = dcn * i_ * (1.f - g_ * g_);
+          ro[u] = d_o * o_ * (1.f - o_);
+          dcn_out[j] = dcn * f_;
+        }
+        zi[jj / 2] = pack_bf16x2(ri[0], ri[1]);
+        zf[jj / 2] = pack_bf16x2(rf[0], rf[1]);
+        zg[jj / 2] = pack_bf16x2(rg[0], rg[1]);
+        zo[jj / 2] = pack_bf16x2(ro[0], ro[1]);
+      }
+      uint4* d4 = reinterpret_cast<uint4*>(dzrow + jb * 16);
+      d4[0] = make_uint4(zi[0], zi[1], zi[2], zi[3]);
+      d4[1] = make_uint4(zi[4], zi[5], zi[6], zi[7]);
+      d4 = reinterpret_cast<uint4*>(dzrow + TC_H + jb * 16);
+      d4[0] = make_uint4(zf[0], zf[1], zf[2], zf[3]);
+      d4[1] = make_uint4(zf[4], zf[5], zf[6], zf[7]);
+      d4 = reinterpret_cast<uint4*>(dzrow + 2 * TC_H + jb * 16);
+      d4[0] = make_uint4(zg[0], zg[1], zg[2], zg[3]);
+      d4[1] = make_uint4(zg[4], zg[5], zg[6], zg[7]);
+      d4 = reinterpret_cast<uint4*>(dzrow + 3 * TC_H + jb * 16);
+      d4[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+      d4[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        reinterpret_cast<float4*>(dcrow + jb * 16)[v] =
+            make_float4(dcn_out[4 * v], dcn_out[4 * v + 1], dcn_out[4 * v + 2], dcn_out[4 * v + 3]);
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 64);
 }
+
+// =============================================================================================
+// Weight gradients as ONE tcgen05 GEMM over all B*(T+1) rows:  D[384 x 1024] = xh^T * dz   (both MN-major)
+//   rows 0..255 -> dU, rows 256..256+I-1 -> dW, row 288 (the constant-one column) -> db.
+// grid = (3 M-tiles, 4 N-tiles, S K-splits); deterministic split-K through fp32 partials.
+// =============================================================================================
+struct WgradParams {
+  int n_kblocks;        // ceil(rows / 64)
+  int kb_per_split;
+  float* partial;       // [S][384][1024]
+};
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGES = 4;
+constexpr uint32_t WG_STAGE_BYTES = 16384 + 32768;
+constexpr uint32_t WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    wgrad_tc_kernel(WgradParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* acc_full = empty + WG_STAGES;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
+  const int kb_beg = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
+  const int nkb = max(0, kb_end - kb_beg);
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_s, 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        if (i >= WG_STAGES) mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&full[s], WG_STAGE_BYTES);
+        uint8_t* st = smem + s * WG_STAGE_BYTES;
+        const int krow = (kb_beg + i) * 64;
+        for (int mb = 0; mb < 2; ++mb) tma_load_2d(st + mb * 8192, &tm_a, &full[s], m0 + mb * 64, krow);
+        for (int nb = 0; nb < 4; ++nb) tma_load_2d(st + 16384 + nb * 8192, &tm_b, &full[s], n0 + nb * 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256, true, true);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        mbar_wait(&full[s], (i / WG_STAGES) & 1);
+        tcgen05_fence_after();
+        uint8_t* st = smem + s * WG_STAGE_BYTES;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint64_t da = make_smem_desc(smem_u32(st) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
+          const uint64_t db = make_smem_desc(smem_u32(st + 16384) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
+          umma_f16(tmem, da, db, idesc, (i | k16) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    float* out = p.partial + ((long)blockIdx.z * 384 + m0 + m) * 1024 + n0;
+    if (nkb > 0) {
+      mbar_wait(acc_full, 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    } else {
+      for (int c0 = 0; c0 < 256; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// Sums the K-split partials and scatters D rows into dU / dW / db of the flat gradient vector.
+__global__ void wgrad_reduce_kernel(int S, int I, const float* __restrict__ partial, float* __restrict__ gU,
+                                    float* __restrict__ gW, float* __restrict__ gb) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)384 * 1024) return;
+  const int row = (int)(idx / 1024), n = (int)(idx % 1024);
+  float* dst = nullptr;
+  if (row < TC_H) dst = gU + (long)row * 1024 + n;
+  else if (row < TC_H + I) dst = gW + (long)(row - TC_H) * 1024 + n;
+  else if (row == TC_ONE) dst = gb + n;
+  if (!dst) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[(long)z * 384 * 1024 + idx];
+  *dst = s;
+}
+
+int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, cudaStream_t s) {
+  TcImpl& m = *st.impl;
+  static bool attrs_set = false;
+  if (!attrs_set) {
+    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    attrs_set = true;
+  }
+  const size_t T = (size_t)m.T;
+  int rc;
+  st.prof->begin(LFMQ_REGION_BWD, s);
+  BwdStepParams bp;
+  bp.B = B; bp.T = m.T; bp.gates = m.gates; bp.cst = m.cst; bp.dhout = m.dhout; bp.dc = m.dc; bp.dz = m.dz;
+  const dim3 bgrid(TC_H / 64, (B + 127) / 128);
+  for (int t = m.T - 1; t >= 0; --t) {
+    bp.t = t;
+    lstm_bwd_step_tc_kernel<<<bgrid, BWD_THREADS, BWD_SMEM, s>>>(bp, m.tm_dz_k, m.tm_ub);
+    LFMQ_LAUNCH_CHECK();
+  }
+  st.prof->end(LFMQ_REGION_BWD, s);
+
+  st.prof->begin(LFMQ_REGION_WGRAD, s);
+  // MN-major maps over exactly the B*(T+1) rows of this call (rows beyond are zero-filled by TMA)
+  const uint64_t rows = (uint64_t)B * (T + 1);
+  CUtensorMap tm_a, tm_b;
+  if ((rc = make_map_2d(&tm_a, m.xh, TC_XH_LD, rows, TC_XH_LD * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&tm_b, m.dz, 4 * TC_H, rows, 4 * TC_H * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  WgradParams wp;
+  wp.n_kblocks = (int)((rows + 63) / 64);
+  int S = 12;
+  if (wp.n_kblocks < S) S = wp.n_kblocks;
+  wp.kb_per_split = (wp.n_kblocks + S - 1) / S;
+  S = (wp.n_kblocks + wp.kb_per_split - 1) / wp.kb_per_split;
+  wp.partial = m.wg_part;
+  wgrad_tc_kernel<<<dim3(3, 4, S), WG_THREADS, WG_SMEM, s>>>(wp, tm_a, tm_b);
+  LFMQ_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<(384 * 1024 + 255) / 256, 256, 0, s>>>(S, m.I, m.wg_part, grads + m.oU, grads + m.oW,
+                                                              grads + m.ob);
+  LFMQ_LAUNCH_CHECK();
+  st.prof->end(LFMQ_REGION_WGRAD, s);
+  (void)params;
+  (void)c;
+  return 0;
+}
+
 }  // namespace lfmq
