@@ -21,6 +21,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "sm100.cuh"
@@ -82,13 +83,13 @@ struct TcImpl {
   int64_t oW, oU, ob, ogamma, obeta, oWo, obo, omean, ovar;
   // workspace
   __nv_bfloat16 *xh, *gates, *dz, *dhout, *Up, *Wp, *Ub;
-  float *cst, *biasp, *head_part, *wg_part, *dc;
+  float *cst, *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
   CUtensorMap tm_dz_k, tm_ub;                  // backward step (K-major)
   CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
   int max_clusters = 0;
-  int head_ctas = 0;
+  int head_ctas = 0, head_wctas = 0;
 };
 
 // =============================================================================================
@@ -148,7 +149,13 @@ struct FwdParams {
   __nv_bfloat16* gates;   // null: do not save
   float* cst;             // null: do not save
   const float* biasp;
+  long long* trace;       // debug (LFMQ_TRACE_FWD=1): clock64 stamps of CTA 0, chain 0, first 16 steps
 };
+
+#define FWD_TRACE(role, t, pt)                                                        \
+  do {                                                                                \
+    if (p.trace && blockIdx.x == 0 && (t) < 16) p.trace[((role) * 16 + (t)) * 8 + (pt)] = clock64(); \
+  } while (0)
 
 constexpr int FWD_THREADS = 32 * (3 + 4 * TC_NCH);   // 2 producers + 1 MMA + 8 epilogue warps = 352
 constexpr uint32_t SM_U = 0;
@@ -214,15 +221,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         const int b0 = ((it * p.n_clusters + cid) * TC_NCH + c) * 128;
         for (int t = 0; t < T; ++t) {
           if (it > 0 || t > 0) mbar_wait(&bars->x_empty[c], (n_xe++) & 1);
+          if (c == 0) FWD_TRACE(0, t, 0);
           mbar_arrive_expect_tx(&bars->x_full[c], 8192);
           tma_load_2d(xbuf, &tm_x, &bars->x_full[c], t * TC_XH_LD + TC_XOFF, b0);
           if (t >= 1) {
             mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);   // all 8 slices of h_{t-1} are in global memory
+            if (c == 0) FWD_TRACE(0, t, 1);
             fence_proxy_async_all();
             mbar_arrive_expect_tx(&bars->h_full[c], 65536);
             for (int kb = 0; kb < 4; ++kb)
               tma_load_2d_mcast(hbuf + kb * 16384 + rank * 2048, &tm_h, &bars->h_full[c], t * TC_XH_LD + kb * 64,
                                 b0 + 16 * (int)rank, 0xFF);
+            if (c == 0) FWD_TRACE(0, t, 2);
           }
         }
         mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);       // phase of step T-1 (keeps parities aligned)
@@ -240,6 +250,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           for (int c = 0; c < TC_NCH; ++c) {
             const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
             mbar_wait(&bars->x_full[c], (n_xf[c]++) & 1);
+            if (c == 0) FWD_TRACE(1, t, 0);
             tcgen05_fence_after();
             for (int k16 = 0; k16 < p.k16_x; ++k16) {
               const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0 + c * 8192) + k16 * 32, 0, 512, LAYOUT_SW64);
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             for (int c = 0; c < TC_NCH; ++c) {
               const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
               mbar_wait(&bars->h_full[c], (n_hf[c]++) & 1);
+              if (c == 0) FWD_TRACE(1, t, 1);
               tcgen05_fence_after();
 #pragma unroll
               for (int kb = 0; kb < 4; ++kb)
@@ -265,6 +277,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
                   umma_f16(acc, da, db, idesc, 1);
                 }
               umma_commit(&bars->acc_full[c][g & 1]);
+              if (c == 0) FWD_TRACE(1, t, 2);
             }
           }
         }
@@ -285,6 +298,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
       for (int t = 0; t < T; ++t) {
         const uint32_t g = (uint32_t)(it * T + t);
         mbar_wait(&bars->acc_full[c][g & 1], (g >> 1) & 1);
+        if (leader && c == 0) FWD_TRACE(2, t, 0);
         tcgen05_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 256 + (g & 1) * 128;
         __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + rank * TC_HS;
@@ -322,40 +336,32 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             pg[jj / 2] = pack_bf16x2(gv[0], gv[1]);
             po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
           }
-          if (valid) {
-            uint4* hd = reinterpret_cast<uint4*>(hrow + jb * 16);
-            hd[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            hd[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          if (valid) {   // one full 32-byte sector per store instruction (STG.256)
+            st_global_v8(hrow + jb * 16, ph);
             if (grow) {
-              uint4* gd = reinterpret_cast<uint4*>(grow + jb * 16);
-              gd[0] = make_uint4(pi[0], pi[1], pi[2], pi[3]);
-              gd[1] = make_uint4(pi[4], pi[5], pi[6], pi[7]);
-              gd = reinterpret_cast<uint4*>(grow + TC_H + jb * 16);
-              gd[0] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
-              gd[1] = make_uint4(pf[4], pf[5], pf[6], pf[7]);
-              gd = reinterpret_cast<uint4*>(grow + 2 * TC_H + jb * 16);
-              gd[0] = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-              gd[1] = make_uint4(pg[4], pg[5], pg[6], pg[7]);
-              gd = reinterpret_cast<uint4*>(grow + 3 * TC_H + jb * 16);
-              gd[0] = make_uint4(po[0], po[1], po[2], po[3]);
-              gd[1] = make_uint4(po[4], po[5], po[6], po[7]);
+              st_global_v8(grow + jb * 16, pi);
+              st_global_v8(grow + TC_H + jb * 16, pf);
+              st_global_v8(grow + 2 * TC_H + jb * 16, pg);
+              st_global_v8(grow + 3 * TC_H + jb * 16, po);
             }
             if (crow) {
-              float4* cd = reinterpret_cast<float4*>(crow + jb * 16);
-#pragma unroll
-              for (int v = 0; v < 4; ++v) cd[v] = make_float4(cn[4 * v], cn[4 * v + 1], cn[4 * v + 2], cn[4 * v + 3]);
+              st_global_v8f(crow + jb * 16, cn);
+              st_global_v8f(crow + jb * 16 + 8, cn + 8);
             }
           }
         }
         tcgen05_fence_before();
-        __threadfence();                       // h slice visible at gpu scope ...
-        fence_proxy_async_all();               // ... and to the async proxy (peers read it with TMA)
+        if (leader && c == 0) FWD_TRACE(2, t, 1);
+        // Publish this CTA's h slice: CTA-level barrier over the chain's 128 threads, then 8 lanes of the leader
+        // warp arrive (release.cluster, cumulative over the barrier) on the 8 CTAs' h_written barriers in parallel.
+        // Readers acquire at cluster scope and cross into the async proxy before their TMA loads.
         named_bar_sync(1 + c, 128);
-        if (leader) {
-          const uint32_t bar = smem_u32(&bars->h_written[c]);
-#pragma unroll
-          for (uint32_t dst = 0; dst < TC_NC; ++dst) mbar_arrive_cluster(mapa_u32(bar, dst));
+        if (leader && c == 0) FWD_TRACE(2, t, 4);
+        if ((warp - 3) % 4 == 0 && lane < TC_NC) {
+          __threadfence();
+          mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written[c]), (uint32_t)lane));
         }
+        if (leader && c == 0) FWD_TRACE(2, t, 5);
       }
     }
   }
@@ -384,13 +390,18 @@ struct HeadParams {
   int64_t row0;
   float* preds;
   __nv_bfloat16* dhout;
+  float* dpred;         // [B*T][16] dLoss/dpred (training), consumed by head_wgrad_kernel
   float* partial;       // [gridDim.x][HEAD_PART]
 };
 
-constexpr int HEAD_PART = TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 16;   // dWo | dgamma | dbeta | dbo | s0 s1 s2
+constexpr int HEAD_PART = 2 * TC_H + TC_OPAD + 16;   // dgamma | dbeta | dbo | s0 s1 s2 (per CTA of the fused pass)
 constexpr int HEAD_THREADS = 256;
+constexpr int HWG_PART = TC_H * TC_OPAD;              // dWo partial per CTA of the weight-gradient pass
+constexpr int HWG_ROWS = 32;                          // rows staged per tile
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(HEAD_THREADS, 1) head_fused_kernel(HeadParams p) {
+  constexpr int HEAD_R = TRAIN ? 4 : 8;            // rows in flight per warp (memory-level parallelism)
   __shared__ __align__(16) float Wo_s[TC_H * TC_OPAD];
   __shared__ float red_s[HEAD_PART];
   __shared__ __align__(16) float bn_s[4][TC_H];      // gamma*inv | beta - gamma*mean*inv | mean | inv
@@ -415,188 +426,293 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_fused_kernel(HeadParams 
   const bool owner = (lane & 1) == 0;
   const float bo_k = (kown < p.O) ? p.bo[kown] : 0.f;
   float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
-  if (p.train) {
+  if (TRAIN) {
     const float Bg = p.denom[0], Mg = p.denom[1];
     c_all = (1.f - p.p1) * (1.f - p.p2) / ((float)p.O * Mg);
     c_last = (1.f - p.p1) * p.p2 / (Bg * (float)p.O);
     c_tar = p.p1 / Bg;
   }
-  float accW[8][TC_OPAD];
   float accG[8], accB[8];
   float accbo = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     accG[i] = 0.f;
     accB[i] = 0.f;
-#pragma unroll
-    for (int k = 0; k < TC_OPAD; ++k) accW[i][k] = 0.f;
   }
   const long rows = (long)p.B * p.T;
   const int nq = TC_H / 4;
-  for (long r = (long)blockIdx.x * (HEAD_THREADS / 32) + warp; r < rows; r += (long)gridDim.x * (HEAD_THREADS / 32)) {
-    const long b = r / p.T;
-    const int t = (int)(r % p.T);
-    const uint4 hraw = *reinterpret_cast<const uint4*>(p.xh + (b * (p.T + 1) + t + 1) * TC_XH_LD + j0);
-    const uint32_t hw[4] = {hraw.x, hraw.y, hraw.z, hraw.w};
-    float hv[8], dm[8], yv[8];
+  for (long rbase = ((long)blockIdx.x * (HEAD_THREADS / 32) + warp) * HEAD_R; rbase < rows;
+       rbase += (long)gridDim.x * (HEAD_THREADS / 32) * HEAD_R) {
+    uint4 hraw[HEAD_R];
+    float ytv[HEAD_R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hv[2 * i] = bf16_lo(hw[i]);
-      hv[2 * i + 1] = bf16_hi(hw[i]);
-    }
-    if (p.use_dropout) {
-      const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + lane * 2;
-      dropout_quad(p.key, qbase, dm);
-      dropout_quad(p.key, qbase + 1, dm + 4);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dm[i] = 1.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) yv[i] = fmaf(bn_s[0][j0 + i], hv[i], bn_s[1][j0 + i]) * dm[i];
-    float pr[TC_OPAD];
-#pragma unroll
-    for (int k = 0; k < TC_OPAD; ++k) pr[k] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float4 w = w4[kk];
-        pr[4 * kk + 0] = fmaf(yv[i], w.x, pr[4 * kk + 0]);
-        pr[4 * kk + 1] = fmaf(yv[i], w.y, pr[4 * kk + 1]);
-        pr[4 * kk + 2] = fmaf(yv[i], w.z, pr[4 * kk + 2]);
-        pr[4 * kk + 3] = fmaf(yv[i], w.w, pr[4 * kk + 3]);
+    for (int u = 0; u < HEAD_R; ++u) {
+      const long r = rbase + u;
+      hraw[u] = make_uint4(0u, 0u, 0u, 0u);
+      ytv[u] = 0.f;
+      if (r < rows) {
+        const long b = r / p.T;
+        const int t = (int)(r % p.T);
+        hraw[u] = *reinterpret_cast<const uint4*>(p.xh + (b * (p.T + 1) + t + 1) * TC_XH_LD + j0);
+        if (p.y && kown < p.O) ytv[u] = p.y[r * p.O + kown];
       }
     }
-    // reduce-scatter butterfly: 16 partial sums over 32 lanes with 8+4+2+1+1 shuffles
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool up = (lane & 16) != 0;
-      const float send = up ? pr[i] : pr[i + 8];
-      const float keep = up ? pr[i + 8] : pr[i];
-      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
+    for (int u = 0; u < HEAD_R; ++u) {
+      const long r = rbase + u;
+      if (r >= rows) break;
+      const long b = r / p.T;
+      const int t = (int)(r % p.T);
+      const uint32_t hw[4] = {hraw[u].x, hraw[u].y, hraw[u].z, hraw[u].w};
+      float hv[8], dm[8], yv[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool up = (lane & 8) != 0;
-      const float send = up ? pr[i] : pr[i + 4];
-      const float keep = up ? pr[i + 4] : pr[i];
-      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const bool up = (lane & 4) != 0;
-      const float send = up ? pr[i] : pr[i + 2];
-      const float keep = up ? pr[i + 2] : pr[i];
-      pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    {
-      const bool up = (lane & 2) != 0;
-      const float send = up ? pr[0] : pr[1];
-      const float keep = up ? pr[1] : pr[0];
-      pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    float pred = pr[0] + __shfl_xor_sync(0xffffffffu, pr[0], 1) + bo_k;
-    if (p.preds && owner && kown < p.O) p.preds[r * p.O + kown] = pred;
-    if (!p.y) continue;
-    const float yt = (kown < p.O) ? p.y[r * p.O + kown] : 0.f;
-    const bool any = __ballot_sync(0xffffffffu, yt != 0.0f) != 0u;      // losses.py:72
-    const float mk = any ? 1.f : 0.f;
-    const float d = (kown < p.O) ? (pred * mk - yt) : 0.f;               // losses.py:75
-    const bool last = (t == p.T - 1);
-    float coef = c_all;
-    if (owner) {
-      const float d2 = d * d;
-      s2 += d2;
-      if (last) {
-        s1 += d2;
-        if (kown == p.target_idx) s0 += d2;
+      for (int i = 0; i < 4; ++i) {
+        hv[2 * i] = bf16_lo(hw[i]);
+        hv[2 * i + 1] = bf16_hi(hw[i]);
       }
-    }
-    if (!p.train) continue;
-    if (last) coef += c_last + ((kown == p.target_idx) ? c_tar : 0.f);
-    const float dp_own = 2.f * d * coef * mk;
-    if (owner) accbo += dp_own;
-    float dp[TC_OPAD];
+      if (p.use_dropout) {
+        const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + lane * 2;
+        dropout_quad(p.key, qbase, dm);
+        dropout_quad(p.key, qbase + 1, dm + 4);
+      } else {
 #pragma unroll
-    for (int k = 0; k < TC_OPAD; ++k) {
-      const int src = ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2;
-      dp[k] = __shfl_sync(0xffffffffu, dp_own, src);
-    }
-    float dyv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
-      float s = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float4 w = w4[kk];
-        s = fmaf(dp[4 * kk + 0], w.x, s);
-        s = fmaf(dp[4 * kk + 1], w.y, s);
-        s = fmaf(dp[4 * kk + 2], w.z, s);
-        s = fmaf(dp[4 * kk + 3], w.w, s);
-        accW[i][4 * kk + 0] = fmaf(yv[i], dp[4 * kk + 0], accW[i][4 * kk + 0]);
-        accW[i][4 * kk + 1] = fmaf(yv[i], dp[4 * kk + 1], accW[i][4 * kk + 1]);
-        accW[i][4 * kk + 2] = fmaf(yv[i], dp[4 * kk + 2], accW[i][4 * kk + 2]);
-        accW[i][4 * kk + 3] = fmaf(yv[i], dp[4 * kk + 3], accW[i][4 * kk + 3]);
+        for (int i = 0; i < 8; ++i) dm[i] = 1.f;
       }
-      const float dd = s * dm[i];                       // through Dropout
-      accG[i] = fmaf(dd, (hv[i] - bn_s[2][j0 + i]) * bn_s[3][j0 + i], accG[i]);
-      accB[i] += dd;
-      dyv[i] = dd * bn_s[0][j0 + i];                    // through BN -> dLoss/dh
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yv[i] = fmaf(bn_s[0][j0 + i], hv[i], bn_s[1][j0 + i]) * dm[i];
+      float pr[TC_OPAD];
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) pr[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 w = w4[kk];
+          pr[4 * kk + 0] = fmaf(yv[i], w.x, pr[4 * kk + 0]);
+          pr[4 * kk + 1] = fmaf(yv[i], w.y, pr[4 * kk + 1]);
+          pr[4 * kk + 2] = fmaf(yv[i], w.z, pr[4 * kk + 2]);
+          pr[4 * kk + 3] = fmaf(yv[i], w.w, pr[4 * kk + 3]);
+        }
+      }
+      // reduce-scatter butterfly: 16 partial sums over 32 lanes with 8+4+2+1+1 shuffles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool up = (lane & 16) != 0;
+        const float send = up ? pr[i] : pr[i + 8];
+        const float keep = up ? pr[i + 8] : pr[i];
+        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool up = (lane & 8) != 0;
+        const float send = up ? pr[i] : pr[i + 4];
+        const float keep = up ? pr[i + 4] : pr[i];
+        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool up = (lane & 4) != 0;
+        const float send = up ? pr[i] : pr[i + 2];
+        const float keep = up ? pr[i + 2] : pr[i];
+        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const bool up = (lane & 2) != 0;
+        const float send = up ? pr[0] : pr[1];
+        const float keep = up ? pr[1] : pr[0];
+        pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float pred = pr[0] + __shfl_xor_sync(0xffffffffu, pr[0], 1) + bo_k;
+      if (p.preds && owner && kown < p.O) p.preds[r * p.O + kown] = pred;
+      if (!p.y) continue;
+      const float yt = ytv[u];
+      const bool any = __ballot_sync(0xffffffffu, yt != 0.0f) != 0u;      // losses.py:72
+      const float mk = any ? 1.f : 0.f;
+      const float d = (kown < p.O) ? (pred * mk - yt) : 0.f;               // losses.py:75
+      const bool last = (t == p.T - 1);
+      if (owner) {
+        const float d2 = d * d;
+        s2 += d2;
+        if (last) {
+          s1 += d2;
+          if (kown == p.target_idx) s0 += d2;
+        }
+      }
+      if (!TRAIN) continue;
+      float coef = c_all;
+      if (last) coef += c_last + ((kown == p.target_idx) ? c_tar : 0.f);
+      const float dp_own = 2.f * d * coef * mk;
+      if (owner) {
+        accbo += dp_own;
+        p.dpred[r * TC_OPAD + kown] = dp_own;
+      }
+      float dp[TC_OPAD];
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) {
+        const int src = ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2;
+        dp[k] = __shfl_sync(0xffffffffu, dp_own, src);
+      }
+      float dyv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
+        float s = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 w = w4[kk];
+          s = fmaf(dp[4 * kk + 0], w.x, s);
+          s = fmaf(dp[4 * kk + 1], w.y, s);
+          s = fmaf(dp[4 * kk + 2], w.z, s);
+          s = fmaf(dp[4 * kk + 3], w.w, s);
+        }
+        const float dd = s * dm[i];                       // through Dropout
+        accG[i] = fmaf(dd, (hv[i] - bn_s[2][j0 + i]) * bn_s[3][j0 + i], accG[i]);
+        accB[i] += dd;
+        dyv[i] = dd * bn_s[0][j0 + i];                    // through BN -> dLoss/dh
+      }
+      uint4 o;
+      o.x = pack_bf16x2(dyv[0], dyv[1]);
+      o.y = pack_bf16x2(dyv[2], dyv[3]);
+      o.z = pack_bf16x2(dyv[4], dyv[5]);
+      o.w = pack_bf16x2(dyv[6], dyv[7]);
+      *reinterpret_cast<uint4*>(p.dhout + r * TC_H + j0) = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(dyv[0], dyv[1]);
-    o.y = pack_bf16x2(dyv[2], dyv[3]);
-    o.z = pack_bf16x2(dyv[4], dyv[5]);
-    o.w = pack_bf16x2(dyv[6], dyv[7]);
-    *reinterpret_cast<uint4*>(p.dhout + r * TC_H + j0) = o;
   }
   // CTA-level reduction of the per-warp accumulators (shared atomics: 8 warps, short)
   if (p.y) {
+    if (TRAIN) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-      for (int k = 0; k < TC_OPAD; ++k) atomicAdd(&red_s[(j0 + i) * TC_OPAD + k], accW[i][k]);
-      atomicAdd(&red_s[TC_H * TC_OPAD + j0 + i], accG[i]);
-      atomicAdd(&red_s[TC_H * TC_OPAD + TC_H + j0 + i], accB[i]);
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&red_s[j0 + i], accG[i]);
+        atomicAdd(&red_s[TC_H + j0 + i], accB[i]);
+      }
     }
     if (owner) {
-      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + kown], accbo);
-      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 0], s0);
-      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 1], s1);
-      atomicAdd(&red_s[TC_H * TC_OPAD + 2 * TC_H + TC_OPAD + 2], s2);
+      if (TRAIN) atomicAdd(&red_s[2 * TC_H + kown], accbo);
+      atomicAdd(&red_s[2 * TC_H + TC_OPAD + 0], s0);
+      atomicAdd(&red_s[2 * TC_H + TC_OPAD + 1], s1);
+      atomicAdd(&red_s[2 * TC_H + TC_OPAD + 2], s2);
     }
     __syncthreads();
     for (int i = tid; i < HEAD_PART; i += HEAD_THREADS) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
   }
 }
 
+// dWo[j][k] = sum_r y[r][j] * dpred[r][k] with y = Dropout(BN(h)) recomputed from h: CTA tiles of 32 rows staged in
+// shared memory, thread (j-group of 4, k-group of 4) keeps a 4x4 block of the 256 x 16 result.
+__global__ void __launch_bounds__(256, 2) head_wgrad_kernel(HeadParams p, float* __restrict__ wpartial) {
+  __shared__ __align__(16) float y_s[HWG_ROWS][TC_H];
+  __shared__ __align__(16) float dp_s[HWG_ROWS][TC_OPAD];
+  __shared__ __align__(16) float bn_s[2][TC_H];
+  const int tid = threadIdx.x;
+  for (int j = tid; j < TC_H; j += 256) {
+    const float iv = 1.0f / sqrtf(p.var[j] + p.eps);
+    bn_s[0][j] = p.gamma[j] * iv;
+    bn_s[1][j] = p.beta[j] - p.gamma[j] * p.mean[j] * iv;
+  }
+  const int jg = tid >> 2, kg = tid & 3;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const long rows = (long)p.B * p.T;
+  const int nq = TC_H / 4;
+  __syncthreads();
+  for (long r0 = (long)blockIdx.x * HWG_ROWS; r0 < rows; r0 += (long)gridDim.x * HWG_ROWS) {
+    // stage: 32 rows x 256 cols, each thread converts 4 x (8 bf16)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;            // 0..1023 = 32 rows x 32 chunks of 8
+      const int rr = idx >> 5, ch = idx & 31;
+      const long r = r0 + rr;
+      float v[8];
+      if (r < rows) {
+        const long b = r / p.T;
+        const int t = (int)(r % p.T);
+        const uint4 raw = *reinterpret_cast<const uint4*>(p.xh + (b * (p.T + 1) + t + 1) * TC_XH_LD + ch * 8);
+        const uint32_t hw[4] = {raw.x, raw.y, raw.z, raw.w};
+        float dm[8];
+        if (p.use_dropout) {
+          const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + ch * 2;
+          dropout_quad(p.key, qbase, dm);
+          dropout_quad(p.key, qbase + 1, dm + 4);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dm[e] = 1.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[2 * e] = fmaf(bn_s[0][ch * 8 + 2 * e], bf16_lo(hw[e]), bn_s[1][ch * 8 + 2 * e]) * dm[2 * e];
+          v[2 * e + 1] = fmaf(bn_s[0][ch * 8 + 2 * e + 1], bf16_hi(hw[e]), bn_s[1][ch * 8 + 2 * e + 1]) * dm[2 * e + 1];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+      *reinterpret_cast<float4*>(&y_s[rr][ch * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&y_s[rr][ch * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    for (int idx = tid; idx < HWG_ROWS * TC_OPAD; idx += 256) {
+      const long r = r0 + idx / TC_OPAD;
+      dp_s[idx / TC_OPAD][idx % TC_OPAD] = (r < rows) ? p.dpred[r * TC_OPAD + idx % TC_OPAD] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < HWG_ROWS; ++rr) {
+      const float4 yv = *reinterpret_cast<const float4*>(&y_s[rr][jg * 4]);
+      const float4 dv = *reinterpret_cast<const float4*>(&dp_s[rr][kg * 4]);
+      const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+      const float da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ya[a], da[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      wpartial[(long)blockIdx.x * HWG_PART + (jg * 4 + a) * TC_OPAD + kg * 4 + b] = acc[a][b];
+}
+
 // Sums the per-CTA head partials in a fixed order and scatters them into the flat gradient vector / loss tail.
-__global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial, int O, int B, const float* denom,
-                                   float p1, float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
+__global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial, int n_wcta,
+                                   const float* __restrict__ wpartial, int O, int B, const float* denom, float p1,
+                                   float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
                                    float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= HEAD_PART) return;
+  if (i < HWG_PART) {
+    if (train) {
+      const int j = i / TC_OPAD, k = i % TC_OPAD;
+      if (k < O) {
+        double s = 0.0;
+        for (int c = 0; c < n_wcta; ++c) s += wpartial[(long)c * HWG_PART + i];
+        gWo[j * O + k] = (float)s;
+      }
+    }
+    return;
+  }
+  const int q = i - HWG_PART;
+  if (q >= HEAD_PART) return;
   double s = 0.0;
-  for (int c = 0; c < n_cta; ++c) s += partial[(long)c * HEAD_PART + i];
-  if (i < TC_H * TC_OPAD) {
-    const int j = i / TC_OPAD, k = i % TC_OPAD;
-    if (train && k < O) gWo[j * O + k] = (float)s;
-  } else if (i < TC_H * TC_OPAD + TC_H) {
-    if (train) ggamma[i - TC_H * TC_OPAD] = (float)s;
-  } else if (i < TC_H * TC_OPAD + 2 * TC_H) {
-    if (train) gbeta[i - TC_H * TC_OPAD - TC_H] = (float)s;
-  } else if (i < TC_H * TC_OPAD + 2 * TC_H + TC_OPAD) {
-    const int k = i - TC_H * TC_OPAD - 2 * TC_H;
+  for (int c = 0; c < n_cta; ++c) s += partial[(long)c * HEAD_PART + q];
+  if (q < TC_H) {
+    if (train) ggamma[q] = (float)s;
+  } else if (q < 2 * TC_H) {
+    if (train) gbeta[q - TC_H] = (float)s;
+  } else if (q < 2 * TC_H + TC_OPAD) {
+    const int k = q - 2 * TC_H;
     if (train && k < O) gbo[k] = (float)s;
-  } else if (i == TC_H * TC_OPAD + 2 * TC_H + TC_OPAD) {
+  } else if (q == 2 * TC_H + TC_OPAD) {
     // the three loss sums live in consecutive slots; one thread finishes the loss (losses.py:87-98)
     double s0 = s, s1 = 0.0, s2 = 0.0;
     for (int c = 0; c < n_cta; ++c) {
-      s1 += partial[(long)c * HEAD_PART + i + 1];
-      s2 += partial[(long)c * HEAD_PART + i + 2];
+      s1 += partial[(long)c * HEAD_PART + q + 1];
+      s2 += partial[(long)c * HEAD_PART + q + 2];
     }
     const double Bg = denom[0], Mg = denom[1];
     const double mse0 = s0 / Bg, mse1 = s1 / (Bg * O), mse2 = s2 / (Mg * O);
@@ -636,6 +752,7 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   m.Ub = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
   m.head_ctas = 148;
+  m.head_wctas = 148 * 2;
   m.head_part_elems = (size_t)m.head_ctas * HEAD_PART;
   m.head_part = reinterpret_cast<float*>(take(m.head_part_elems * 4));
   if (!c.forward_only) {
@@ -644,10 +761,13 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
     m.dz = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * 4 * H * 2));
     m.dhout = reinterpret_cast<__nv_bfloat16*>(take(B * T * H * 2));
     m.dc = reinterpret_cast<float*>(take(B * H * 4));
+    m.dpred = reinterpret_cast<float*>(take(B * T * TC_OPAD * 4));
+    m.head_wpart = reinterpret_cast<float*>(take((size_t)m.head_wctas * HWG_PART * 4));
     m.wg_part_elems = (size_t)64 * 384 * 1024;
     m.wg_part = reinterpret_cast<float*>(take(m.wg_part_elems * 4));
   } else {
     m.gates = nullptr; m.cst = nullptr; m.dz = nullptr; m.dhout = nullptr; m.dc = nullptr; m.wg_part = nullptr;
+    m.dpred = nullptr; m.head_wpart = nullptr;
     m.wg_part_elems = 0;
   }
   const int64_t I = c.n_inputs, O = c.n_outputs;
@@ -734,6 +854,13 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   p.gates = save ? m.gates : nullptr;
   p.cst = save ? m.cst : nullptr;
   p.biasp = m.biasp;
+  static long long* trace_dev = nullptr;
+  static const bool want_trace = getenv("LFMQ_TRACE_FWD") != nullptr;
+  if (want_trace && !trace_dev) {
+    LFMQ_CUDA_CHECK(cudaMalloc(&trace_dev, 3 * 16 * 8 * sizeof(long long)));
+  }
+  if (want_trace) LFMQ_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, 3 * 16 * 8 * sizeof(long long), s));
+  p.trace = want_trace ? trace_dev : nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(TC_NC * p.n_clusters);
   cfg.blockDim = dim3(FWD_THREADS);
@@ -748,6 +875,24 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   cfg.numAttrs = 1;
   LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
   g_launches++;
+  if (want_trace) {
+    long long h[3 * 16 * 8];
+    LFMQ_CUDA_CHECK(cudaStreamSynchronize(s));
+    LFMQ_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long t0 = h[(1 * 16 + 0) * 8 + 0];
+    const char* names[3] = {"producer", "mma", "epilogue"};
+    for (int t = 0; t < 12; ++t) {
+      fprintf(stderr, "[trace t=%2d]", t);
+      for (int r = 0; r < 3; ++r) {
+        fprintf(stderr, "  %s:", names[r]);
+        for (int k = 0; k < 6; ++k) {
+          const long long v = h[(r * 16 + t) * 8 + k];
+          fprintf(stderr, " %lld", v ? v - t0 : -1LL);
+        }
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }
 
@@ -772,14 +917,22 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   h.row0 = row0;
   h.preds = preds;
   h.dhout = train ? m.dhout : nullptr;
+  h.dpred = train ? m.dpred : nullptr;
   h.partial = m.head_part;
-  head_fused_kernel<<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
-  LFMQ_LAUNCH_CHECK();
+  if (train) {
+    head_fused_kernel<true><<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
+    LFMQ_LAUNCH_CHECK();
+    head_wgrad_kernel<<<m.head_wctas, 256, 0, s>>>(h, m.head_wpart);
+    LFMQ_LAUNCH_CHECK();
+  } else {
+    head_fused_kernel<false><<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
+    LFMQ_LAUNCH_CHECK();
+  }
   if (y) {
-    head_reduce_kernel<<<(HEAD_PART + 255) / 256, 256, 0, s>>>(
-        m.head_ctas, m.head_part, m.O, B, denom, c.target_lambda, c.rnn_lambda, train ? 1 : 0,
-        grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr, grads ? grads + m.ogamma : nullptr,
-        grads ? grads + m.obeta : nullptr, out2);
+    head_reduce_kernel<<<(HWG_PART + HEAD_PART + 255) / 256, 256, 0, s>>>(
+        m.head_ctas, m.head_part, m.head_wctas, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda,
+        train ? 1 : 0, grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr,
+        grads ? grads + m.ogamma : nullptr, grads ? grads + m.obeta : nullptr, out2);
     LFMQ_LAUNCH_CHECK();
   }
   return 0;
@@ -931,35 +1084,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       }
       if (!valid) continue;
       uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
-      {
-        const uint4* s4 = reinterpret_cast<const uint4*>(grow + jb * 16);
-        uint4 a = s4[0], bq = s4[1];
-        gi[0] = a.x; gi[1] = a.y; gi[2] = a.z; gi[3] = a.w; gi[4] = bq.x; gi[5] = bq.y; gi[6] = bq.z; gi[7] = bq.w;
-        s4 = reinterpret_cast<const uint4*>(grow + TC_H + jb * 16);
-        a = s4[0]; bq = s4[1];
-        gf[0] = a.x; gf[1] = a.y; gf[2] = a.z; gf[3] = a.w; gf[4] = bq.x; gf[5] = bq.y; gf[6] = bq.z; gf[7] = bq.w;
-        s4 = reinterpret_cast<const uint4*>(grow + 2 * TC_H + jb * 16);
-        a = s4[0]; bq = s4[1];
-        gg[0] = a.x; gg[1] = a.y; gg[2] = a.z; gg[3] = a.w; gg[4] = bq.x; gg[5] = bq.y; gg[6] = bq.z; gg[7] = bq.w;
-        s4 = reinterpret_cast<const uint4*>(grow + 3 * TC_H + jb * 16);
-        a = s4[0]; bq = s4[1];
-        go[0] = a.x; go[1] = a.y; go[2] = a.z; go[3] = a.w; go[4] = bq.x; go[5] = bq.y; go[6] = bq.z; go[7] = bq.w;
-        s4 = reinterpret_cast<const uint4*>(dhrow + jb * 16);
-        a = s4[0]; bq = s4[1];
-        dhp[0] = a.x; dhp[1] = a.y; dhp[2] = a.z; dhp[3] = a.w; dhp[4] = bq.x; dhp[5] = bq.y; dhp[6] = bq.z;
-        dhp[7] = bq.w;
-      }
+      ld_global_v8(grow + jb * 16, gi);
+      ld_global_v8(grow + TC_H + jb * 16, gf);
+      ld_global_v8(grow + 2 * TC_H + jb * 16, gg);
+      ld_global_v8(grow + 3 * TC_H + jb * 16, go);
+      ld_global_v8(dhrow + jb * 16, dhp);
       float ct[16], cp[16], dcv[16];
+      ld_global_v8f(crow + jb * 16, ct);
+      ld_global_v8f(crow + jb * 16 + 8, ct + 8);
+      if (p.t > 0) {
+        ld_global_v8f(crow - TC_H + jb * 16, cp);
+        ld_global_v8f(crow - TC_H + jb * 16 + 8, cp + 8);
+      } else {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const float4 c4 = reinterpret_cast<const float4*>(crow + jb * 16)[v];
-        ct[4 * v] = c4.x; ct[4 * v + 1] = c4.y; ct[4 * v + 2] = c4.z; ct[4 * v + 3] = c4.w;
-        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.t > 0) p4 = reinterpret_cast<const float4*>(crow - TC_H + jb * 16)[v];
-        cp[4 * v] = p4.x; cp[4 * v + 1] = p4.y; cp[4 * v + 2] = p4.z; cp[4 * v + 3] = p4.w;
-        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_gemm) d4 = reinterpret_cast<const float4*>(dcrow + jb * 16)[v];
-        dcv[4 * v] = d4.x; dcv[4 * v + 1] = d4.y; dcv[4 * v + 2] = d4.z; dcv[4 * v + 3] = d4.w;
+        for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+      }
+      if (has_gemm) {
+        ld_global_v8f(dcrow + jb * 16, dcv);
+        ld_global_v8f(dcrow + jb * 16 + 8, dcv + 8);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dcv[j] = 0.f;
       }
       uint32_t zi[8], zf[8], zg[8], zo[8];
       float dcn_out[16];
@@ -988,22 +1133,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         zg[jj / 2] = pack_bf16x2(rg[0], rg[1]);
         zo[jj / 2] = pack_bf16x2(ro[0], ro[1]);
       }
-      uint4* d4 = reinterpret_cast<uint4*>(dzrow + jb * 16);
-      d4[0] = make_uint4(zi[0], zi[1], zi[2], zi[3]);
-      d4[1] = make_uint4(zi[4], zi[5], zi[6], zi[7]);
-      d4 = reinterpret_cast<uint4*>(dzrow + TC_H + jb * 16);
-      d4[0] = make_uint4(zf[0], zf[1], zf[2], zf[3]);
-      d4[1] = make_uint4(zf[4], zf[5], zf[6], zf[7]);
-      d4 = reinterpret_cast<uint4*>(dzrow + 2 * TC_H + jb * 16);
-      d4[0] = make_uint4(zg[0], zg[1], zg[2], zg[3]);
-      d4[1] = make_uint4(zg[4], zg[5], zg[6], zg[7]);
-      d4 = reinterpret_cast<uint4*>(dzrow + 3 * TC_H + jb * 16);
-      d4[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
-      d4[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        reinterpret_cast<float4*>(dcrow + jb * 16)[v] =
-            make_float4(dcn_out[4 * v], dcn_out[4 * v + 1], dcn_out[4 * v + 2], dcn_out[4 * v + 3]);
+      st_global_v8(dzrow + jb * 16, zi);
+      st_global_v8(dzrow + TC_H + jb * 16, zf);
+      st_global_v8(dzrow + 2 * TC_H + jb * 16, zg);
+      st_global_v8(dzrow + 3 * TC_H + jb * 16, zo);
+      st_global_v8f(dcrow + jb * 16, dcn_out);
+      st_global_v8f(dcrow + jb * 16 + 8, dcn_out + 8);
     }
   }
   __syncwarp();
