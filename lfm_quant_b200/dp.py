@@ -1,0 +1,28 @@
+"""Data parallelism over the company-batch axis: host-side plumbing shared by
+ForecasterEngine.train_step_dp, bench.py and the gloo tests.  One process per GPU; exactly ONE collective on the
+data path per step -- the SUM all-reduce of the flat gradient (+ its loss / mse tail) over NCCL."""
+from __future__ import absolute_import, division, print_function
+
+
+def shard_rows(batch_global, rank, world):
+    """Rank r takes rows [r*B/R, (r+1)*B/R) of each global batch; returns (row0, n_rows)."""
+    base, rem = divmod(batch_global, world)
+    n = base + (1 if rank < rem else 0)
+    row0 = rank * base + min(rank, rem)
+    return row0, n
+
+
+def global_denominators(local_denom, dist):
+    """{B_local, mask_count_local} -> {B_global, mask_count_global}: the loss denominators are global
+    (losses.py:87,90,131-135), so each rank scales dLoss/dpred with them before the gradient all-reduce.
+    Targets only -- done once per batch when it is built, not on the step path."""
+    out = local_denom.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    return out
+
+
+def allreduce_flat_gradient(flat_grads, n_trainable, dist):
+    """The single data-path collective: SUM over ranks of grads[0 : n_trainable + 2] (gradient, loss, mse_0).
+    clip_by_global_norm, the optimizer and MaxNorm then run redundantly on every rank on the reduced gradient."""
+    dist.all_reduce(flat_grads[:n_trainable + 2], op=dist.ReduceOp.SUM)
+    return flat_grads

@@ -182,8 +182,9 @@ class ForecasterEngine(object):
         """Data-parallel step: local BPTT with global denominators, ONE NCCL all-reduce over the flat
         gradient (+ loss/mse tail), then the replicated clip + optimizer."""
         import torch.distributed as dist
+        from .dp import allreduce_flat_gradient
         self.backward(x, y, step=step, row0=row0, denom=denom_global)
-        dist.all_reduce(self.grads[:self.n_trainable + 2], op=dist.ReduceOp.SUM)
+        allreduce_flat_gradient(self.grads, self.n_trainable, dist)
         self.apply(lr, step)
         return self.grads[self.n_trainable:self.n_trainable + 2]
 

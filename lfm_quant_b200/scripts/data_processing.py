@@ -140,7 +140,7 @@ class Dataset(object):
         num['date'] = num['date'].dt.strftime('%Y%m%d').astype(np.float64)
         num['gvkey'] = 0.0
         self.table = np.ascontiguousarray(num.values.astype(np.float64))
-        self._keys = self.data['gvkey'].values.astype(str)
+        self._keys = np.asarray([str(k) for k in self.data['gvkey'].tolist()], dtype=str)   # plain numpy '<U' array
         self._dates = self.data['date'].values
         self._dataset = {k: None for k in ('train_X', 'train_Y', 'valid_X', 'valid_Y', 'test_X', 'test_Y')}
         self._meta = {'train': None, 'valid': None, 'test': None}
@@ -289,7 +289,7 @@ class Dataset(object):
 
     def _get_gvkeys(self):
         g = self.data[['date', 'gvkey']]
-        return g[g['date'] <= self.end_date]['gvkey'].unique()
+        return np.asarray([str(k) for k in g[g['date'] <= self.end_date]['gvkey'].unique()], dtype=str)
 
     @staticmethod
     def train_test_split(keys, validation_size, seed, is_train):

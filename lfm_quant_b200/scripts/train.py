@@ -1,0 +1,163 @@
+"""Train driver (reference: scripts/train.py:27-432).
+
+Same life cycle -- build model/optimizer/losses, materialise every batch up front (train.py:64-80), epoch loop
+with shuffled batch order, CSV logs (train.py:133-147,156-167,227-238), save-best / early-stop
+(train.py:240-266) -- but the step body ``_train_step_point`` (train.py:178-199) is ONE native call
+(fwd + loss + BPTT + clip + optimizer + MaxNorm on the GPU) and the per-step ``mse.numpy()`` host sync of the
+reference (train.py:199) is deferred: device scalars are read back only when a log line is due.
+"""
+from __future__ import absolute_import, division, print_function
+
+import copy
+import os
+import pathlib
+import random
+import time
+from collections import defaultdict
+
+import numpy as np
+import pandas as pd
+
+from .model_utils.losses import Losses
+from .model_utils.model import Model
+from .model_utils.optimizers import Optimizers
+
+
+class Train(object):
+
+    def __init__(self, config, dataset):
+        self.config = config
+        self.dataset = dataset
+        self.dataset.generate_dataset()
+        self.model = Model(self.config, self.dataset).get_model()
+        self.target_index = self.dataset.target_index
+        self.optimizer = Optimizers(self.config).get_optimizer()
+        self.optimizer.bind(self.model)
+        self.losses = Losses(self.config, self.target_index, engine=self.model.engine)
+
+        self.train_set = self.dataset.train_set
+        self.valid_set = self.dataset.valid_set
+        self.train_set = self.train_set.shuffle(buffer_size=10000, seed=self.config.seed)
+        self.train_set = self.train_set.batch(batch_size=self.config.batch_size)
+        self.valid_set = self.valid_set.batch(batch_size=self.config.batch_size)
+
+        self.model_dir = os.path.join(self.config.experiments_dir, self.config.model_dir)
+        self.chkpts_dir = os.path.join(self.model_dir, 'chkpts')
+        self.train_log_dir = os.path.join(self.model_dir, 'train_log')
+        train_dirs = [self.model_dir, self.chkpts_dir, self.train_log_dir]
+        print(train_dirs)
+        for dirname in train_dirs:
+            if not os.path.isdir(dirname):
+                print("Creating dir %s" % dirname)
+                pathlib.Path(dirname).mkdir(parents=True, exist_ok=True)
+
+        self.min_valid_mse = np.inf
+        self.min_valid_uq_loss = np.inf
+        self._grad_norm = 1.0
+
+        print("Creating batches ...")
+        self._batches = [self.dataset.get_batch(*items) for items in self.train_set]
+        self._valid_batches = [self.dataset.get_batch(*items) for items in self.valid_set]
+
+    def train(self):
+        if self.config.load_saved_weights:
+            self.model.load_weights(os.path.join(self.chkpts_dir, "chkpt"))
+        print("Training in progress ...")
+        epochs = self.config.max_epoch
+        checkpoint_prefix = os.path.join(self.chkpts_dir, "chkpt")
+        train_logs_batch = defaultdict(list)
+        train_logs_epoch = defaultdict(list)
+        self.model.save_weights(checkpoint_prefix)
+        valid_mse = None
+        start = time.time()
+        for epoch in range(epochs):
+            self.model.reset_states()
+            mse_steps, uq_loss_steps = [], []
+            random.shuffle(self._batches)                       # train.py:115 (unseeded in the reference)
+            for (batch_n, cur_batch) in enumerate(self._batches):
+                inp, target = cur_batch[0], cur_batch[1]
+                if self.config.UQ:
+                    raise NotImplementedError('UQ range estimates are outside the recurrent point-estimate hot path')
+                mse = self._train_step_point(inp, target)       # device scalar, no host sync here
+                uq_loss = None
+                mse_steps.append(mse)
+                uq_loss_steps.append(uq_loss)
+                if batch_n % self.config.logging_interval == 0:
+                    train_logs_batch['batch_n'].append(batch_n)
+                    train_logs_batch['time'].append(time.time() - start)
+                    train_logs_batch['mse'].append(self._mean(mse_steps))
+                    train_logs_batch['uq_loss'].append(None)
+                    train_logs_batch['valid_mse'].append(None)
+                    train_logs_batch['valid_uq_loss'].append(None)
+                    self._write_train_logs(train_logs_batch, 'train-logs-batch')
+
+            if epoch % self.config.epoch_logging_interval == 0:
+                valid_uq_loss, valid_mse, valid_mse_fcst = self._validation_metrics_point_estimate()
+                train_logs_epoch['epoch'].append(epoch)
+                train_logs_epoch['time'].append(time.time() - start)
+                train_logs_epoch['mse'].append(self._mean(mse_steps))
+                train_logs_epoch['uq_loss'].append(None)
+                train_logs_epoch['valid_mse'].append(valid_mse)
+                train_logs_epoch['valid_uq_loss'].append(valid_uq_loss)
+                train_logs_epoch['valid_mse_fcst'].append(valid_mse_fcst)
+                self._write_train_logs(train_logs_epoch, 'train-logs-epoch')
+                if self._save_criteria(train_logs_epoch):
+                    self.model.save_weights(checkpoint_prefix)
+                if self._stop_criteria(train_logs_epoch):
+                    break
+        return valid_mse
+
+    @staticmethod
+    def _mean(device_scalars):
+        import torch
+        return float(torch.stack(list(device_scalars)).mean().item())
+
+    def _train_step_point(self, inp, targets):
+        """train.py:178-199 as one fused native step; returns the step's mse_0 as a device scalar."""
+        assert not self.config.UQ
+        lr = self.optimizer.current_lr()
+        out = self.model.train_step(inp, targets, lr, self.optimizer.iterations)
+        self.optimizer.iterations += 1
+        return out[1]
+
+    def _write_train_logs(self, train_logs, name):
+        df = pd.DataFrame.from_dict(train_logs)
+        fname = os.path.join(self.train_log_dir, self.config.name + '-' + name + '.csv')
+        df.to_csv(fname, sep=',', index=False)
+
+    def _save_criteria(self, train_logs_epoch):
+        assert len(train_logs_epoch['valid_mse']) > 0, 'Error in computing valid_mse or incorrect train log dict passed'
+        if train_logs_epoch['valid_mse'][-1] < self.min_valid_mse:
+            self.min_valid_mse = train_logs_epoch['valid_mse'][-1]
+            return True
+        return False
+
+    def _stop_criteria(self, train_logs_epoch):
+        """train.py:253-266, including its off-by-one."""
+        assert len(train_logs_epoch['valid_mse']) > 0, \
+            'Error in computing valid_mse or incorrect train log dict passed'
+        valid_mse = np.array(train_logs_epoch['valid_mse'])
+        return bool(valid_mse.shape[0] - np.argmin(valid_mse) + 1 >= self.config.early_stop)
+
+    def _validation_metrics_point_estimate(self):
+        """train.py:268-336: predict every validation batch, loss over the stacked arrays, scaled and un-scaled."""
+        preds, targets = [], []
+        for cur_batch in self._valid_batches:
+            preds.append(self.model.predict(cur_batch[0]))
+            targets.append(cur_batch[1].cpu().numpy())
+        if not preds:
+            return None, float('nan'), float('nan')
+        pred_all, target_all = np.vstack(preds), np.vstack(targets)
+        pred_unscaled = self._unscale_preds(copy.deepcopy(pred_all))
+        target_unscaled = self._unscale_preds(copy.deepcopy(target_all))
+        _, valid_mse = self.losses.weight_adjusted_mse([target_all], [pred_all], True)
+        _, valid_mse_fcst = self.losses.weight_adjusted_mse([target_unscaled], [pred_unscaled], True)
+        return None, valid_mse.numpy(), valid_mse_fcst.numpy()
+
+    def _unscale_preds(self, arr):
+        """train.py:420-432."""
+        arr = np.multiply(arr, self.dataset.scaling_params['scale'][:self.dataset.n_outputs]) + \
+            self.dataset.scaling_params['center'][:self.dataset.n_outputs]
+        if self.config.log_squasher:
+            arr = self.dataset.reverse_log_squasher(arr)
+        return arr

@@ -171,6 +171,44 @@ def gather_batch(table, inp_idx, tar_idx, tar_valid, *, seq_len, stride, inp_col
     return inp.astype(np.float32), tar.astype(np.float32), norms
 
 
+def create_window_index(keys, active, dates, *, train, stride, forecast_n, min_unrollings, max_unrollings,
+                        start_date, end_date, last_train_date):
+    """data_processing.py:203-305 as the reference writes it: one Python iteration per table row.
+
+    keys [n] str, active [n] bool/int, dates [n] comparable (e.g. np.datetime64).  Returns
+    (inp [N,3] int, tar [N,3] int, row_index [N]) for the rows that yield a window.
+    """
+    n = len(keys)
+    min_steps = stride * (min_unrollings - 1) + 1
+    max_steps = stride * (max_unrollings - 1) + 1
+    last_key, cur_len = '', 1
+    inp, tar, rows = [], [], []
+    for i in range(n):
+        key = keys[i]
+        act = bool(int(active[i]))
+        date = dates[i]
+        tar_key = keys[i + forecast_n] if i + forecast_n <= n - 1 else ''
+        if key != last_key:
+            cur_len = 1
+        if train:
+            ok = cur_len >= min_steps and act and start_date <= date <= last_train_date and tar_key == key
+        else:
+            ok = cur_len >= min_steps and act and start_date <= date <= end_date
+        if ok:
+            seq_len = min(cur_len - (cur_len - 1) % stride, max_steps)        # :263
+            pad = (max_steps - seq_len) // stride                              # :264
+            inp.append([i - seq_len + 1, i, pad])
+            if key == tar_key:
+                tar.append([i - seq_len + 1 + forecast_n, i + forecast_n, pad])
+            else:
+                tar.append([i - seq_len + 1 + forecast_n, i, pad])
+            rows.append(i)
+        cur_len += 1
+        last_key = key
+    return np.array(inp, dtype=np.int64).reshape(-1, 3), np.array(tar, dtype=np.int64).reshape(-1, 3), \
+        np.array(rows, dtype=np.int64)
+
+
 # --------------------------------------------------------------------------------------
 # Model forward  (rnn_point_estimate.py:76-107; Keras layer algorithms, SURVEY App. A.1-A.2)
 # --------------------------------------------------------------------------------------

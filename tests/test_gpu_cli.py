@@ -1,0 +1,84 @@
+"""End-to-end test of the drop-in boundary on the GPU: the reference's CLI flow
+(`lfm_quant.py --config=config/system-test.conf --train=True`, then `--train=False`; README.md:33-59) on a
+synthetic open-dataset.dat -- BASELINE configs[0]: 1-layer RNN, H=64, batch=32, T=20."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import lfm_oracle as orc
+from lfm_quant_b200.scripts import configs
+from lfm_quant_b200.scripts import lfm_quant as cli
+from lfm_quant_b200.scripts.synthetic import write_open_dataset, write_system_test_conf
+
+pytestmark = pytest.mark.gpu
+
+PRED_COLS_HEAD = ['date', 'gvkey', 'seq_norm']
+PRED_COLS_TAIL = ['targets_1', 'norm_preds_1', 'norm_variance_1', 'norm_targets_1', 'norm_squared_diff_1', 'preds_1',
+                  'variance_1', 'fcst_err_1', 'abs_err_1', 'unscaled_squared_err_1']
+
+
+@pytest.fixture(scope='module')
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp('sys')
+    write_open_dataset(str(d / 'datasets' / 'open-dataset.dat'), n_keys=30, n_months=420, seed=9)
+    write_system_test_conf(str(d / 'config' / 'system-test.conf'), str(d / 'datasets'), str(d / 'experiments'))
+    os.environ.setdefault('LFM_QUANT_ROOT', str(d))
+    return d
+
+
+def test_cli_train_then_predict(workdir):
+    conf = str(workdir / 'config' / 'system-test.conf')
+    configs.reset()
+    valid_mse = cli.main(['--config=' + conf, '--train=True'])
+    mdir = workdir / 'experiments' / 'system-test-model'
+    assert np.isfinite(valid_mse)
+    assert (mdir / 'scales.dat').is_file() and (mdir / 'chkpts' / 'chkpt.lfmq.npz').is_file()
+    ep = pd.read_csv(mdir / 'train_log' / 'system-test-train-logs-epoch.csv')
+    assert list(ep.columns) == ['epoch', 'time', 'mse', 'uq_loss', 'valid_mse', 'valid_uq_loss', 'valid_mse_fcst']
+    assert len(ep) == 2 and ep['mse'].iloc[1] < ep['mse'].iloc[0]            # it learns
+    bt = pd.read_csv(mdir / 'train_log' / 'system-test-train-logs-batch.csv')
+    assert list(bt.columns) == ['batch_n', 'time', 'mse', 'uq_loss', 'valid_mse', 'valid_uq_loss']
+    w = np.load(mdir / 'chkpts' / 'chkpt.lfmq.npz')
+    assert set(orc.param_names(1)) <= set(w.files) and w['lstm_1/kernel'].shape == (32, 256)
+    assert np.linalg.norm(w['lstm_1/kernel'], axis=0).max() <= 3.0 * (1 + 1e-5)   # MaxNorm held
+
+    configs.reset()
+    df = cli.main(['--config=' + conf, '--train=False'])
+    out = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
+    cols = list(out.columns)
+    assert cols[:3] == PRED_COLS_HEAD and cols[-10:] == PRED_COLS_TAIL
+    assert cols[3:-10] == ['inp_t%d' % t for t in range(-19, 1)]
+    assert len(out) == len(df) > 100
+    assert np.isfinite(out['norm_preds_1']).all() and np.isfinite(out['preds_1']).all()
+    known = out['targets_1'].notna()
+    assert known.any() and (~known).any()            # windows at the end of the file have no target yet
+    assert (out.loc[known, 'norm_squared_diff_1'] >= 0).all()
+    configs.reset()
+
+
+def test_dataset_get_batch_matches_oracle(workdir):
+    from lfm_quant_b200.scripts import base_config
+    from lfm_quant_b200.scripts.data_processing import Dataset
+    conf = str(workdir / 'config' / 'system-test.conf')
+    for extra, train in ((['--model_dir', 'gb-train'], True), (['--model_dir', 'gb-train', '--train=False'], False)):
+        configs.reset()
+        c = base_config.get_configs(['--config=' + conf, '--aux_masking'] + extra)
+        ds = Dataset(c)
+        ds.generate_dataset()
+        s = ds.train_set if train else ds.test_set
+        inp_idx, tar_idx, meta = next(iter(s.batch(97)))
+        x, y, md = ds.get_batch(inp_idx, tar_idx, meta)
+        valid = np.array([m[1] == m[2] for m in meta])
+        ref = orc.gather_batch(ds.table, inp_idx, tar_idx, valid, seq_len=ds.seq_len, stride=c.stride,
+                               inp_cols=ds.inp_col_ids, fin_cols=ds.fin_col_ids, seq_norm_col=ds._seq_norm_idx,
+                               center=np.asarray(ds.scaling_params['center']), scale=np.asarray(ds.scaling_params['scale']),
+                               scale_inp_ids=ds.scale_inp_col_ids, aux_inp_ids=ds._aux_col_ids_seq, log_squash=True,
+                               aux_masking=True, train=train)
+        np.testing.assert_array_max_ulp(x.cpu().numpy(), ref[0], maxulp=1)
+        np.testing.assert_array_equal(np.isnan(y.cpu().numpy()), np.isnan(ref[1]))
+        np.testing.assert_array_max_ulp(np.nan_to_num(y.cpu().numpy()), np.nan_to_num(ref[1]), maxulp=1)
+        np.testing.assert_array_equal(md[:, 2].astype(np.float64), ref[2])
+        assert (x.cpu().numpy()[:, :-1, 16:] == 0).all()          # aux masking
+    configs.reset()
