@@ -461,10 +461,12 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(int B, int T, int O, con
 __global__ void loss_final_kernel(int nblk, const double* __restrict__ partial, const float* __restrict__ denom,
                                   int B, int O, float p1, float p2, int mode, float* __restrict__ out,
                                   float* __restrict__ maskout) {
-  if (threadIdx.x != 0) return;
+  // one warp, fixed summation order (lane-strided then butterfly): deterministic
   double s[4] = {0, 0, 0, 0};
-  for (int b = 0; b < nblk; ++b)
+  for (int b = threadIdx.x; b < nblk; b += 32)
     for (int i = 0; i < 4; ++i) s[i] += partial[(long)b * 4 + i];
+  for (int i = 0; i < 4; ++i) s[i] = warp_sum(s[i]);
+  if (threadIdx.x != 0) return;
   if (maskout) {
     maskout[0] = (float)B;
     maskout[1] = (float)s[3];
@@ -512,9 +514,10 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(long n, const float*
 
 __global__ void norm_final_kernel(int nblk, const double* __restrict__ partial, float clip,
                                   float* __restrict__ scalars) {
-  if (threadIdx.x != 0) return;
   double s = 0;
-  for (int b = 0; b < nblk; ++b) s += partial[(long)b * 4];
+  for (int b = threadIdx.x; b < nblk; b += 32) s += partial[(long)b * 4];
+  s = warp_sum(s);
+  if (threadIdx.x != 0) return;
   const float gn = (float)sqrt(s);
   scalars[0] = gn;
   scalars[1] = (clip > 0.f) ? clip / fmaxf(gn, clip) : 1.0f;

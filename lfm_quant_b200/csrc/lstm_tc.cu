@@ -5,8 +5,9 @@
 //   xh    bf16 [maxB][T+1][384]   row (b,t): cols 0..255 = h_{t-1} (zero at t=0), 256..287 = x_t, 288 = 1.0 (t<T),
 //                                 rest 0.  One buffer serves: the A operand of the forward recurrence (K-major
 //                                 tiles via TMA), the head (h_t = row t+1) and the weight-gradient GEMM (MN-major).
-//   gates bf16 [maxB][T][4H]      post-activation i|f|g|o, saved for BPTT
-//   cst   f32  [maxB][T][H]       cell states
+//   gates bf16 [T][tiles][8][128][4*32]  post-activation i|f|g|o saved for BPTT, one contiguous 32 KB block per
+//                                 (step, 128-row tile, forward CTA rank): DRAM-page-friendly writes and reads
+//   cst   f32  [T][tiles][8][128][32]    cell states, same blocking
 //   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
 //   dhout bf16 [maxB][T][H]       dLoss/dh from the head (after BN/dropout backward)
 //
@@ -82,37 +83,47 @@ struct TcImpl {
   // parameter offsets in the flat fp32 vector (L = 1)
   int64_t oW, oU, ob, ogamma, obeta, oWo, obo, omean, ovar;
   // workspace
-  __nv_bfloat16 *xh, *gates, *dz, *dhout, *Up, *Wp, *Ub;
+  __nv_bfloat16 *xh, *gates, *dz, *dhout, *Up, *Wp, *Ubk, *pexch;
   float *cst, *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
-  CUtensorMap tm_dz_k, tm_ub;                  // backward step (K-major)
+  CUtensorMap tm_ubk, tm_px;                   // backward recurrence
   CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
-  int max_clusters = 0;
+  int max_clusters = 0, bwd_max_clusters = 0;
+  bool bwd_ready = false;
   int head_ctas = 0, head_wctas = 0;
 };
 
 // =============================================================================================
 // Small packing / cast kernels
 // =============================================================================================
-// x f32 [B,T,F] -> xh[b][t][256 .. 256+F), plus the constant-one column.
+// x f32 [B,T,F] -> xh[b][t][256 .. 256+F), plus the constant-one column.  One 16-byte chunk per thread.
 __global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ x, __nv_bfloat16* __restrict__ xh) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (b,t)
-  if (idx >= (long)B * T) return;
-  const long b = idx / T;
-  const int t = (int)(idx % T);
-  const float* xr = x + idx * F;
-  __nv_bfloat16* dst = xh + (b * (T + 1) + t) * TC_XH_LD + TC_XOFF;
-  for (int f = 0; f < 32; ++f) dst[f] = __float2bfloat16(f < F ? xr[f] : 0.f);
-  dst[TC_ONE - TC_XOFF] = __float2bfloat16(1.0f);
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, chunk) with 5 chunks of 8 columns per row
+  if (idx >= (long)B * T * 5) return;
+  const long row = idx / 5;
+  const int c = (int)(idx % 5);
+  const long b = row / T;
+  const int t = (int)(row % T);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int f = c * 8 + e;
+    v[e] = (f < F) ? x[row * F + f] : ((f == TC_ONE - TC_XOFF) ? 1.0f : 0.f);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(xh + (b * (T + 1) + t) * TC_XH_LD + TC_XOFF + c * 8) = o;
 }
 
 // Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 32r+j is row n = 32g+j of
 // slice r; the three sigmoid gates are pre-scaled by 0.5 (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
 __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const float* __restrict__ U,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ Up,
-                                    __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp,
-                                    __nv_bfloat16* __restrict__ Ub) {
+                                    __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp) {
   const int H = TC_H;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < (long)4 * H * H) {          // Up: [8][128][256]
@@ -122,8 +133,6 @@ __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const fl
     const int g = n / TC_HS, j = n % TC_HS;
     const float sc = (g == 2) ? 1.0f : 0.5f;
     Up[idx] = __float2bfloat16(sc * U[(long)k * 4 * H + g * H + r * TC_HS + j]);
-    // Ub: plain bf16 copy of U [H][4H] (B operand of the backward recurrence)
-    Ub[idx] = __float2bfloat16(U[idx]);
   }
   if (idx < (long)4 * H * 32) {         // Wp: [8][128][32]
     const int k = (int)(idx % 32);
@@ -144,7 +153,7 @@ __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const fl
 // Persistent forward recurrence
 // =============================================================================================
 struct FwdParams {
-  int B, T, n_iters, n_clusters, k16_x;
+  int B, T, n_iters, n_clusters, k16_x, n_tiles_cap;
   __nv_bfloat16* xh;
   __nv_bfloat16* gates;   // null: do not save
   float* cst;             // null: do not save
@@ -291,7 +300,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     const bool leader = ((warp - 3) % 4 == 0) && lane == 0;
     float cstate[TC_HS];
     for (int it = 0; it < p.n_iters; ++it) {
-      const long b = (long)((it * p.n_clusters + cid) * TC_NCH + c) * 128 + m;
+      const int tile_c = (it * p.n_clusters + cid) * TC_NCH + c;
+      const long b = (long)tile_c * 128 + m;
       const bool valid = b < p.B;
 #pragma unroll
       for (int j = 0; j < TC_HS; ++j) cstate[j] = 0.f;
@@ -302,8 +312,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         tcgen05_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 256 + (g & 1) * 128;
         __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + rank * TC_HS;
-        __nv_bfloat16* grow = p.gates ? p.gates + (b * T + t) * 4 * TC_H + rank * TC_HS : nullptr;
-        float* crow = p.cst ? p.cst + (b * T + t) * TC_H + rank * TC_HS : nullptr;
+        const long blk = (((long)t * p.n_tiles_cap + tile_c) * TC_NC + rank) * 128 + m;   // saved-state block row
+        __nv_bfloat16* grow = p.gates ? p.gates + blk * (4 * TC_HS) : nullptr;
+        float* crow = p.cst ? p.cst + blk * TC_HS : nullptr;
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           uint32_t vi[16], vf[16], vg[16], vo[16];
@@ -340,9 +351,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             st_global_v8(hrow + jb * 16, ph);
             if (grow) {
               st_global_v8(grow + jb * 16, pi);
-              st_global_v8(grow + TC_H + jb * 16, pf);
-              st_global_v8(grow + 2 * TC_H + jb * 16, pg);
-              st_global_v8(grow + 3 * TC_H + jb * 16, po);
+              st_global_v8(grow + TC_HS + jb * 16, pf);
+              st_global_v8(grow + 2 * TC_HS + jb * 16, pg);
+              st_global_v8(grow + 3 * TC_HS + jb * 16, po);
             }
             if (crow) {
               st_global_v8f(crow + jb * 16, cn);
@@ -749,25 +760,27 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   m.xh = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * TC_XH_LD * 2));
   m.Up = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.Wp = reinterpret_cast<__nv_bfloat16*>(take(4 * H * 32 * 2));
-  m.Ub = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
+  m.Ubk = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
   m.head_ctas = 148;
   m.head_wctas = 148 * 2;
   m.head_part_elems = (size_t)m.head_ctas * HEAD_PART;
   m.head_part = reinterpret_cast<float*>(take(m.head_part_elems * 4));
   if (!c.forward_only) {
-    m.gates = reinterpret_cast<__nv_bfloat16*>(take(B * T * 4 * H * 2));
-    m.cst = reinterpret_cast<float*>(take(B * T * H * 4));
+    const size_t Bt = (B + 127) / 128 * 128;      // saved state is blocked by 128-row tiles
+    m.gates = reinterpret_cast<__nv_bfloat16*>(take(Bt * T * 4 * H * 2));
+    m.cst = reinterpret_cast<float*>(take(Bt * T * H * 4));
     m.dz = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * 4 * H * 2));
     m.dhout = reinterpret_cast<__nv_bfloat16*>(take(B * T * H * 2));
-    m.dc = reinterpret_cast<float*>(take(B * H * 4));
+    m.dc = nullptr;
+    m.pexch = reinterpret_cast<__nv_bfloat16*>(take(((B + 127) / 128) * 2 * 16 * 128 * 64 * 2));
     m.dpred = reinterpret_cast<float*>(take(B * T * TC_OPAD * 4));
     m.head_wpart = reinterpret_cast<float*>(take((size_t)m.head_wctas * HWG_PART * 4));
     m.wg_part_elems = (size_t)64 * 384 * 1024;
     m.wg_part = reinterpret_cast<float*>(take(m.wg_part_elems * 4));
   } else {
     m.gates = nullptr; m.cst = nullptr; m.dz = nullptr; m.dhout = nullptr; m.dc = nullptr; m.wg_part = nullptr;
-    m.dpred = nullptr; m.head_wpart = nullptr;
+    m.dpred = nullptr; m.head_wpart = nullptr; m.pexch = nullptr;
     m.wg_part_elems = 0;
   }
   const int64_t I = c.n_inputs, O = c.n_outputs;
@@ -792,11 +805,6 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if (m.dz) {
-    const uint64_t dz_row = (uint64_t)(T + 1) * 4 * TC_H;
-    if ((rc = make_map_2d(&m.tm_dz_k, m.dz, dz_row, B, dz_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_map_2d(&m.tm_ub, m.Ub, 4 * TC_H, TC_H, 4 * TC_H * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  }
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   // how many 8-CTA clusters can be co-resident (one CTA per SM because of shared memory)
   cudaLaunchConfig_t cfg = {};
@@ -827,20 +835,26 @@ void tc_destroy(TcState& st) {
   st.impl = nullptr;
 }
 
+__global__ void pack_ubk_kernel(const float* __restrict__ U, __nv_bfloat16* __restrict__ Ubk);
+
 static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   TcImpl& m = *st.impl;
   if (!st.weights_dirty) return 0;
   const long n = (long)4 * TC_H * TC_H;
   pack_weights_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(m.I, params + m.oW, params + m.oU, params + m.ob, m.Up,
-                                                           m.Wp, m.biasp, m.Ub);
+                                                           m.Wp, m.biasp);
   LFMQ_LAUNCH_CHECK();
+  if (m.pexch) {   // training handle: K-slices of U for the backward recurrence
+    pack_ubk_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(params + m.oU, m.Ubk);
+    LFMQ_LAUNCH_CHECK();
+  }
   st.weights_dirty = 0;
   return 0;
 }
 
 static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cudaStream_t s) {
   TcImpl& m = *st.impl;
-  const long bt = (long)B * m.T;
+  const long bt = (long)B * m.T * 5;
   xh_fill_x_kernel<<<(int)((bt + 255) / 256), 256, 0, s>>>(B, m.T, m.I, x, m.xh);
   LFMQ_LAUNCH_CHECK();
   const int n_tiles = (B + 127) / 128;
@@ -850,6 +864,7 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   p.n_clusters = n_pairs < m.max_clusters ? n_pairs : m.max_clusters;
   p.n_iters = (n_pairs + p.n_clusters - 1) / p.n_clusters;
   p.k16_x = (m.I + 15) / 16;
+  p.n_tiles_cap = (m.maxB + 127) / 128;
   p.xh = m.xh;
   p.gates = save ? m.gates : nullptr;
   p.cst = save ? m.cst : nullptr;
@@ -979,172 +994,289 @@ int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* g
 }  // namespace lfmq
 
 // =============================================================================================
-// Backward recurrence, one launch per time step (reverse t):
-//   dh_rec[128 x 64] = dz_{t+1}[128 x 1024] * U[64 slice][1024]^T      tcgen05, TMA ring over K
-//   dz_t = gate-gradient(dh_out_t + dh_rec, saved gates, c_t, c_{t-1}, dc)   fused epilogue
-// grid = (H/64, row tiles).  A = dz rows of step t+1 (K-major, the [B, T+1, 4H] buffer), B = bf16 copy of U.
+// Persistent backward recurrence (reverse t inside the kernel), clusters of 4 CTAs per 128-row tile.
+//   CTA r owns hidden units [64r, 64r+64): it computes dz_t for its 256 gate columns (pointwise),
+//   keeps them as the A operand in shared memory and multiplies by ITS K-slice of U (resident for the whole unroll):
+//       partial_r[128 x 256] = dz_t[:, own 256 gate cols] * U[all 256 hidden, own gate cols]^T       (tcgen05)
+//   dh_{t-1}[:, slice q] = sum_r partial_r[:, slice q]: the three foreign 128x64 slices travel as bf16 through a
+//   global scratch (written with STG.256, fetched with TMA) -- a reduce-scatter whose volume (48 KB in per CTA and
+//   step) is 5x smaller than all-gathering dz; DSMEM would cost ~3700 cycles for it (profiles/r01_tc_probe.txt).
+//   K order inside the slice: k' = 64*jb + 16*g + jj  <->  gate column g*H + 64r + 16*jb + jj, so hidden chunk jb
+//   (16 units x 4 gates) is one 64-wide k-block and its MMAs overlap the pointwise work of chunk jb+1.
 // =============================================================================================
 namespace lfmq {
 
-struct BwdStepParams {
-  int B, T, t;
+struct BwdParams {
+  int B, T, n_iters, n_clusters, n_tiles_cap;
   const __nv_bfloat16* gates;
   const float* cst;
   const __nv_bfloat16* dhout;
-  float* dc;
   __nv_bfloat16* dz;
+  __nv_bfloat16* pexch;      // [tile][parity][src][dst][128][64]
 };
 
+constexpr int BWD_NC = 4;
 constexpr int BWD_THREADS = 192;
-constexpr int BWD_STAGES = 6;
-constexpr uint32_t BWD_STAGE_BYTES = 16384 + 8192;
-constexpr uint32_t BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
+constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
+constexpr uint32_t SB_R = 163840;               // 3 foreign slices x [128 x 128 B]
+constexpr uint32_t SB_BARS = 212992;
+constexpr uint32_t BWD_SMEM = SB_BARS + 256 + 1024;
+
+struct BwdBars {
+  uint64_t w_full, a_full[2], a_empty[2], acc_full[2], recv_full, recv_free, exp_ready;
+  uint32_t tmem_base;
+};
+
+// Ubk[r][n][k'] = U[n][g*H + 64r + 16jb + jj], k' = 64jb + 16g + jj
+__global__ void pack_ubk_kernel(const float* __restrict__ U, __nv_bfloat16* __restrict__ Ubk) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)4 * TC_H * TC_H) return;
+  const int kp = (int)(idx % 256);
+  const int n = (int)((idx / 256) % TC_H);
+  const int r = (int)(idx / (256 * TC_H));
+  const int jb = kp / 64, g = (kp % 64) / 16, jj = kp % 16;
+  Ubk[idx] = __float2bfloat16(U[(long)n * 4 * TC_H + g * TC_H + 64 * r + 16 * jb + jj]);
+}
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-    lstm_bwd_step_tc_kernel(BwdStepParams p, const __grid_constant__ CUtensorMap tm_dz,
-                            const __grid_constant__ CUtensorMap tm_ub) {
+    lstm_bwd_tc_kernel(BwdParams p, const __grid_constant__ CUtensorMap tm_ubk,
+                       const __grid_constant__ CUtensorMap tm_px) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + BWD_STAGES * BWD_STAGE_BYTES);
-  uint64_t* empty = full + BWD_STAGES;
-  uint64_t* acc_full = empty + BWD_STAGES;
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
+  BwdBars* bars = reinterpret_cast<BwdBars*>(smem + SB_BARS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * 64;            // hidden slice
-  const int b0 = blockIdx.y * 128;
-  const bool has_gemm = p.t < p.T - 1;
-  constexpr int NKB = 4 * TC_H / 64;         // 16 k-blocks over the 1024 gate columns
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x / BWD_NC;
+  const int T = p.T;
 
   if (tid == 0) {
-    for (int s = 0; s < BWD_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    mbar_init(&bars->w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->a_full[i], 128);
+      mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->acc_full[i], 1);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(&bars->recv_full, 1);
+    mbar_init(&bars->recv_free, 1);
+    mbar_init(&bars->exp_ready, BWD_NC - 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_s, 64);
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_base_s;
+  const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0 && has_gemm) {
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int s = kb % BWD_STAGES;
-        if (kb >= BWD_STAGES) mbar_wait(&empty[s], ((kb / BWD_STAGES) - 1) & 1);
-        mbar_arrive_expect_tx(&full[s], BWD_STAGE_BYTES);
-        tma_load_2d(smem + s * BWD_STAGE_BYTES, &tm_dz, &full[s], (p.t + 1) * 4 * TC_H + kb * 64, b0);
-        tma_load_2d(smem + s * BWD_STAGE_BYTES + 16384, &tm_ub, &full[s], kb * 64, n0);
+    // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->w_full, 131072);
+      for (int jb = 0; jb < 4; ++jb) tma_load_2d(smem + SB_U + jb * 32768, &tm_ubk, &bars->w_full, jb * 64, rank * 256);
+      uint32_t n_er = 0;
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int tile = it * p.n_clusters + cid;
+        for (int t = T - 2; t >= 0; --t) {           // step t consumes the partials exported after step t+1
+          mbar_wait_cluster(&bars->exp_ready, (n_er) & 1);
+          mbar_wait(&bars->recv_free, (n_er++) & 1);    // own epilogue is done reading the previous slices
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(&bars->recv_full, 3 * 16384);
+          const int par = (t + 1) & 1;
+          for (uint32_t d = 1; d < BWD_NC; ++d) {
+            const uint32_t src = (rank + d) & 3;
+            tma_load_2d(smem + SB_R + (d - 1) * 16384, &tm_px, &bars->recv_full, 0,
+                        ((((tile * 2 + par) * 4 + (int)src) * 4 + (int)rank)) * 128);
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_gemm) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, false, false);
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int s = kb % BWD_STAGES;
-        mbar_wait(&full[s], (kb / BWD_STAGES) & 1);
-        tcgen05_fence_after();
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256, false, false);
+      mbar_wait(&bars->w_full, 0);
+      uint32_t q = 0;       // global chunk counter
+      uint32_t gs = 0;      // global step counter
+      for (int it = 0; it < p.n_iters; ++it) {
+        for (int t = T - 1; t >= 0; --t, ++gs) {
+          const uint32_t acc = tmem + (gs & 1) * 256;
+          for (int jb = 0; jb < 4; ++jb, ++q) {
+            const uint32_t st = q & 1;
+            mbar_wait(&bars->a_full[st], (q >> 1) & 1);
+            tcgen05_fence_after();
 #pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          const uint64_t da = make_smem_desc(smem_u32(smem + s * BWD_STAGE_BYTES) + k16 * 32, 0, 1024, LAYOUT_SW128);
-          const uint64_t db =
-              make_smem_desc(smem_u32(smem + s * BWD_STAGE_BYTES + 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
-          umma_f16(tmem, da, db, idesc, (kb | k16) != 0);
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint64_t da = make_smem_desc(smem_u32(smem + SB_A + st * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+              const uint64_t db = make_smem_desc(smem_u32(smem + SB_U + jb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
+              umma_f16(acc, da, db, idesc, (jb | k16) != 0);
+            }
+            umma_commit(&bars->a_empty[st]);
+          }
+          umma_commit(&bars->acc_full[gs & 1]);
         }
-        umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const long b = (long)b0 + m;
-    const bool valid = b < p.B;
-    if (has_gemm) {
-      mbar_wait(acc_full, 0);
-      tcgen05_fence_after();
-    }
-    const long rt = b * p.T + p.t;                       // row index in [B,T,*] buffers
-    const __nv_bfloat16* grow = p.gates + rt * 4 * TC_H + n0;
-    const float* crow = p.cst + rt * TC_H + n0;
-    const __nv_bfloat16* dhrow = p.dhout + rt * TC_H + n0;
-    float* dcrow = p.dc + b * TC_H + n0;
-    __nv_bfloat16* dzrow = p.dz + (b * (p.T + 1) + p.t) * 4 * TC_H + n0;
-#pragma unroll 1
-    for (int jb = 0; jb < 4; ++jb) {
-      uint32_t vr[16];
-      if (has_gemm) {
-        tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + jb * 16, vr);
-        tmem_ld_wait();
-      } else {
+    // ===================== pointwise gate gradients, A-operand staging, partial exchange =====================
+    const int wq = warp & 3;                 // TMEM lane quadrant
+    const int m = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    float dc[64];
+    uint32_t q = 0, gs = 0, n_rf = 0;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int tile = it * p.n_clusters + cid;
+      const long b = (long)tile * 128 + m;
+      const bool valid = b < p.B;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) vr[j] = 0u;
-      }
-      if (!valid) continue;
-      uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
-      ld_global_v8(grow + jb * 16, gi);
-      ld_global_v8(grow + TC_H + jb * 16, gf);
-      ld_global_v8(grow + 2 * TC_H + jb * 16, gg);
-      ld_global_v8(grow + 3 * TC_H + jb * 16, go);
-      ld_global_v8(dhrow + jb * 16, dhp);
-      float ct[16], cp[16], dcv[16];
-      ld_global_v8f(crow + jb * 16, ct);
-      ld_global_v8f(crow + jb * 16 + 8, ct + 8);
-      if (p.t > 0) {
-        ld_global_v8f(crow - TC_H + jb * 16, cp);
-        ld_global_v8f(crow - TC_H + jb * 16 + 8, cp + 8);
-      } else {
+      for (int j = 0; j < 64; ++j) dc[j] = 0.f;
+      for (int t = T - 1; t >= 0; --t, ++gs) {
+        const bool has_rec = t < T - 1;
+        const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
+        if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
+        const long rt = b * T + t;
+        const long blk0 = (((long)t * p.n_tiles_cap + tile) * 8 + 2 * rank) * 128 + m;     // forward rank 2r (+1: +128 rows)
+        const long tstride = (long)p.n_tiles_cap * 8 * 128;                               // block rows per time step
+        const __nv_bfloat16* dhrow = p.dhout + rt * TC_H + rank * 64;
+        __nv_bfloat16* dzrow = p.dz + (b * (T + 1) + t) * 4 * TC_H + rank * 64;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-      }
-      if (has_gemm) {
-        ld_global_v8f(dcrow + jb * 16, dcv);
-        ld_global_v8f(dcrow + jb * 16 + 8, dcv + 8);
-      } else {
+        for (int jb = 0; jb < 4; ++jb, ++q) {
+          uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
+          float ct[16], cp[16];
+          if (valid) {
+            const long blk = blk0 + (jb >> 1) * 128;
+            const __nv_bfloat16* grow = p.gates + blk * 128 + (jb & 1) * 16;
+            const float* crow = p.cst + blk * 32 + (jb & 1) * 16;
+            ld_global_v8(grow, gi);
+            ld_global_v8(grow + 32, gf);
+            ld_global_v8(grow + 64, gg);
+            ld_global_v8(grow + 96, go);
+            ld_global_v8(dhrow + jb * 16, dhp);
+            ld_global_v8f(crow, ct);
+            ld_global_v8f(crow + 8, ct + 8);
+            if (t > 0) {
+              ld_global_v8f(crow - tstride * 32, cp);
+              ld_global_v8f(crow - tstride * 32 + 8, cp + 8);
+            } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dcv[j] = 0.f;
-      }
-      uint32_t zi[8], zf[8], zg[8], zo[8];
-      float dcn_out[16];
+              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+            }
+          } else {
 #pragma unroll
-      for (int jj = 0; jj < 16; jj += 2) {
-        float ri[2], rf[2], rg[2], ro[2];
+            for (int j = 0; j < 8; ++j) gi[j] = gf[j] = gg[j] = go[j] = dhp[j] = 0u;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = jj + u;
-          const float i_ = u ? bf16_hi(gi[jj / 2]) : bf16_lo(gi[jj / 2]);
-          const float f_ = u ? bf16_hi(gf[jj / 2]) : bf16_lo(gf[jj / 2]);
-          const float g_ = u ? bf16_hi(gg[jj / 2]) : bf16_lo(gg[jj / 2]);
-          const float o_ = u ? bf16_hi(go[jj / 2]) : bf16_lo(go[jj / 2]);
-          const float dh = (u ? bf16_hi(dhp[jj / 2]) : bf16_lo(dhp[jj / 2])) + __uint_as_float(vr[j]);
-          const float tc = tanh_approx(ct[j]);
-          const float d_o = dh * tc;
-          const float dcn = dcv[j] + dh * o_ * (1.f - tc * tc);
-          ri[u] = dcn * g_ * i_ * (1.f - i_);
-          rf[u] = dcn * cp[j] * f_ * (1.f - f_);
-          rg[u] = dcn * i_ * (1.f - g_ * g_);
-          ro[u] = d_o * o_ * (1.f - o_);
-          dcn_out[j] = dcn * f_;
+            for (int j = 0; j < 16; ++j) ct[j] = cp[j] = 0.f;
+          }
+          float rec[16];
+          if (has_rec) {
+            uint32_t vr[16];
+            tmem_ld_32x32b_x16(acc_prev + lane_addr + rank * 64 + jb * 16, vr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rec[j] = __uint_as_float(vr[j]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const uint8_t* rs = smem + SB_R + d * 16384 + m * 128;
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rs + (((2 * jb + h2) ^ (m & 7)) << 4));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  rec[8 * h2 + 2 * e] += bf16_lo(w[e]);
+                  rec[8 * h2 + 2 * e + 1] += bf16_hi(w[e]);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rec[j] = 0.f;
+          }
+          uint32_t zi[8], zf[8], zg[8], zo[8];
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            float ri[2], rf[2], rg[2], ro[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = jj + u;
+              const float i_ = u ? bf16_hi(gi[jj / 2]) : bf16_lo(gi[jj / 2]);
+              const float f_ = u ? bf16_hi(gf[jj / 2]) : bf16_lo(gf[jj / 2]);
+              const float g_ = u ? bf16_hi(gg[jj / 2]) : bf16_lo(gg[jj / 2]);
+              const float o_ = u ? bf16_hi(go[jj / 2]) : bf16_lo(go[jj / 2]);
+              const float dh = (u ? bf16_hi(dhp[jj / 2]) : bf16_lo(dhp[jj / 2])) + rec[j];
+              const float tc = tanh_approx(ct[j]);
+              const float d_o = dh * tc;
+              const float dcn = dc[jb * 16 + j] + dh * o_ * (1.f - tc * tc);
+              ri[u] = dcn * g_ * i_ * (1.f - i_);
+              rf[u] = dcn * cp[j] * f_ * (1.f - f_);
+              rg[u] = dcn * i_ * (1.f - g_ * g_);
+              ro[u] = d_o * o_ * (1.f - o_);
+              dc[jb * 16 + j] = dcn * f_;
+            }
+            zi[jj / 2] = pack_bf16x2(ri[0], ri[1]);
+            zf[jj / 2] = pack_bf16x2(rf[0], rf[1]);
+            zg[jj / 2] = pack_bf16x2(rg[0], rg[1]);
+            zo[jj / 2] = pack_bf16x2(ro[0], ro[1]);
+          }
+          if (valid) {
+            st_global_v8(dzrow + jb * 16, zi);
+            st_global_v8(dzrow + TC_H + jb * 16, zf);
+            st_global_v8(dzrow + 2 * TC_H + jb * 16, zg);
+            st_global_v8(dzrow + 3 * TC_H + jb * 16, zo);
+          }
+          // A operand k-block jb: row m, chunk 2g+h holds gate g, units 8h..8h+7 (128B-swizzled K-major tile)
+          const uint32_t st = q & 1;
+          if (q >= 2) mbar_wait(&bars->a_empty[st], ((q >> 1) - 1) & 1);
+          uint8_t* arow = smem + SB_A + st * 16384 + m * 128;
+          const int sw = m & 7;
+          *reinterpret_cast<uint4*>(arow + ((0 ^ sw) << 4)) = make_uint4(zi[0], zi[1], zi[2], zi[3]);
+          *reinterpret_cast<uint4*>(arow + ((1 ^ sw) << 4)) = make_uint4(zi[4], zi[5], zi[6], zi[7]);
+          *reinterpret_cast<uint4*>(arow + ((2 ^ sw) << 4)) = make_uint4(zf[0], zf[1], zf[2], zf[3]);
+          *reinterpret_cast<uint4*>(arow + ((3 ^ sw) << 4)) = make_uint4(zf[4], zf[5], zf[6], zf[7]);
+          *reinterpret_cast<uint4*>(arow + ((4 ^ sw) << 4)) = make_uint4(zg[0], zg[1], zg[2], zg[3]);
+          *reinterpret_cast<uint4*>(arow + ((5 ^ sw) << 4)) = make_uint4(zg[4], zg[5], zg[6], zg[7]);
+          *reinterpret_cast<uint4*>(arow + ((6 ^ sw) << 4)) = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+          *reinterpret_cast<uint4*>(arow + ((7 ^ sw) << 4)) = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+          fence_proxy_async_smem();
+          mbar_arrive(&bars->a_full[st]);
         }
-        zi[jj / 2] = pack_bf16x2(ri[0], ri[1]);
-        zf[jj / 2] = pack_bf16x2(rf[0], rf[1]);
-        zg[jj / 2] = pack_bf16x2(rg[0], rg[1]);
-        zo[jj / 2] = pack_bf16x2(ro[0], ro[1]);
+        // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
+        if (t > 0) {
+          mbar_wait(&bars->acc_full[gs & 1], (gs >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t acc = tmem + (gs & 1) * 256 + lane_addr;
+          const int par = t & 1;
+#pragma unroll
+          for (uint32_t d = 1; d < BWD_NC; ++d) {
+            const uint32_t dst = (rank + d) & 3;
+            __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(acc + dst * 64 + h2 * 32, v);
+              tmem_ld_wait();
+              uint32_t pk[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+              st_global_v8(out + h2 * 32, pk);
+              st_global_v8(out + h2 * 32 + 16, pk + 8);
+            }
+          }
+          tcgen05_fence_before();
+          named_bar_sync(1, 128);
+          if (warp == 2 && lane == 0) mbar_arrive(&bars->recv_free);
+          if (warp == 2 && lane >= 1 && lane < BWD_NC) {
+            __threadfence();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
+          }
+        }
       }
-      st_global_v8(dzrow + jb * 16, zi);
-      st_global_v8(dzrow + TC_H + jb * 16, zf);
-      st_global_v8(dzrow + 2 * TC_H + jb * 16, zg);
-      st_global_v8(dzrow + 3 * TC_H + jb * 16, zo);
-      st_global_v8f(dcrow + jb * 16, dcn_out);
-      st_global_v8f(dcrow + jb * 16 + 8, dcn_out + 8);
     }
   }
   __syncwarp();
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 64);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -1266,22 +1398,57 @@ __global__ void wgrad_reduce_kernel(int S, int I, const float* __restrict__ part
 
 int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, cudaStream_t s) {
   TcImpl& m = *st.impl;
-  static bool attrs_set = false;
-  if (!attrs_set) {
-    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+  int rc;
+  if (!m.bwd_ready) {
+    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     LFMQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-    attrs_set = true;
+    if ((rc = make_map_2d(&m.tm_ubk, m.Ubk, 256, 4 * TC_H, 512, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const uint64_t px_rows = (uint64_t)((m.maxB + 127) / 128) * 2 * 16 * 128;
+    if ((rc = make_map_2d(&m.tm_px, m.pexch, 64, px_rows, 128, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(BWD_NC * 37);
+    qc.blockDim = dim3(BWD_THREADS);
+    qc.dynamicSmemBytes = BWD_SMEM;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = BWD_NC;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int ncl = 0;
+    LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&ncl, lstm_bwd_tc_kernel, &qc));
+    if (ncl < 1) {
+      LFMQ_SET_ERR("no 4-CTA cluster of the backward kernel fits on this device");
+      return LFMQ_ERR_UNSUPPORTED;
+    }
+    m.bwd_max_clusters = ncl;
+    m.bwd_ready = true;
   }
   const size_t T = (size_t)m.T;
-  int rc;
   st.prof->begin(LFMQ_REGION_BWD, s);
-  BwdStepParams bp;
-  bp.B = B; bp.T = m.T; bp.gates = m.gates; bp.cst = m.cst; bp.dhout = m.dhout; bp.dc = m.dc; bp.dz = m.dz;
-  const dim3 bgrid(TC_H / 64, (B + 127) / 128);
-  for (int t = m.T - 1; t >= 0; --t) {
-    bp.t = t;
-    lstm_bwd_step_tc_kernel<<<bgrid, BWD_THREADS, BWD_SMEM, s>>>(bp, m.tm_dz_k, m.tm_ub);
-    LFMQ_LAUNCH_CHECK();
+  {
+    BwdParams bp;
+    const int n_tiles = (B + 127) / 128;
+    bp.B = B; bp.T = m.T;
+    bp.n_tiles_cap = (m.maxB + 127) / 128;
+    bp.n_clusters = n_tiles < m.bwd_max_clusters ? n_tiles : m.bwd_max_clusters;
+    bp.n_iters = (n_tiles + bp.n_clusters - 1) / bp.n_clusters;
+    bp.gates = m.gates; bp.cst = m.cst; bp.dhout = m.dhout; bp.dz = m.dz; bp.pexch = m.pexch;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(BWD_NC * bp.n_clusters);
+    cfg.blockDim = dim3(BWD_THREADS);
+    cfg.dynamicSmemBytes = BWD_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = BWD_NC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, bp, m.tm_ubk, m.tm_px));
+    g_launches++;
   }
   st.prof->end(LFMQ_REGION_BWD, s);
 
