@@ -34,10 +34,9 @@ using namespace sm100;
 namespace {
 
 constexpr int TC_H = 256;          // hidden units (bf16 path is specialised for H = 256)
-constexpr int TC_NC = 8;           // CTAs per cluster
-constexpr int TC_HS = 32;          // hidden units per CTA
-constexpr int TC_NSL = 128;        // gate columns per CTA
-constexpr int TC_NCH = 2;          // batch chains per cluster
+constexpr int TC_NC = 4;           // CTAs per forward cluster
+constexpr int TC_HS = 64;          // hidden units per forward CTA
+constexpr int TC_NSL = 256;        // gate columns per forward CTA
 constexpr int TC_XH_LD = 384;      // elements per xh row
 constexpr int TC_XOFF = 256;       // first x column inside an xh row
 constexpr int TC_ONE = 288;        // the constant-one column (db falls out of the weight-gradient GEMM)
@@ -119,14 +118,14 @@ __global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ 
   *reinterpret_cast<uint4*>(xh + (b * (T + 1) + t) * TC_XH_LD + TC_XOFF + c * 8) = o;
 }
 
-// Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 32r+j is row n = 32g+j of
+// Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 64r+j is row n = 64g+j of
 // slice r; the three sigmoid gates are pre-scaled by 0.5 (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
 __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const float* __restrict__ U,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ Up,
                                     __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp) {
   const int H = TC_H;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (long)4 * H * H) {          // Up: [8][128][256]
+  if (idx < (long)4 * H * H) {          // Up: [4][256][256]
     const int k = (int)(idx % H);
     const int n = (int)((idx / H) % TC_NSL);
     const int r = (int)(idx / ((long)H * TC_NSL));
@@ -134,7 +133,7 @@ __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const fl
     const float sc = (g == 2) ? 1.0f : 0.5f;
     Up[idx] = __float2bfloat16(sc * U[(long)k * 4 * H + g * H + r * TC_HS + j]);
   }
-  if (idx < (long)4 * H * 32) {         // Wp: [8][128][32]
+  if (idx < (long)4 * H * 32) {         // Wp: [4][256][32]
     const int k = (int)(idx % 32);
     const int n = (int)((idx / 32) % TC_NSL);
     const int r = (int)(idx / (32 * TC_NSL));
@@ -142,7 +141,7 @@ __global__ void pack_weights_kernel(int I, const float* __restrict__ W, const fl
     const float sc = (g == 2) ? 1.0f : 0.5f;
     Wp[idx] = __float2bfloat16(k < I ? sc * W[(long)k * 4 * H + g * H + r * TC_HS + j] : 0.f);
   }
-  if (idx < 4 * H) {                    // biasp: [8][128]
+  if (idx < 4 * H) {                    // biasp: [4][256]
     const int n = (int)(idx % TC_NSL), r = (int)(idx / TC_NSL);
     const int g = n / TC_HS, j = n % TC_HS;
     biasp[idx] = ((g == 2) ? 1.0f : 0.5f) * bias[g * H + r * TC_HS + j];
@@ -158,27 +157,28 @@ struct FwdParams {
   __nv_bfloat16* gates;   // null: do not save
   float* cst;             // null: do not save
   const float* biasp;
-  long long* trace;       // debug (LFMQ_TRACE_FWD=1): clock64 stamps of CTA 0, chain 0, first 16 steps
+  long long* trace;       // debug (LFMQ_TRACE_FWD=1): clock64 stamps of CTA 0, every third step
 };
 
 #define FWD_TRACE(role, t, pt)                                                        \
   do {                                                                                \
-    if (p.trace && blockIdx.x == 0 && (t) < 16) p.trace[((role) * 16 + (t)) * 8 + (pt)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && (t) % 3 == 0) p.trace[((role) * 16 + (t) / 3) * 8 + (pt)] = clock64(); \
   } while (0)
 
-constexpr int FWD_THREADS = 32 * (3 + 4 * TC_NCH);   // 2 producers + 1 MMA + 8 epilogue warps = 352
-constexpr uint32_t SM_U = 0;
-constexpr uint32_t SM_W = 65536;
-constexpr uint32_t SM_H0 = 73728;            // hbuf[c] = SM_H0 + c * 65536
-constexpr uint32_t SM_X0 = 204800;           // xbuf[c] = SM_X0 + c * 8192
+constexpr int FWD_EPI_WARPS = 8;                          // 4 TMEM lane quadrants x 2 column halves
+constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS);     // producer + MMA + epilogue = 320
+constexpr uint32_t SM_U = 0;                 // 4 k-blocks x [256 x 128 B]
+constexpr uint32_t SM_W = 131072;            // [256 x 64 B]
+constexpr uint32_t SM_H0 = 147456;           // 4 k-blocks x [128 x 128 B]
+constexpr uint32_t SM_X0 = 212992;           // [128 x 64 B]
 constexpr uint32_t SM_BIAS = 221184;
-constexpr uint32_t SM_BARS = 221696;
+constexpr uint32_t SM_BARS = 222208;
 constexpr uint32_t FWD_SMEM = SM_BARS + 256 + 1024;   // + alignment slack
 
 struct FwdBars {
-  uint64_t w_full;
-  uint64_t x_full[TC_NCH], x_empty[TC_NCH], h_full[TC_NCH], h_written[TC_NCH];
-  uint64_t acc_full[TC_NCH][2];
+  uint64_t w_full, x_full, x_empty, h_full, h_written;
+  uint64_t acc_full[2];
+  uint64_t acc_free;      // deferred saved-state stores have drained the staging TMEM buffer
   uint32_t tmem_base;
 };
 
@@ -195,18 +195,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
 
   if (tid == 0) {
     mbar_init(&bars->w_full, 1);
-    for (int c = 0; c < TC_NCH; ++c) {
-      mbar_init(&bars->x_full[c], 1);
-      mbar_init(&bars->x_empty[c], 1);
-      mbar_init(&bars->h_full[c], 1);
-      mbar_init(&bars->h_written[c], TC_NC);
-      mbar_init(&bars->acc_full[c][0], 1);
-      mbar_init(&bars->acc_full[c][1], 1);
-    }
+    mbar_init(&bars->x_full, 1);
+    mbar_init(&bars->x_empty, 1);
+    mbar_init(&bars->h_full, 1);
+    mbar_init(&bars->h_written, TC_NC);
+    mbar_init(&bars->acc_full[0], 1);
+    mbar_init(&bars->acc_full[1], 1);
+    mbar_init(&bars->acc_free, 32 * FWD_EPI_WARPS);
     fence_mbar_init();
   }
   if (tid < TC_NSL) bias_s[tid] = p.biasp[rank * TC_NSL + tid];
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();          // peers' barriers are initialised before anyone multicasts / arrives remotely
@@ -214,107 +213,103 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
   const uint32_t tmem = bars->tmem_base;
   const int T = p.T;
 
-  if (warp < TC_NCH) {
-    // ===================== TMA producer of chain `warp` =====================
+  if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      const int c = warp;
-      if (c == 0) {
-        mbar_arrive_expect_tx(&bars->w_full, 65536 + 8192);
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SM_U + kb * 16384, &tm_u, &bars->w_full, kb * 64, rank * TC_NSL);
-        tma_load_2d(smem + SM_W, &tm_w, &bars->w_full, 0, rank * TC_NSL);
-      }
-      uint8_t* hbuf = smem + SM_H0 + c * 65536;
-      uint8_t* xbuf = smem + SM_X0 + c * 8192;
+      mbar_arrive_expect_tx(&bars->w_full, 131072 + 16384);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SM_U + kb * 32768, &tm_u, &bars->w_full, kb * 64, rank * TC_NSL);
+      tma_load_2d(smem + SM_W, &tm_w, &bars->w_full, 0, rank * TC_NSL);
+      uint8_t* hbuf = smem + SM_H0;
+      uint8_t* xbuf = smem + SM_X0;
       uint32_t n_hw = 0, n_xe = 0;
       for (int it = 0; it < p.n_iters; ++it) {
-        const int b0 = ((it * p.n_clusters + cid) * TC_NCH + c) * 128;
+        const int b0 = (it * p.n_clusters + cid) * 128;
         for (int t = 0; t < T; ++t) {
-          if (it > 0 || t > 0) mbar_wait(&bars->x_empty[c], (n_xe++) & 1);
-          if (c == 0) FWD_TRACE(0, t, 0);
-          mbar_arrive_expect_tx(&bars->x_full[c], 8192);
-          tma_load_2d(xbuf, &tm_x, &bars->x_full[c], t * TC_XH_LD + TC_XOFF, b0);
+          if (it > 0 || t > 0) mbar_wait(&bars->x_empty, (n_xe++) & 1);
+          FWD_TRACE(0, t, 0);
+          mbar_arrive_expect_tx(&bars->x_full, 8192);
+          tma_load_2d(xbuf, &tm_x, &bars->x_full, t * TC_XH_LD + TC_XOFF, b0);
           if (t >= 1) {
-            mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);   // all 8 slices of h_{t-1} are in global memory
-            if (c == 0) FWD_TRACE(0, t, 1);
-            fence_proxy_async_all();
-            mbar_arrive_expect_tx(&bars->h_full[c], 65536);
+            mbar_wait_cluster(&bars->h_written, (n_hw++) & 1);   // all 4 slices of h_{t-1} are in global memory
+            FWD_TRACE(0, t, 1);
+            fence_proxy_async_global();
+            mbar_arrive_expect_tx(&bars->h_full, 65536);
             for (int kb = 0; kb < 4; ++kb)
-              tma_load_2d_mcast(hbuf + kb * 16384 + rank * 2048, &tm_h, &bars->h_full[c], t * TC_XH_LD + kb * 64,
-                                b0 + 16 * (int)rank, 0xFF);
-            if (c == 0) FWD_TRACE(0, t, 2);
+              tma_load_2d_mcast(hbuf + kb * 16384 + rank * 4096, &tm_h, &bars->h_full, t * TC_XH_LD + kb * 64,
+                                b0 + 32 * (int)rank, 0xF);
+            FWD_TRACE(0, t, 2);
           }
         }
-        mbar_wait_cluster(&bars->h_written[c], (n_hw++) & 1);       // phase of step T-1 (keeps parities aligned)
+        mbar_wait_cluster(&bars->h_written, (n_hw++) & 1);       // phase of step T-1 (keeps parities aligned)
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, TC_NSL, false, false);
       mbar_wait(&bars->w_full, 0);
-      uint32_t n_xf[TC_NCH] = {0, 0}, n_hf[TC_NCH] = {0, 0};
+      uint32_t n_xf = 0, n_hf = 0;
       for (int it = 0; it < p.n_iters; ++it) {
         for (int t = 0; t < T; ++t) {
           const uint32_t g = (uint32_t)(it * T + t);
-          for (int c = 0; c < TC_NCH; ++c) {
-            const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
-            mbar_wait(&bars->x_full[c], (n_xf[c]++) & 1);
-            if (c == 0) FWD_TRACE(1, t, 0);
-            tcgen05_fence_after();
-            for (int k16 = 0; k16 < p.k16_x; ++k16) {
-              const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0 + c * 8192) + k16 * 32, 0, 512, LAYOUT_SW64);
-              const uint64_t db = make_smem_desc(smem_u32(smem + SM_W) + k16 * 32, 0, 512, LAYOUT_SW64);
-              umma_f16(acc, da, db, idesc, k16 > 0);
-            }
-            umma_commit(&bars->x_empty[c]);
-            if (t == 0) umma_commit(&bars->acc_full[c][g & 1]);
+          const uint32_t acc = tmem + (g & 1) * 256;
+          mbar_wait(&bars->x_full, (n_xf++) & 1);
+          // training: acc[g&1] doubled as the staging buffer of step g-1's saved gates / cell states
+          if (p.gates && g > 0) mbar_wait(&bars->acc_free, (g - 1) & 1);
+          FWD_TRACE(1, t, 0);
+          tcgen05_fence_after();
+          for (int k16 = 0; k16 < p.k16_x; ++k16) {
+            const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0) + k16 * 32, 0, 512, LAYOUT_SW64);
+            const uint64_t db = make_smem_desc(smem_u32(smem + SM_W) + k16 * 32, 0, 512, LAYOUT_SW64);
+            umma_f16(acc, da, db, idesc, k16 > 0);
           }
-          if (t > 0) {
-            for (int c = 0; c < TC_NCH; ++c) {
-              const uint32_t acc = tmem + c * 256 + (g & 1) * 128;
-              mbar_wait(&bars->h_full[c], (n_hf[c]++) & 1);
-              if (c == 0) FWD_TRACE(1, t, 1);
-              tcgen05_fence_after();
+          umma_commit(&bars->x_empty);
+          if (t == 0) {
+            umma_commit(&bars->acc_full[g & 1]);
+          } else {
+            mbar_wait(&bars->h_full, (n_hf++) & 1);
+            FWD_TRACE(1, t, 1);
+            tcgen05_fence_after();
 #pragma unroll
-              for (int kb = 0; kb < 4; ++kb)
+            for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  const uint64_t da = make_smem_desc(smem_u32(smem + SM_H0 + c * 65536 + kb * 16384) + k16 * 32, 0,
-                                                     1024, LAYOUT_SW128);
-                  const uint64_t db =
-                      make_smem_desc(smem_u32(smem + SM_U + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
-                  umma_f16(acc, da, db, idesc, 1);
-                }
-              umma_commit(&bars->acc_full[c][g & 1]);
-              if (c == 0) FWD_TRACE(1, t, 2);
-            }
+              for (int k16 = 0; k16 < 4; ++k16) {
+                const uint64_t da = make_smem_desc(smem_u32(smem + SM_H0 + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+                const uint64_t db = make_smem_desc(smem_u32(smem + SM_U + kb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
+                umma_f16(acc, da, db, idesc, 1);
+              }
+            umma_commit(&bars->acc_full[g & 1]);
+            FWD_TRACE(1, t, 2);
           }
         }
       }
     }
   } else {
     // ===================== epilogue: gates, cell update, h exchange =====================
-    const int c = (warp - 3) / 4;
+    const int half = (warp - 2) / 4;        // which 32 of this CTA's 64 hidden units
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int m = q * 32 + lane;            // row of the 128-row tile
-    const bool leader = ((warp - 3) % 4 == 0) && lane == 0;
-    float cstate[TC_HS];
+    const bool leader = (warp == 2) && lane == 0;
+    const int fr = 2 * (int)rank + half;    // 32-unit block index (saved-state layout, hidden offset 32*fr)
+    float cstate[32];
     for (int it = 0; it < p.n_iters; ++it) {
-      const int tile_c = (it * p.n_clusters + cid) * TC_NCH + c;
+      const int tile_c = it * p.n_clusters + cid;
       const long b = (long)tile_c * 128 + m;
       const bool valid = b < p.B;
 #pragma unroll
-      for (int j = 0; j < TC_HS; ++j) cstate[j] = 0.f;
+      for (int j = 0; j < 32; ++j) cstate[j] = 0.f;
       for (int t = 0; t < T; ++t) {
         const uint32_t g = (uint32_t)(it * T + t);
-        mbar_wait(&bars->acc_full[c][g & 1], (g >> 1) & 1);
-        if (leader && c == 0) FWD_TRACE(2, t, 0);
+        mbar_wait(&bars->acc_full[g & 1], (g >> 1) & 1);
+        if (leader) FWD_TRACE(2, t, 0);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + c * 256 + (g & 1) * 128;
-        __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + rank * TC_HS;
-        const long blk = (((long)t * p.n_tiles_cap + tile_c) * TC_NC + rank) * 128 + m;   // saved-state block row
-        __nv_bfloat16* grow = p.gates ? p.gates + blk * (4 * TC_HS) : nullptr;
-        float* crow = p.cst ? p.cst + blk * TC_HS : nullptr;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t taddr = tmem + lane_addr + (g & 1) * 256 + half * 32;
+        const uint32_t taddr_other = tmem + lane_addr + ((g + 1) & 1) * 256 + half * 96;
+        __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + fr * 32;
+        const long blk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 128 + m;   // saved-state block row
+        __nv_bfloat16* grow = p.gates ? p.gates + blk * 128 : nullptr;
+        float* crow = p.cst ? p.cst + blk * 32 : nullptr;
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           uint32_t vi[16], vf[16], vg[16], vo[16];
@@ -325,16 +320,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           tmem_ld_wait();
           uint32_t ph[8], pi[8], pf[8], pg[8], po[8];
           float cn[16];
+          const float* bs = bias_s + half * 32 + jb * 16;
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) {
             float hv[2], iv[2], fv[2], gv[2], ov[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int j = jb * 16 + jj + u;
-              const float gi = fmaf(0.5f, tanh_approx(__uint_as_float(vi[jj + u]) + bias_s[j]), 0.5f);
-              const float gf = fmaf(0.5f, tanh_approx(__uint_as_float(vf[jj + u]) + bias_s[TC_HS + j]), 0.5f);
-              const float gg = tanh_approx(__uint_as_float(vg[jj + u]) + bias_s[2 * TC_HS + j]);
-              const float go = fmaf(0.5f, tanh_approx(__uint_as_float(vo[jj + u]) + bias_s[3 * TC_HS + j]), 0.5f);
+              const float gi = fmaf(0.5f, tanh_approx(__uint_as_float(vi[jj + u]) + bs[jj + u]), 0.5f);
+              const float gf = fmaf(0.5f, tanh_approx(__uint_as_float(vf[jj + u]) + bs[TC_HS + jj + u]), 0.5f);
+              const float gg = tanh_approx(__uint_as_float(vg[jj + u]) + bs[2 * TC_HS + jj + u]);
+              const float go = fmaf(0.5f, tanh_approx(__uint_as_float(vo[jj + u]) + bs[3 * TC_HS + jj + u]), 0.5f);
               const float cc = fmaf(gf, cstate[j], gi * gg);
               cstate[j] = cc;
               cn[jj + u] = cc;
@@ -347,39 +343,62 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             pg[jj / 2] = pack_bf16x2(gv[0], gv[1]);
             po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
           }
-          if (valid) {   // one full 32-byte sector per store instruction (STG.256)
-            st_global_v8(hrow + jb * 16, ph);
-            if (grow) {
-              st_global_v8(grow + jb * 16, pi);
-              st_global_v8(grow + TC_HS + jb * 16, pf);
-              st_global_v8(grow + 2 * TC_HS + jb * 16, pg);
-              st_global_v8(grow + 3 * TC_HS + jb * 16, po);
-            }
-            if (crow) {
-              st_global_v8f(crow + jb * 16, cn);
-              st_global_v8f(crow + jb * 16 + 8, cn + 8);
-            }
+          if (valid) st_global_v8(hrow + jb * 16, ph);   // one full 32-byte sector per store (STG.256)
+          if (grow) {
+            // Saved gates / cell states are not needed by the h exchange: park them in the idle accumulator
+            // buffer (TMEM) and write them to HBM after the publish, off the per-step critical path.
+            const uint32_t tst = taddr_other + jb * 48;
+            uint32_t cu[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cu[e] = __float_as_uint(cn[e]);
+            tmem_st_32x32b_x8(tst, pi);
+            tmem_st_32x32b_x8(tst + 8, pf);
+            tmem_st_32x32b_x8(tst + 16, pg);
+            tmem_st_32x32b_x8(tst + 24, po);
+            tmem_st_32x32b_x16(tst + 32, cu);
           }
         }
+        if (grow) tmem_st_wait();
         tcgen05_fence_before();
-        if (leader && c == 0) FWD_TRACE(2, t, 1);
-        // Publish this CTA's h slice: CTA-level barrier over the chain's 128 threads, then 8 lanes of the leader
-        // warp arrive (release.cluster, cumulative over the barrier) on the 8 CTAs' h_written barriers in parallel.
+        if (leader) FWD_TRACE(2, t, 1);
+        // Publish this CTA's h slice: CTA-level barrier over the 256 epilogue threads, then 4 lanes of the leader
+        // warp arrive (release.cluster, cumulative over the barrier) on the 4 CTAs' h_written barriers in parallel.
         // Readers acquire at cluster scope and cross into the async proxy before their TMA loads.
-        named_bar_sync(1 + c, 128);
-        if (leader && c == 0) FWD_TRACE(2, t, 4);
-        if ((warp - 3) % 4 == 0 && lane < TC_NC) {
-          __threadfence();
-          mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written[c]), (uint32_t)lane));
+        named_bar_sync(1, 32 * FWD_EPI_WARPS);
+        if (leader) FWD_TRACE(2, t, 4);
+        if (warp == 2 && lane < TC_NC)
+          mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written), (uint32_t)lane));
+        if (grow) {
+          // The parked state goes out only after the next step's TMA loads are in flight: a burst of STG.256 right
+          // after the publish would queue ahead of the producer's fence + TMA issue in the SM's memory pipe.
+          if (t < T - 1) mbar_wait(&bars->h_full, (uint32_t)(it * (T - 1) + t) & 1);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int jb = 0; jb < 2; ++jb) {
+            uint32_t sg[32], sc[16];
+            tmem_ld_32x32b_x32(taddr_other + jb * 48, sg);
+            tmem_ld_32x32b_x16(taddr_other + jb * 48 + 32, sc);
+            tmem_ld_wait();
+            if (valid) {
+              st_global_v8(grow + jb * 16, sg);
+              st_global_v8(grow + 32 + jb * 16, sg + 8);
+              st_global_v8(grow + 64 + jb * 16, sg + 16);
+              st_global_v8(grow + 96 + jb * 16, sg + 24);
+              st_global_v8(crow + jb * 16, sc);
+              st_global_v8(crow + jb * 16 + 8, sc + 8);
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&bars->acc_free);
         }
-        if (leader && c == 0) FWD_TRACE(2, t, 5);
+        if (leader) FWD_TRACE(2, t, 5);
       }
     }
   }
   __syncwarp();
   tcgen05_fence_before();
   cluster_sync_all();          // nobody leaves while peers may still multicast into / arrive on this CTA
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
@@ -801,14 +820,14 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if (m.dz) LFMQ_CUDA_CHECK(cudaMemset(m.dz, 0, B * (T + 1) * 4 * TC_H * 2));
   const uint64_t xh_row = (uint64_t)(T + 1) * TC_XH_LD;     // elements per batch row of the 2-D view
   int rc;
-  if ((rc = make_map_2d(&m.tm_h, m.xh, xh_row, B, xh_row * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_h, m.xh, xh_row, B, xh_row * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   // how many 8-CTA clusters can be co-resident (one CTA per SM because of shared memory)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(TC_NC * 18);
+  cfg.gridDim = dim3(TC_NC * 37);
   cfg.blockDim = dim3(FWD_THREADS);
   cfg.dynamicSmemBytes = FWD_SMEM;
   cudaLaunchAttribute attr[1];
@@ -821,7 +840,7 @@ int tc_init(TcState& st, const lfmq_config& c) {
   int nclusters = 0;
   LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nclusters, lstm_fwd_tc_kernel, &cfg));
   if (nclusters < 1) {
-    LFMQ_SET_ERR("no 8-CTA cluster of the forward kernel fits on this device");
+    LFMQ_SET_ERR("no 4-CTA cluster of the forward kernel fits on this device");
     return LFMQ_ERR_UNSUPPORTED;
   }
   m.max_clusters = nclusters;
@@ -858,11 +877,10 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   xh_fill_x_kernel<<<(int)((bt + 255) / 256), 256, 0, s>>>(B, m.T, m.I, x, m.xh);
   LFMQ_LAUNCH_CHECK();
   const int n_tiles = (B + 127) / 128;
-  const int n_pairs = (n_tiles + TC_NCH - 1) / TC_NCH;
   FwdParams p;
   p.B = B; p.T = m.T;
-  p.n_clusters = n_pairs < m.max_clusters ? n_pairs : m.max_clusters;
-  p.n_iters = (n_pairs + p.n_clusters - 1) / p.n_clusters;
+  p.n_clusters = n_tiles < m.max_clusters ? n_tiles : m.max_clusters;
+  p.n_iters = (n_tiles + p.n_clusters - 1) / p.n_clusters;
   p.k16_x = (m.I + 15) / 16;
   p.n_tiles_cap = (m.maxB + 127) / 128;
   p.xh = m.xh;
@@ -896,8 +914,8 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
     LFMQ_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
     const long long t0 = h[(1 * 16 + 0) * 8 + 0];
     const char* names[3] = {"producer", "mma", "epilogue"};
-    for (int t = 0; t < 12; ++t) {
-      fprintf(stderr, "[trace t=%2d]", t);
+    for (int t = 0; t < 16; ++t) {
+      fprintf(stderr, "[trace t=%2d]", 3 * t);
       for (int r = 0; r < 3; ++r) {
         fprintf(stderr, "  %s:", names[r]);
         for (int k = 0; k < 6; ++k) {
@@ -1007,13 +1025,19 @@ int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* g
 namespace lfmq {
 
 struct BwdParams {
-  int B, T, n_iters, n_clusters, n_tiles_cap;
+  int B, T, n_iters, n_clusters, n_tiles_cap, l2_prefetch;
   const __nv_bfloat16* gates;
   const float* cst;
   const __nv_bfloat16* dhout;
   __nv_bfloat16* dz;
   __nv_bfloat16* pexch;      // [tile][parity][src][dst][128][64]
+  long long* trace;          // debug (LFMQ_TRACE_BWD=1)
 };
+
+#define BWD_TRACE(role, k, pt)                                                                            \
+  do {                                                                                                    \
+    if (p.trace && blockIdx.x == 0 && (k) % 3 == 0) p.trace[((role) * 16 + (k) / 3) * 8 + (pt)] = clock64();      \
+  } while (0)
 
 constexpr int BWD_NC = 4;
 constexpr int BWD_THREADS = 192;
@@ -1070,17 +1094,38 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
+    // ===================== TMA producer: weights once, then the foreign partial slices of every step;
+    // the whole warp also prefetches the saved activations two steps ahead into L2 =========
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->w_full, 131072);
       for (int jb = 0; jb < 4; ++jb) tma_load_2d(smem + SB_U + jb * 32768, &tm_ubk, &bars->w_full, jb * 64, rank * 256);
-      uint32_t n_er = 0;
-      for (int it = 0; it < p.n_iters; ++it) {
-        const int tile = it * p.n_clusters + cid;
-        for (int t = T - 2; t >= 0; --t) {           // step t consumes the partials exported after step t+1
+    }
+    uint32_t n_er = 0;
+    const long tstride = (long)p.n_tiles_cap * 8 * 128;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int tile = it * p.n_clusters + cid;
+      for (int t = T - 1; t >= 0; --t) {
+        // L2 prefetch of the inputs of step t-2 (t-1 and t-2 at the start of a tile)
+        for (int tp = (t == T - 1) ? t - 1 : t - 2; p.l2_prefetch && tp >= t - 2 && tp >= 0; --tp) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = lane + 32 * i;
+            const long b = (long)tile * 128 + m;
+            if (b < p.B) {
+              const long blk0 = (((long)tp * p.n_tiles_cap + tile) * 8 + 2 * rank) * 128 + m;
+              prefetch_l2_bulk(p.gates + blk0 * 128, 256);
+              prefetch_l2_bulk(p.gates + (blk0 + 128) * 128, 256);
+              prefetch_l2_bulk(p.cst + blk0 * 32, 128);
+              prefetch_l2_bulk(p.cst + (blk0 + 128) * 32, 128);
+              prefetch_l2_bulk(p.dhout + (b * T + tp) * TC_H + rank * 64, 128);
+            }
+          }
+        }
+        if (lane == 0 && t <= T - 2) {               // step t consumes the partials exported after step t+1
           mbar_wait_cluster(&bars->exp_ready, (n_er) & 1);
           mbar_wait(&bars->recv_free, (n_er++) & 1);    // own epilogue is done reading the previous slices
-          fence_proxy_async_all();
+          BWD_TRACE(0, T - 1 - t, 0);
+          fence_proxy_async_global();
           mbar_arrive_expect_tx(&bars->recv_full, 3 * 16384);
           const int par = (t + 1) & 1;
           for (uint32_t d = 1; d < BWD_NC; ++d) {
@@ -1089,8 +1134,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
                         ((((tile * 2 + par) * 4 + (int)src) * 4 + (int)rank)) * 128);
           }
         }
+        __syncwarp();
       }
     }
+    (void)tstride;
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -1104,6 +1151,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           for (int jb = 0; jb < 4; ++jb, ++q) {
             const uint32_t st = q & 1;
             mbar_wait(&bars->a_full[st], (q >> 1) & 1);
+            if (jb == 0) BWD_TRACE(1, T - 1 - t, 0);
+            if (jb == 3) BWD_TRACE(1, T - 1 - t, 1);
             tcgen05_fence_after();
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
@@ -1134,6 +1183,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         const bool has_rec = t < T - 1;
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
         if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
+        if (tid == 64) BWD_TRACE(2, T - 1 - t, 0);
         const long rt = b * T + t;
         const long blk0 = (((long)t * p.n_tiles_cap + tile) * 8 + 2 * rank) * 128 + m;     // forward rank 2r (+1: +128 rows)
         const long tstride = (long)p.n_tiles_cap * 8 * 128;                               // block rows per time step
@@ -1239,10 +1289,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           *reinterpret_cast<uint4*>(arow + ((7 ^ sw) << 4)) = make_uint4(zo[4], zo[5], zo[6], zo[7]);
           fence_proxy_async_smem();
           mbar_arrive(&bars->a_full[st]);
+          if (tid == 64 && jb == 0) BWD_TRACE(2, T - 1 - t, 1);
+          if (tid == 64 && jb == 3) BWD_TRACE(2, T - 1 - t, 2);
         }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
           mbar_wait(&bars->acc_full[gs & 1], (gs >> 1) & 1);
+          if (tid == 64) BWD_TRACE(2, T - 1 - t, 3);
           tcgen05_fence_after();
           const uint32_t acc = tmem + (gs & 1) * 256 + lane_addr;
           const int par = t & 1;
@@ -1263,10 +1316,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             }
           }
           tcgen05_fence_before();
+          if (tid == 64) BWD_TRACE(2, T - 1 - t, 4);
           named_bar_sync(1, 128);
+          if (tid == 64) BWD_TRACE(2, T - 1 - t, 5);
           if (warp == 2 && lane == 0) mbar_arrive(&bars->recv_free);
           if (warp == 2 && lane >= 1 && lane < BWD_NC) {
-            __threadfence();
             mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
           }
         }
@@ -1432,9 +1486,16 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
     const int n_tiles = (B + 127) / 128;
     bp.B = B; bp.T = m.T;
     bp.n_tiles_cap = (m.maxB + 127) / 128;
+    static const int want_pf = getenv("LFMQ_BWD_PREFETCH") ? atoi(getenv("LFMQ_BWD_PREFETCH")) : 0;
+    bp.l2_prefetch = want_pf;
     bp.n_clusters = n_tiles < m.bwd_max_clusters ? n_tiles : m.bwd_max_clusters;
     bp.n_iters = (n_tiles + bp.n_clusters - 1) / bp.n_clusters;
     bp.gates = m.gates; bp.cst = m.cst; bp.dhout = m.dhout; bp.dz = m.dz; bp.pexch = m.pexch;
+    static long long* btrace = nullptr;
+    static const bool want_btrace = getenv("LFMQ_TRACE_BWD") != nullptr;
+    if (want_btrace && !btrace) LFMQ_CUDA_CHECK(cudaMalloc(&btrace, 3 * 16 * 8 * sizeof(long long)));
+    if (want_btrace) LFMQ_CUDA_CHECK(cudaMemsetAsync(btrace, 0, 3 * 16 * 8 * sizeof(long long), s));
+    bp.trace = want_btrace ? btrace : nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(BWD_NC * bp.n_clusters);
     cfg.blockDim = dim3(BWD_THREADS);
@@ -1449,6 +1510,24 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
     cfg.numAttrs = 1;
     LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, bp, m.tm_ubk, m.tm_px));
     g_launches++;
+    if (want_btrace) {
+      long long h[3 * 16 * 8];
+      LFMQ_CUDA_CHECK(cudaStreamSynchronize(s));
+      LFMQ_CUDA_CHECK(cudaMemcpy(h, btrace, sizeof(h), cudaMemcpyDeviceToHost));
+      const long long t0 = h[(2 * 16 + 0) * 8 + 0];
+      const char* names[3] = {"producer", "mma", "epilogue"};
+      for (int k = 0; k < 16; ++k) {
+        fprintf(stderr, "[btrace k=%2d]", 3 * k);
+        for (int r = 0; r < 3; ++r) {
+          fprintf(stderr, "  %s:", names[r]);
+          for (int q = 0; q < 6; ++q) {
+            const long long v = h[(r * 16 + k) * 8 + q];
+            fprintf(stderr, " %lld", v ? v - t0 : -1LL);
+          }
+        }
+        fprintf(stderr, "\n");
+      }
+    }
   }
   st.prof->end(LFMQ_REGION_BWD, s);
 
