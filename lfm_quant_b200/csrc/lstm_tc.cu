@@ -5,9 +5,11 @@
 //   xh    bf16 [maxB][T+1][384]   row (b,t): cols 0..255 = h_{t-1} (zero at t=0), 256..287 = x_t, 288 = 1.0 (t<T),
 //                                 rest 0.  One buffer serves: the A operand of the forward recurrence (K-major
 //                                 tiles via TMA), the head (h_t = row t+1) and the weight-gradient GEMM (MN-major).
-//   gates bf16 [T][tiles][8][128][4*32]  post-activation i|f|g|o saved for BPTT, one contiguous 32 KB block per
-//                                 (step, 128-row tile, forward CTA rank): DRAM-page-friendly writes and reads
-//   cst   f32  [T][tiles][8][128][32]    cell states, same blocking
+//   gates bf16 [T][tiles][8 blocks of 32 units][4 warps][8 pieces = gate*2+half][32 lanes][16]   post-activation
+//                                 i|f|g|o saved for BPTT.  Writer (forward) and reader (backward) both map one
+//                                 row to one thread, so the state is stored SoA at 32-byte granularity: a warp's
+//                                 256-bit access to `piece` covers 1 KB contiguously instead of 32 scattered sectors
+//   cst   f32  [T][tiles][8][4][4 pieces][32][8]    cell states, same scheme
 //   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
 //   dhout bf16 [maxB][T][H]       dLoss/dh from the head (after BN/dropout backward)
 //
@@ -307,9 +309,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         const uint32_t taddr = tmem + lane_addr + (g & 1) * 256 + half * 32;
         const uint32_t taddr_other = tmem + lane_addr + ((g + 1) & 1) * 256 + half * 96;
         __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + fr * 32;
-        const long blk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 128 + m;   // saved-state block row
-        __nv_bfloat16* grow = p.gates ? p.gates + blk * 128 : nullptr;
-        float* crow = p.cst ? p.cst + blk * 32 : nullptr;
+        // saved state, SoA at 32-byte granularity: [(t, tile, fr, quadrant)][piece][lane]
+        const long wblk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 4 + q;
+        __nv_bfloat16* grow = p.gates ? p.gates + (wblk * 8 * 32 + lane) * 16 : nullptr;   // + piece * 512
+        float* crow = p.cst ? p.cst + (wblk * 4 * 32 + lane) * 8 : nullptr;                // + piece * 256
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           uint32_t vi[16], vf[16], vg[16], vo[16];
@@ -369,9 +372,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         if (warp == 2 && lane < TC_NC)
           mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written), (uint32_t)lane));
         if (grow) {
-          // The parked state goes out only after the next step's TMA loads are in flight: a burst of STG.256 right
-          // after the publish would queue ahead of the producer's fence + TMA issue in the SM's memory pipe.
-          if (t < T - 1) mbar_wait(&bars->h_full, (uint32_t)(it * (T - 1) + t) & 1);
           tcgen05_fence_after();
 #pragma unroll
           for (int jb = 0; jb < 2; ++jb) {
@@ -380,12 +380,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             tmem_ld_32x32b_x16(taddr_other + jb * 48 + 32, sc);
             tmem_ld_wait();
             if (valid) {
-              st_global_v8(grow + jb * 16, sg);
-              st_global_v8(grow + 32 + jb * 16, sg + 8);
-              st_global_v8(grow + 64 + jb * 16, sg + 16);
-              st_global_v8(grow + 96 + jb * 16, sg + 24);
-              st_global_v8(crow + jb * 16, sc);
-              st_global_v8(crow + jb * 16 + 8, sc + 8);
+              st_global_v8(grow + (0 * 2 + jb) * 512, sg);
+              st_global_v8(grow + (1 * 2 + jb) * 512, sg + 8);
+              st_global_v8(grow + (2 * 2 + jb) * 512, sg + 16);
+              st_global_v8(grow + (3 * 2 + jb) * 512, sg + 24);
+              st_global_v8(crow + (jb * 2 + 0) * 256, sc);
+              st_global_v8(crow + (jb * 2 + 1) * 256, sc + 8);
             }
           }
           tcgen05_fence_before();
@@ -1025,7 +1025,7 @@ int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* g
 namespace lfmq {
 
 struct BwdParams {
-  int B, T, n_iters, n_clusters, n_tiles_cap, l2_prefetch;
+  int B, T, n_iters, n_clusters, n_tiles_cap;
   const __nv_bfloat16* gates;
   const float* cst;
   const __nv_bfloat16* dhout;
@@ -1040,7 +1040,7 @@ struct BwdParams {
   } while (0)
 
 constexpr int BWD_NC = 4;
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;   // producer + MMA + 2 sets of 4 pointwise warps
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
 constexpr uint32_t SB_R = 163840;               // 3 foreign slices x [128 x 128 B]
@@ -1094,33 +1094,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer: weights once, then the foreign partial slices of every step;
-    // the whole warp also prefetches the saved activations two steps ahead into L2 =========
+    // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
+    // (an L2 prefetch of the saved activations two steps ahead was tried here and made the kernel 25 % slower)
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->w_full, 131072);
       for (int jb = 0; jb < 4; ++jb) tma_load_2d(smem + SB_U + jb * 32768, &tm_ubk, &bars->w_full, jb * 64, rank * 256);
     }
     uint32_t n_er = 0;
-    const long tstride = (long)p.n_tiles_cap * 8 * 128;
     for (int it = 0; it < p.n_iters; ++it) {
       const int tile = it * p.n_clusters + cid;
       for (int t = T - 1; t >= 0; --t) {
-        // L2 prefetch of the inputs of step t-2 (t-1 and t-2 at the start of a tile)
-        for (int tp = (t == T - 1) ? t - 1 : t - 2; p.l2_prefetch && tp >= t - 2 && tp >= 0; --tp) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int m = lane + 32 * i;
-            const long b = (long)tile * 128 + m;
-            if (b < p.B) {
-              const long blk0 = (((long)tp * p.n_tiles_cap + tile) * 8 + 2 * rank) * 128 + m;
-              prefetch_l2_bulk(p.gates + blk0 * 128, 256);
-              prefetch_l2_bulk(p.gates + (blk0 + 128) * 128, 256);
-              prefetch_l2_bulk(p.cst + blk0 * 32, 128);
-              prefetch_l2_bulk(p.cst + (blk0 + 128) * 32, 128);
-              prefetch_l2_bulk(p.dhout + (b * T + tp) * TC_H + rank * 64, 128);
-            }
-          }
-        }
         if (lane == 0 && t <= T - 2) {               // step t consumes the partials exported after step t+1
           mbar_wait_cluster(&bars->exp_ready, (n_er) & 1);
           mbar_wait(&bars->recv_free, (n_er++) & 1);    // own epilogue is done reading the previous slices
@@ -1137,20 +1120,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         __syncwarp();
       }
     }
-    (void)tstride;
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256, false, false);
       mbar_wait(&bars->w_full, 0);
-      uint32_t q = 0;       // global chunk counter
       uint32_t gs = 0;      // global step counter
       for (int it = 0; it < p.n_iters; ++it) {
         for (int t = T - 1; t >= 0; --t, ++gs) {
           const uint32_t acc = tmem + (gs & 1) * 256;
-          for (int jb = 0; jb < 4; ++jb, ++q) {
-            const uint32_t st = q & 1;
-            mbar_wait(&bars->a_full[st], (q >> 1) & 1);
+          for (int jb = 0; jb < 4; ++jb) {
+            const uint32_t st = jb & 1;                      // stage = producing warp-set
+            const uint32_t n_use = gs * 2 + (jb >> 1);
+            mbar_wait(&bars->a_full[st], n_use & 1);
             if (jb == 0) BWD_TRACE(1, T - 1 - t, 0);
             if (jb == 3) BWD_TRACE(1, T - 1 - t, 1);
             tcgen05_fence_after();
@@ -1168,55 +1150,66 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     }
   } else {
     // ===================== pointwise gate gradients, A-operand staging, partial exchange =====================
+    // Two warp-sets (A: warps 2-5, B: warps 6-9) split the four 16-unit chunks of a step: set s handles chunks
+    // s and s+2 and owns A-operand stage s, so two chunks' global loads are always in flight together, and each
+    // set issues the loads of its first chunk of step t-1 before the exchange of step t (they do not depend on it).
+    const int set = (warp - 2) >> 2;         // 0 / 1
     const int wq = warp & 3;                 // TMEM lane quadrant
     const int m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    float dc[64];
-    uint32_t q = 0, gs = 0, n_rf = 0;
+    const int sw = m & 7;
+    float dc[32];
+    uint32_t gs = 0, n_rf = 0;
+    // inputs of one chunk
+    uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
+    float ct[16], cp[16];
+    const long tstride = (long)p.n_tiles_cap * 8 * 128;            // saved-state block rows per time step
+
+    auto load_chunk = [&](int tile, long b, bool valid, int t, int jb) {
+      if (valid) {
+        const long wblk = (((long)t * p.n_tiles_cap + tile) * 8 + 2 * rank + (jb >> 1)) * 4 + wq;
+        const int hb = jb & 1;
+        const __nv_bfloat16* grow = p.gates + (wblk * 8 * 32 + lane) * 16;
+        const float* crow = p.cst + (wblk * 4 * 32 + lane) * 8;
+        ld_global_v8(grow + (0 * 2 + hb) * 512, gi);
+        ld_global_v8(grow + (1 * 2 + hb) * 512, gf);
+        ld_global_v8(grow + (2 * 2 + hb) * 512, gg);
+        ld_global_v8(grow + (3 * 2 + hb) * 512, go);
+        ld_global_v8(p.dhout + (b * T + t) * TC_H + rank * 64 + jb * 16, dhp);
+        ld_global_v8f(crow + (hb * 2 + 0) * 256, ct);
+        ld_global_v8f(crow + (hb * 2 + 1) * 256, ct + 8);
+        if (t > 0) {
+          ld_global_v8f(crow - tstride * 32 + (hb * 2 + 0) * 256, cp);
+          ld_global_v8f(crow - tstride * 32 + (hb * 2 + 1) * 256, cp + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gi[j] = gf[j] = gg[j] = go[j] = dhp[j] = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ct[j] = cp[j] = 0.f;
+      }
+    };
+
     for (int it = 0; it < p.n_iters; ++it) {
       const int tile = it * p.n_clusters + cid;
       const long b = (long)tile * 128 + m;
       const bool valid = b < p.B;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) dc[j] = 0.f;
+      for (int j = 0; j < 32; ++j) dc[j] = 0.f;
+      load_chunk(tile, b, valid, T - 1, set);
       for (int t = T - 1; t >= 0; --t, ++gs) {
         const bool has_rec = t < T - 1;
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
         if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
         if (tid == 64) BWD_TRACE(2, T - 1 - t, 0);
-        const long rt = b * T + t;
-        const long blk0 = (((long)t * p.n_tiles_cap + tile) * 8 + 2 * rank) * 128 + m;     // forward rank 2r (+1: +128 rows)
-        const long tstride = (long)p.n_tiles_cap * 8 * 128;                               // block rows per time step
-        const __nv_bfloat16* dhrow = p.dhout + rt * TC_H + rank * 64;
         __nv_bfloat16* dzrow = p.dz + (b * (T + 1) + t) * 4 * TC_H + rank * 64;
 #pragma unroll
-        for (int jb = 0; jb < 4; ++jb, ++q) {
-          uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
-          float ct[16], cp[16];
-          if (valid) {
-            const long blk = blk0 + (jb >> 1) * 128;
-            const __nv_bfloat16* grow = p.gates + blk * 128 + (jb & 1) * 16;
-            const float* crow = p.cst + blk * 32 + (jb & 1) * 16;
-            ld_global_v8(grow, gi);
-            ld_global_v8(grow + 32, gf);
-            ld_global_v8(grow + 64, gg);
-            ld_global_v8(grow + 96, go);
-            ld_global_v8(dhrow + jb * 16, dhp);
-            ld_global_v8f(crow, ct);
-            ld_global_v8f(crow + 8, ct + 8);
-            if (t > 0) {
-              ld_global_v8f(crow - tstride * 32, cp);
-              ld_global_v8f(crow - tstride * 32 + 8, cp + 8);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gi[j] = gf[j] = gg[j] = go[j] = dhp[j] = 0u;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ct[j] = cp[j] = 0.f;
-          }
+        for (int ci = 0; ci < 2; ++ci) {
+          const int jb = 2 * ci + set;
+          if (ci == 1) load_chunk(tile, b, valid, t, jb);
           float rec[16];
           if (has_rec) {
             uint32_t vr[16];
@@ -1229,7 +1222,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
               const uint8_t* rs = smem + SB_R + d * 16384 + m * 128;
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
-                const uint4 v = *reinterpret_cast<const uint4*>(rs + (((2 * jb + h2) ^ (m & 7)) << 4));
+                const uint4 v = *reinterpret_cast<const uint4*>(rs + (((2 * jb + h2) ^ sw) << 4));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1256,12 +1249,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
               const float dh = (u ? bf16_hi(dhp[jj / 2]) : bf16_lo(dhp[jj / 2])) + rec[j];
               const float tc = tanh_approx(ct[j]);
               const float d_o = dh * tc;
-              const float dcn = dc[jb * 16 + j] + dh * o_ * (1.f - tc * tc);
+              const float dcn = dc[ci * 16 + j] + dh * o_ * (1.f - tc * tc);
               ri[u] = dcn * g_ * i_ * (1.f - i_);
               rf[u] = dcn * cp[j] * f_ * (1.f - f_);
               rg[u] = dcn * i_ * (1.f - g_ * g_);
               ro[u] = d_o * o_ * (1.f - o_);
-              dc[jb * 16 + j] = dcn * f_;
+              dc[ci * 16 + j] = dcn * f_;
             }
             zi[jj / 2] = pack_bf16x2(ri[0], ri[1]);
             zf[jj / 2] = pack_bf16x2(rf[0], rf[1]);
@@ -1274,11 +1267,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             st_global_v8(dzrow + 2 * TC_H + jb * 16, zg);
             st_global_v8(dzrow + 3 * TC_H + jb * 16, zo);
           }
-          // A operand k-block jb: row m, chunk 2g+h holds gate g, units 8h..8h+7 (128B-swizzled K-major tile)
-          const uint32_t st = q & 1;
-          if (q >= 2) mbar_wait(&bars->a_empty[st], ((q >> 1) - 1) & 1);
-          uint8_t* arow = smem + SB_A + st * 16384 + m * 128;
-          const int sw = m & 7;
+          // A operand k-block jb in stage `set`: row m, chunk 2g+h holds gate g, units 8h..8h+7 (SW128 K-major)
+          const uint32_t n_use = gs * 2 + ci;                 // use index of this stage
+          if (n_use >= 1) mbar_wait(&bars->a_empty[set], (n_use - 1) & 1);
+          uint8_t* arow = smem + SB_A + set * 16384 + m * 128;
           *reinterpret_cast<uint4*>(arow + ((0 ^ sw) << 4)) = make_uint4(zi[0], zi[1], zi[2], zi[3]);
           *reinterpret_cast<uint4*>(arow + ((1 ^ sw) << 4)) = make_uint4(zi[4], zi[5], zi[6], zi[7]);
           *reinterpret_cast<uint4*>(arow + ((2 ^ sw) << 4)) = make_uint4(zf[0], zf[1], zf[2], zf[3]);
@@ -1288,10 +1280,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           *reinterpret_cast<uint4*>(arow + ((6 ^ sw) << 4)) = make_uint4(zo[0], zo[1], zo[2], zo[3]);
           *reinterpret_cast<uint4*>(arow + ((7 ^ sw) << 4)) = make_uint4(zo[4], zo[5], zo[6], zo[7]);
           fence_proxy_async_smem();
-          mbar_arrive(&bars->a_full[st]);
-          if (tid == 64 && jb == 0) BWD_TRACE(2, T - 1 - t, 1);
-          if (tid == 64 && jb == 3) BWD_TRACE(2, T - 1 - t, 2);
+          mbar_arrive(&bars->a_full[set]);
+          if (tid == 64 && ci == 0) BWD_TRACE(2, T - 1 - t, 1);
+          if (tid == 64 && ci == 1) BWD_TRACE(2, T - 1 - t, 2);
         }
+        // inputs of this set's first chunk of the next step: independent of the exchange below
+        if (t > 0) load_chunk(tile, b, valid, t - 1, set);
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
           mbar_wait(&bars->acc_full[gs & 1], (gs >> 1) & 1);
@@ -1302,22 +1296,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
           for (uint32_t d = 1; d < BWD_NC; ++d) {
             const uint32_t dst = (rank + d) & 3;
-            __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64;
+            __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64 + set * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(acc + dst * 64 + set * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(acc + dst * 64 + h2 * 32, v);
-              tmem_ld_wait();
-              uint32_t pk[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-              st_global_v8(out + h2 * 32, pk);
-              st_global_v8(out + h2 * 32 + 16, pk + 8);
-            }
+            for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            st_global_v8(out, pk);
+            st_global_v8(out + 16, pk + 8);
           }
           tcgen05_fence_before();
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 4);
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 5);
           if (warp == 2 && lane == 0) mbar_arrive(&bars->recv_free);
           if (warp == 2 && lane >= 1 && lane < BWD_NC) {
@@ -1486,8 +1477,6 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
     const int n_tiles = (B + 127) / 128;
     bp.B = B; bp.T = m.T;
     bp.n_tiles_cap = (m.maxB + 127) / 128;
-    static const int want_pf = getenv("LFMQ_BWD_PREFETCH") ? atoi(getenv("LFMQ_BWD_PREFETCH")) : 0;
-    bp.l2_prefetch = want_pf;
     bp.n_clusters = n_tiles < m.bwd_max_clusters ? n_tiles : m.bwd_max_clusters;
     bp.n_iters = (n_tiles + bp.n_clusters - 1) / bp.n_clusters;
     bp.gates = m.gates; bp.cst = m.cst; bp.dhout = m.dhout; bp.dz = m.dz; bp.pexch = m.pexch;
