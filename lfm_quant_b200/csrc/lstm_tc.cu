@@ -11,7 +11,8 @@
 //                                 256-bit access to `piece` covers 1 KB contiguously instead of 32 scattered sectors
 //   cst   f32  [T][tiles][8][4][4 pieces][32][8]    cell states, same scheme
 //   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
-//   dhout bf16 [maxB][T][H]       dLoss/dh from the head (after BN/dropout backward)
+//   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dLoss/dh from the head (after BN/dropout
+//                                 backward), already in the backward kernel's per-thread SoA order
 //
 // Forward recurrence = ONE persistent kernel (lstm_fwd_tc_kernel): clusters of 8 CTAs, CTA r keeps the weight
 // slice of hidden units [32r, 32r+32) (all four gates, 128 gate columns) resident in shared memory for the whole
@@ -88,6 +89,7 @@ struct TcImpl {
   float *cst, *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
+  CUtensorMap tm_h128;                         // head: 128-row h tiles
   CUtensorMap tm_ubk, tm_px;                   // backward recurrence
   CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
   int max_clusters = 0, bwd_max_clusters = 0;
@@ -429,32 +431,40 @@ constexpr int HEAD_THREADS = 256;
 constexpr int HWG_PART = TC_H * TC_OPAD;              // dWo partial per CTA of the weight-gradient pass
 constexpr int HWG_ROWS = 32;                          // rows staged per tile
 
+// Thread-per-row head over TMA-staged tiles: a CTA takes 128 windows of one time step (the 128 x 256 bf16 h tile
+// arrives as four SWIZZLE_128B boxes), every thread owns one row: y = Dropout(BN(h)) on the fly, pred = y*Wo + bo
+// with Wo broadcast from shared memory (no cross-lane traffic), loss terms, dLoss/dpred, dy = dpred*Wo^T, dLoss/dh
+// written in the backward kernel's SoA layout; dgamma/dbeta need a cross-row sum per column, done with a 31-shuffle
+// reduce-scatter per group of 32 columns.
+constexpr int HROWS_SMEM = 65536 + 1024 + 256;
+
 template <bool TRAIN>
-__global__ void __launch_bounds__(HEAD_THREADS, 1) head_fused_kernel(HeadParams p) {
-  constexpr int HEAD_R = TRAIN ? 4 : 8;            // rows in flight per warp (memory-level parallelism)
+__global__ void __launch_bounds__(128, 2) head_rows_kernel(HeadParams p, const __grid_constant__ CUtensorMap tm_h,
+                                                          int n_btiles, int n_tiles_cap) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tile + 65536);
   __shared__ __align__(16) float Wo_s[TC_H * TC_OPAD];
-  __shared__ float red_s[HEAD_PART];
   __shared__ __align__(16) float bn_s[4][TC_H];      // gamma*inv | beta - gamma*mean*inv | mean | inv
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int j = tid; j < TC_H; j += HEAD_THREADS) {
+  __shared__ float red_s[HEAD_PART];
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  for (int j = tid; j < TC_H; j += 128) {
     const float iv = 1.0f / sqrtf(p.var[j] + p.eps);
     bn_s[0][j] = p.gamma[j] * iv;
     bn_s[1][j] = p.beta[j] - p.gamma[j] * p.mean[j] * iv;
     bn_s[2][j] = p.mean[j];
     bn_s[3][j] = iv;
   }
-  for (int i = tid; i < TC_H * TC_OPAD; i += HEAD_THREADS) {
+  for (int i = tid; i < TC_H * TC_OPAD; i += 128) {
     const int j = i / TC_OPAD, k = i % TC_OPAD;
     Wo_s[i] = (k < p.O) ? p.Wo[j * p.O + k] : 0.f;
   }
-  for (int i = tid; i < HEAD_PART; i += HEAD_THREADS) red_s[i] = 0.f;
+  for (int i = tid; i < HEAD_PART; i += 128) red_s[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
   __syncthreads();
-
-  const int j0 = lane * 8;
-  // which output this lane owns after the butterfly: lane bit4 -> k bit3, bit3 -> bit2, bit2 -> bit1, bit1 -> bit0
-  const int kown = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  const bool owner = (lane & 1) == 0;
-  const float bo_k = (kown < p.O) ? p.bo[kown] : 0.f;
   float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
   if (TRAIN) {
     const float Bg = p.denom[0], Mg = p.denom[1];
@@ -462,170 +472,186 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_fused_kernel(HeadParams 
     c_last = (1.f - p.p1) * p.p2 / (Bg * (float)p.O);
     c_tar = p.p1 / Bg;
   }
-  float accG[8], accB[8];
-  float accbo = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  float accbo[TC_OPAD];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    accG[i] = 0.f;
-    accB[i] = 0.f;
-  }
-  const long rows = (long)p.B * p.T;
+  for (int k = 0; k < TC_OPAD; ++k) accbo[k] = 0.f;
+  const int sw = tid & 7;
   const int nq = TC_H / 4;
-  for (long rbase = ((long)blockIdx.x * (HEAD_THREADS / 32) + warp) * HEAD_R; rbase < rows;
-       rbase += (long)gridDim.x * (HEAD_THREADS / 32) * HEAD_R) {
-    uint4 hraw[HEAD_R];
-    float ytv[HEAD_R];
-#pragma unroll
-    for (int u = 0; u < HEAD_R; ++u) {
-      const long r = rbase + u;
-      hraw[u] = make_uint4(0u, 0u, 0u, 0u);
-      ytv[u] = 0.f;
-      if (r < rows) {
-        const long b = r / p.T;
-        const int t = (int)(r % p.T);
-        hraw[u] = *reinterpret_cast<const uint4*>(p.xh + (b * (p.T + 1) + t + 1) * TC_XH_LD + j0);
-        if (p.y && kown < p.O) ytv[u] = p.y[r * p.O + kown];
-      }
+  uint32_t phase = 0;
+  const int n_tiles = p.T * n_btiles;
+  for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+    const int t = ti / n_btiles, bt = ti % n_btiles;
+    const long b = (long)bt * 128 + tid;
+    const bool valid = b < p.B;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar, 65536);
+      for (int kb = 0; kb < 4; ++kb)
+        tma_load_2d(tile + kb * 16384, &tm_h, bar, (t + 1) * TC_XH_LD + kb * 64, bt * 128);
     }
+    const long r = b * p.T + t;
+    float yt[TC_OPAD];
 #pragma unroll
-    for (int u = 0; u < HEAD_R; ++u) {
-      const long r = rbase + u;
-      if (r >= rows) break;
-      const long b = r / p.T;
-      const int t = (int)(r % p.T);
-      const uint32_t hw[4] = {hraw[u].x, hraw[u].y, hraw[u].z, hraw[u].w};
-      float hv[8], dm[8], yv[8];
+    for (int k = 0; k < TC_OPAD; ++k) yt[k] = 0.f;
+    if (p.y && valid) {
+      for (int k = 0; k < p.O; ++k) yt[k] = p.y[r * p.O + k];
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    const uint8_t* hrow = tile + tid * 128;
+    float pr[TC_OPAD];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        hv[2 * i] = bf16_lo(hw[i]);
-        hv[2 * i + 1] = bf16_hi(hw[i]);
-      }
+    for (int k = 0; k < TC_OPAD; ++k) pr[k] = (k < p.O) ? p.bo[k] : 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(hrow + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
+      const uint32_t hw[4] = {raw.x, raw.y, raw.z, raw.w};
+      float dm[8];
       if (p.use_dropout) {
-        const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + lane * 2;
+        const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + c * 2;
         dropout_quad(p.key, qbase, dm);
         dropout_quad(p.key, qbase + 1, dm + 4);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dm[i] = 1.f;
+        for (int e = 0; e < 8; ++e) dm[e] = 1.f;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) yv[i] = fmaf(bn_s[0][j0 + i], hv[i], bn_s[1][j0 + i]) * dm[i];
-      float pr[TC_OPAD];
-#pragma unroll
-      for (int k = 0; k < TC_OPAD; ++k) pr[k] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
+      for (int e = 0; e < 8; ++e) {
+        const int j = c * 8 + e;
+        const float hv = (e & 1) ? bf16_hi(hw[e >> 1]) : bf16_lo(hw[e >> 1]);
+        const float yv = fmaf(bn_s[0][j], hv, bn_s[1][j]) * dm[e];
+        const float4* w4 = reinterpret_cast<const float4*>(Wo_s + j * TC_OPAD);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float4 w = w4[kk];
-          pr[4 * kk + 0] = fmaf(yv[i], w.x, pr[4 * kk + 0]);
-          pr[4 * kk + 1] = fmaf(yv[i], w.y, pr[4 * kk + 1]);
-          pr[4 * kk + 2] = fmaf(yv[i], w.z, pr[4 * kk + 2]);
-          pr[4 * kk + 3] = fmaf(yv[i], w.w, pr[4 * kk + 3]);
+          pr[4 * kk + 0] = fmaf(yv, w.x, pr[4 * kk + 0]);
+          pr[4 * kk + 1] = fmaf(yv, w.y, pr[4 * kk + 1]);
+          pr[4 * kk + 2] = fmaf(yv, w.z, pr[4 * kk + 2]);
+          pr[4 * kk + 3] = fmaf(yv, w.w, pr[4 * kk + 3]);
         }
       }
-      // reduce-scatter butterfly: 16 partial sums over 32 lanes with 8+4+2+1+1 shuffles
+    }
+    if (p.preds && valid) {
+      for (int k = 0; k < p.O; ++k) p.preds[r * p.O + k] = pr[k];
+    }
+    if (p.y) {
+      bool any = false;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool up = (lane & 16) != 0;
-        const float send = up ? pr[i] : pr[i + 8];
-        const float keep = up ? pr[i + 8] : pr[i];
-        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool up = (lane & 8) != 0;
-        const float send = up ? pr[i] : pr[i + 4];
-        const float keep = up ? pr[i + 4] : pr[i];
-        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const bool up = (lane & 4) != 0;
-        const float send = up ? pr[i] : pr[i + 2];
-        const float keep = up ? pr[i + 2] : pr[i];
-        pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      {
-        const bool up = (lane & 2) != 0;
-        const float send = up ? pr[0] : pr[1];
-        const float keep = up ? pr[1] : pr[0];
-        pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-      const float pred = pr[0] + __shfl_xor_sync(0xffffffffu, pr[0], 1) + bo_k;
-      if (p.preds && owner && kown < p.O) p.preds[r * p.O + kown] = pred;
-      if (!p.y) continue;
-      const float yt = ytv[u];
-      const bool any = __ballot_sync(0xffffffffu, yt != 0.0f) != 0u;      // losses.py:72
-      const float mk = any ? 1.f : 0.f;
-      const float d = (kown < p.O) ? (pred * mk - yt) : 0.f;               // losses.py:75
+      for (int k = 0; k < TC_OPAD; ++k) any |= (yt[k] != 0.0f);          // losses.py:72
+      const float mk = (any && valid) ? 1.f : 0.f;
       const bool last = (t == p.T - 1);
-      if (owner) {
-        const float d2 = d * d;
-        s2 += d2;
-        if (last) {
-          s1 += d2;
-          if (kown == p.target_idx) s0 += d2;
-        }
-      }
-      if (!TRAIN) continue;
-      float coef = c_all;
-      if (last) coef += c_last + ((kown == p.target_idx) ? c_tar : 0.f);
-      const float dp_own = 2.f * d * coef * mk;
-      if (owner) {
-        accbo += dp_own;
-        p.dpred[r * TC_OPAD + kown] = dp_own;
-      }
       float dp[TC_OPAD];
 #pragma unroll
       for (int k = 0; k < TC_OPAD; ++k) {
-        const int src = ((k >> 3) & 1) * 16 + ((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2;
-        dp[k] = __shfl_sync(0xffffffffu, dp_own, src);
-      }
-      float dyv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4* w4 = reinterpret_cast<const float4*>(Wo_s + (j0 + i) * TC_OPAD);
-        float s = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float4 w = w4[kk];
-          s = fmaf(dp[4 * kk + 0], w.x, s);
-          s = fmaf(dp[4 * kk + 1], w.y, s);
-          s = fmaf(dp[4 * kk + 2], w.z, s);
-          s = fmaf(dp[4 * kk + 3], w.w, s);
+        const float d = (k < p.O && valid) ? (pr[k] * mk - yt[k]) : 0.f;  // losses.py:75
+        const float d2 = d * d;
+        s2 += d2;
+        float coef = c_all;
+        if (last) {
+          s1 += d2;
+          coef += c_last;
+          if (k == p.target_idx) {
+            s0 += d2;
+            coef += c_tar;
+          }
         }
-        const float dd = s * dm[i];                       // through Dropout
-        accG[i] = fmaf(dd, (hv[i] - bn_s[2][j0 + i]) * bn_s[3][j0 + i], accG[i]);
-        accB[i] += dd;
-        dyv[i] = dd * bn_s[0][j0 + i];                    // through BN -> dLoss/dh
+        dp[k] = TRAIN ? 2.f * d * coef * mk : 0.f;
+        if (TRAIN) accbo[k] += dp[k];
       }
-      uint4 o;
-      o.x = pack_bf16x2(dyv[0], dyv[1]);
-      o.y = pack_bf16x2(dyv[2], dyv[3]);
-      o.z = pack_bf16x2(dyv[4], dyv[5]);
-      o.w = pack_bf16x2(dyv[6], dyv[7]);
-      *reinterpret_cast<uint4*>(p.dhout + r * TC_H + j0) = o;
-    }
-  }
-  // CTA-level reduction of the per-warp accumulators (shared atomics: 8 warps, short)
-  if (p.y) {
-    if (TRAIN) {
+      if (TRAIN) {
+        if (valid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&red_s[j0 + i], accG[i]);
-        atomicAdd(&red_s[TC_H + j0 + i], accB[i]);
+          for (int k4 = 0; k4 < TC_OPAD; k4 += 4)
+            *reinterpret_cast<float4*>(p.dpred + r * TC_OPAD + k4) = make_float4(dp[k4], dp[k4 + 1], dp[k4 + 2], dp[k4 + 3]);
+        }
+        // dLoss/dh in the backward kernel's layout: [t][tile][rank r'][warp][chunk][lane][16]
+        __nv_bfloat16* dh_base = p.dhout + ((((long)t * n_tiles_cap + bt) * 4) * 4 + wq) * 4 * 32 * 16 + lane * 16;
+#pragma unroll 1
+        for (int grp = 0; grp < 8; ++grp) {          // 32 columns per group
+          float dd[32], gd[32];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c = grp * 4 + cc;
+            const uint4 raw = *reinterpret_cast<const uint4*>(hrow + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
+            const uint32_t hw[4] = {raw.x, raw.y, raw.z, raw.w};
+            float dm[8];
+            if (p.use_dropout) {
+              const uint64_t qbase = ((uint64_t)(p.row0 + b) * p.T + t) * nq + c * 2;
+              dropout_quad(p.key, qbase, dm);
+              dropout_quad(p.key, qbase + 1, dm + 4);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dm[e] = 1.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = c * 8 + e;
+              const float hv = (e & 1) ? bf16_hi(hw[e >> 1]) : bf16_lo(hw[e >> 1]);
+              const float4* w4 = reinterpret_cast<const float4*>(Wo_s + j * TC_OPAD);
+              float sacc = 0.f;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const float4 w = w4[kk];
+                sacc = fmaf(dp[4 * kk + 0], w.x, sacc);
+                sacc = fmaf(dp[4 * kk + 1], w.y, sacc);
+                sacc = fmaf(dp[4 * kk + 2], w.z, sacc);
+                sacc = fmaf(dp[4 * kk + 3], w.w, sacc);
+              }
+              const float d_ = sacc * dm[e];                       // through Dropout
+              dd[cc * 8 + e] = d_;
+              gd[cc * 8 + e] = d_ * (hv - bn_s[2][j]) * bn_s[3][j];
+            }
+          }
+          // dLoss/dh = dd * gamma * inv -> two 16-unit chunks of this group
+          if (valid) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int jj = hh * 16 + 2 * e;
+                pk[e] = pack_bf16x2(dd[jj] * bn_s[0][grp * 32 + jj], dd[jj + 1] * bn_s[0][grp * 32 + jj + 1]);
+              }
+              const int c16 = grp * 2 + hh;                         // 16-unit chunk 0..15: rank r' = c16/4, chunk c16%4
+              st_global_v8(dh_base + ((long)(c16 >> 2) * 4 * 4 + (c16 & 3)) * 32 * 16, pk);
+            }
+          }
+          // column sums over the warp's 32 rows: reduce-scatter butterfly, lane l ends with column perm(l)
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const bool up = (lane & off) != 0;
+              const float sd = up ? dd[i] : dd[i + off];
+              const float kd = up ? dd[i + off] : dd[i];
+              dd[i] = kd + __shfl_xor_sync(0xffffffffu, sd, off);
+              const float sg = up ? gd[i] : gd[i + off];
+              const float kg = up ? gd[i + off] : gd[i];
+              gd[i] = kg + __shfl_xor_sync(0xffffffffu, sg, off);
+            }
+          }
+          // lane's column within the group: bit b of lane selects +2^b  (lane bit4 -> +16 ... bit0 -> +1)
+          atomicAdd(&red_s[TC_H + grp * 32 + lane], dd[0]);
+          atomicAdd(&red_s[grp * 32 + lane], gd[0]);
+        }
       }
     }
-    if (owner) {
-      if (TRAIN) atomicAdd(&red_s[2 * TC_H + kown], accbo);
+    __syncthreads();        // everyone is done with the tile before it is overwritten
+  }
+  if (p.y) {
+    // block-level sums of the loss terms and dbo
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) accbo[k] = warp_sum(accbo[k]);
+    if (lane == 0) {
       atomicAdd(&red_s[2 * TC_H + TC_OPAD + 0], s0);
       atomicAdd(&red_s[2 * TC_H + TC_OPAD + 1], s1);
       atomicAdd(&red_s[2 * TC_H + TC_OPAD + 2], s2);
+      if (TRAIN)
+        for (int k = 0; k < TC_OPAD; ++k) atomicAdd(&red_s[2 * TC_H + k], accbo[k]);
     }
     __syncthreads();
-    for (int i = tid; i < HEAD_PART; i += HEAD_THREADS) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
+    for (int i = tid; i < HEAD_PART; i += 128) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
   }
 }
 
@@ -781,7 +807,7 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   m.Wp = reinterpret_cast<__nv_bfloat16*>(take(4 * H * 32 * 2));
   m.Ubk = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
-  m.head_ctas = 148;
+  m.head_ctas = 148 * 2;
   m.head_wctas = 148 * 2;
   m.head_part_elems = (size_t)m.head_ctas * HEAD_PART;
   m.head_part = reinterpret_cast<float*>(take(m.head_part_elems * 4));
@@ -790,7 +816,7 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
     m.gates = reinterpret_cast<__nv_bfloat16*>(take(Bt * T * 4 * H * 2));
     m.cst = reinterpret_cast<float*>(take(Bt * T * H * 4));
     m.dz = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * 4 * H * 2));
-    m.dhout = reinterpret_cast<__nv_bfloat16*>(take(B * T * H * 2));
+    m.dhout = reinterpret_cast<__nv_bfloat16*>(take(((B + 127) / 128 * 128) * T * H * 2));
     m.dc = nullptr;
     m.pexch = reinterpret_cast<__nv_bfloat16*>(take(((B + 127) / 128) * 2 * 16 * 128 * 64 * 2));
     m.dpred = reinterpret_cast<float*>(take(B * T * TC_OPAD * 4));
@@ -822,6 +848,9 @@ int tc_init(TcState& st, const lfmq_config& c) {
   int rc;
   if ((rc = make_map_2d(&m.tm_h, m.xh, xh_row, B, xh_row * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&m.tm_h128, m.xh, xh_row, B, xh_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
   if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -952,13 +981,19 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   h.dhout = train ? m.dhout : nullptr;
   h.dpred = train ? m.dpred : nullptr;
   h.partial = m.head_part;
+  const int n_btiles = (B + 127) / 128;
+  const int n_tiles_cap = (m.maxB + 127) / 128;
+  int grid = m.T * n_btiles;
+  if (grid > m.head_ctas) grid = m.head_ctas;
+  h.partial = m.head_part;
+  if (y) LFMQ_CUDA_CHECK(cudaMemsetAsync(m.head_part, 0, m.head_part_elems * sizeof(float), s));
   if (train) {
-    head_fused_kernel<true><<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
+    head_rows_kernel<true><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
     LFMQ_LAUNCH_CHECK();
     head_wgrad_kernel<<<m.head_wctas, 256, 0, s>>>(h, m.head_wpart);
     LFMQ_LAUNCH_CHECK();
   } else {
-    head_fused_kernel<false><<<m.head_ctas, HEAD_THREADS, 0, s>>>(h);
+    head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
     LFMQ_LAUNCH_CHECK();
   }
   if (y) {
@@ -1175,7 +1210,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         ld_global_v8(grow + (1 * 2 + hb) * 512, gf);
         ld_global_v8(grow + (2 * 2 + hb) * 512, gg);
         ld_global_v8(grow + (3 * 2 + hb) * 512, go);
-        ld_global_v8(p.dhout + (b * T + t) * TC_H + rank * 64 + jb * 16, dhp);
+        ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16, dhp);
         ld_global_v8f(crow + (hb * 2 + 0) * 256, ct);
         ld_global_v8f(crow + (hb * 2 + 1) * 256, ct + 8);
         if (t > 0) {
