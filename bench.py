@@ -199,20 +199,18 @@ def main():
             return eng.train_step_dp(x, y, i, lr, rank * B, denoms[i % NB])
         return eng.train_step(x, y, i, lr)
 
-    xd = torch.empty(B, T, F, dtype=torch.float32, device=dev)
-    yd = torch.empty(B, T, O, dtype=torch.float32, device=dev)
-    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    # e2e: the public host-batch API (lfm_quant_b200.engine.HostBatchPipeline): every step copies its own inputs
+    # from pinned host memory (H2D on a copy stream, overlapped with the previous step's compute) and reads its
+    # {loss, mse_0} back to the host.
+    from lfm_quant_b200.engine import HostBatchPipeline
+    if world > 1:
+        step_fn = lambda x, y, i, lr_: eng.train_step_dp(x, y, i, lr_, rank * B, denoms[i % NB])
+    else:
+        step_fn = None
+    pipe = HostBatchPipeline(eng, B, step_fn=step_fn)
 
     def step_e2e(i):
-        px, py = pinned[i % NB]
-        xd.copy_(px, non_blocking=True)                 # host -> device, inside the timed region
-        yd.copy_(py, non_blocking=True)
-        if world > 1:
-            out = eng.train_step_dp(xd, yd, i, lr, rank * B, denoms[i % NB])
-        else:
-            out = eng.train_step(xd, yd, i, lr)
-        loss_host.copy_(out, non_blocking=False)        # device -> host read of the step's result
-        return loss_host
+        return pipe.step(pinned[i % NB][0], pinned[i % NB][1], i, lr, next_batch=pinned[(i + 1) % NB])
 
     def sync():
         if world > 1:
@@ -254,8 +252,9 @@ def main():
         step_e2e(it)
         it += 1
     ms_e2e = timed(step_e2e, args.steps, it)
+    pipe.finish()
     it += args.steps
-    final = step_resident(it).float().cpu().numpy()
+    final = step_resident(it + 1).float().cpu().numpy()
 
     if rank == 0:
         value = world * B * args.steps / (ms * 1e-3)

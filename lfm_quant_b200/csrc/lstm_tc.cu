@@ -9,7 +9,7 @@
 //                                 i|f|g|o saved for BPTT.  Writer (forward) and reader (backward) both map one
 //                                 row to one thread, so the state is stored SoA at 32-byte granularity: a warp's
 //                                 256-bit access to `piece` covers 1 KB contiguously instead of 32 scattered sectors
-//   cst   f32  [T][tiles][8][4][4 pieces][32][8]    cell states, same scheme
+//   cst   bf16 [T][tiles][8][4][2 pieces][32][16]   cell states (the recurrence itself keeps them in fp32 registers)
 //   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
 //   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dLoss/dh from the head (after BN/dropout
 //                                 backward), already in the backward kernel's per-thread SoA order
@@ -86,7 +86,8 @@ struct TcImpl {
   int64_t oW, oU, ob, ogamma, obeta, oWo, obo, omean, ovar;
   // workspace
   __nv_bfloat16 *xh, *gates, *dz, *dhout, *Up, *Wp, *Ubk, *pexch;
-  float *cst, *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
+  __nv_bfloat16* cst;
+  float *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
   CUtensorMap tm_h128;                         // head: 128-row h tiles
@@ -159,7 +160,7 @@ struct FwdParams {
   int B, T, n_iters, n_clusters, k16_x, n_tiles_cap;
   __nv_bfloat16* xh;
   __nv_bfloat16* gates;   // null: do not save
-  float* cst;             // null: do not save
+  __nv_bfloat16* cst;     // null: do not save
   const float* biasp;
   long long* trace;       // debug (LFMQ_TRACE_FWD=1): clock64 stamps of CTA 0, every third step
 };
@@ -309,12 +310,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         tcgen05_fence_after();
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t taddr = tmem + lane_addr + (g & 1) * 256 + half * 32;
-        const uint32_t taddr_other = tmem + lane_addr + ((g + 1) & 1) * 256 + half * 96;
+        const uint32_t taddr_other = tmem + lane_addr + ((g + 1) & 1) * 256 + half * 80;
         __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + fr * 32;
         // saved state, SoA at 32-byte granularity: [(t, tile, fr, quadrant)][piece][lane]
         const long wblk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 4 + q;
         __nv_bfloat16* grow = p.gates ? p.gates + (wblk * 8 * 32 + lane) * 16 : nullptr;   // + piece * 512
-        float* crow = p.cst ? p.cst + (wblk * 4 * 32 + lane) * 8 : nullptr;                // + piece * 256
+        __nv_bfloat16* crow = p.cst ? p.cst + (wblk * 2 * 32 + lane) * 16 : nullptr;       // + piece * 512
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           uint32_t vi[16], vf[16], vg[16], vo[16];
@@ -352,15 +353,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           if (grow) {
             // Saved gates / cell states are not needed by the h exchange: park them in the idle accumulator
             // buffer (TMEM) and write them to HBM after the publish, off the per-step critical path.
-            const uint32_t tst = taddr_other + jb * 48;
-            uint32_t cu[16];
+            const uint32_t tst = taddr_other + jb * 40;
+            uint32_t cu[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) cu[e] = __float_as_uint(cn[e]);
+            for (int e = 0; e < 8; ++e) cu[e] = pack_bf16x2(cn[2 * e], cn[2 * e + 1]);
             tmem_st_32x32b_x8(tst, pi);
             tmem_st_32x32b_x8(tst + 8, pf);
             tmem_st_32x32b_x8(tst + 16, pg);
             tmem_st_32x32b_x8(tst + 24, po);
-            tmem_st_32x32b_x16(tst + 32, cu);
+            tmem_st_32x32b_x8(tst + 32, cu);
           }
         }
         if (grow) tmem_st_wait();
@@ -377,17 +378,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           tcgen05_fence_after();
 #pragma unroll
           for (int jb = 0; jb < 2; ++jb) {
-            uint32_t sg[32], sc[16];
-            tmem_ld_32x32b_x32(taddr_other + jb * 48, sg);
-            tmem_ld_32x32b_x16(taddr_other + jb * 48 + 32, sc);
+            uint32_t sg[32], sc[8];
+            tmem_ld_32x32b_x32(taddr_other + jb * 40, sg);
+            tmem_ld_32x32b_x8(taddr_other + jb * 40 + 32, sc);
             tmem_ld_wait();
             if (valid) {
               st_global_v8(grow + (0 * 2 + jb) * 512, sg);
               st_global_v8(grow + (1 * 2 + jb) * 512, sg + 8);
               st_global_v8(grow + (2 * 2 + jb) * 512, sg + 16);
               st_global_v8(grow + (3 * 2 + jb) * 512, sg + 24);
-              st_global_v8(crow + (jb * 2 + 0) * 256, sc);
-              st_global_v8(crow + (jb * 2 + 1) * 256, sc + 8);
+              st_global_v8(crow + jb * 512, sc);
             }
           }
           tcgen05_fence_before();
@@ -814,7 +814,7 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   if (!c.forward_only) {
     const size_t Bt = (B + 127) / 128 * 128;      // saved state is blocked by 128-row tiles
     m.gates = reinterpret_cast<__nv_bfloat16*>(take(Bt * T * 4 * H * 2));
-    m.cst = reinterpret_cast<float*>(take(Bt * T * H * 4));
+    m.cst = reinterpret_cast<__nv_bfloat16*>(take(Bt * T * H * 2));
     m.dz = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * 4 * H * 2));
     m.dhout = reinterpret_cast<__nv_bfloat16*>(take(((B + 127) / 128 * 128) * T * H * 2));
     m.dc = nullptr;
@@ -1062,7 +1062,7 @@ namespace lfmq {
 struct BwdParams {
   int B, T, n_iters, n_clusters, n_tiles_cap;
   const __nv_bfloat16* gates;
-  const float* cst;
+  const __nv_bfloat16* cst;
   const __nv_bfloat16* dhout;
   __nv_bfloat16* dz;
   __nv_bfloat16* pexch;      // [tile][parity][src][dst][128][64]
@@ -1195,36 +1195,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     const int sw = m & 7;
     float dc[32];
     uint32_t gs = 0, n_rf = 0;
-    // inputs of one chunk
-    uint32_t gi[8], gf[8], gg[8], go[8], dhp[8];
-    float ct[16], cp[16];
-    const long tstride = (long)p.n_tiles_cap * 8 * 128;            // saved-state block rows per time step
+    // inputs of this set's two chunks of one step (slot ci): loaded ahead of the exchange they do not depend on
+    uint32_t gi[2][8], gf[2][8], gg[2][8], go[2][8], dhp[2][8], ct[2][8], cp[2][8];
+    const long tstride = (long)p.n_tiles_cap * 8 * 4 * 2 * 32 * 16;   // cst elements per time step
 
-    auto load_chunk = [&](int tile, long b, bool valid, int t, int jb) {
+    auto load_chunk = [&](int ci, int tile, bool valid, int t) {
+      const int jb = 2 * ci + set;
       if (valid) {
         const long wblk = (((long)t * p.n_tiles_cap + tile) * 8 + 2 * rank + (jb >> 1)) * 4 + wq;
         const int hb = jb & 1;
         const __nv_bfloat16* grow = p.gates + (wblk * 8 * 32 + lane) * 16;
-        const float* crow = p.cst + (wblk * 4 * 32 + lane) * 8;
-        ld_global_v8(grow + (0 * 2 + hb) * 512, gi);
-        ld_global_v8(grow + (1 * 2 + hb) * 512, gf);
-        ld_global_v8(grow + (2 * 2 + hb) * 512, gg);
-        ld_global_v8(grow + (3 * 2 + hb) * 512, go);
-        ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16, dhp);
-        ld_global_v8f(crow + (hb * 2 + 0) * 256, ct);
-        ld_global_v8f(crow + (hb * 2 + 1) * 256, ct + 8);
+        const __nv_bfloat16* crow = p.cst + ((wblk * 2 + hb) * 32 + lane) * 16;
+        ld_global_v8(grow + (0 * 2 + hb) * 512, gi[ci]);
+        ld_global_v8(grow + (1 * 2 + hb) * 512, gf[ci]);
+        ld_global_v8(grow + (2 * 2 + hb) * 512, gg[ci]);
+        ld_global_v8(grow + (3 * 2 + hb) * 512, go[ci]);
+        ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16,
+                     dhp[ci]);
+        ld_global_v8(crow, ct[ci]);
         if (t > 0) {
-          ld_global_v8f(crow - tstride * 32 + (hb * 2 + 0) * 256, cp);
-          ld_global_v8f(crow - tstride * 32 + (hb * 2 + 1) * 256, cp + 8);
+          ld_global_v8(crow - tstride, cp[ci]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) cp[j] = 0.f;
+          for (int j = 0; j < 8; ++j) cp[ci][j] = 0u;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gi[j] = gf[j] = gg[j] = go[j] = dhp[j] = 0u;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ct[j] = cp[j] = 0.f;
+        for (int j = 0; j < 8; ++j)
+          gi[ci][j] = gf[ci][j] = gg[ci][j] = go[ci][j] = dhp[ci][j] = ct[ci][j] = cp[ci][j] = 0u;
       }
     };
 
@@ -1234,7 +1232,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       const bool valid = b < p.B;
 #pragma unroll
       for (int j = 0; j < 32; ++j) dc[j] = 0.f;
-      load_chunk(tile, b, valid, T - 1, set);
+      load_chunk(0, tile, valid, T - 1);
+      load_chunk(1, tile, valid, T - 1);
       for (int t = T - 1; t >= 0; --t, ++gs) {
         const bool has_rec = t < T - 1;
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
@@ -1244,7 +1243,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int jb = 2 * ci + set;
-          if (ci == 1) load_chunk(tile, b, valid, t, jb);
           float rec[16];
           if (has_rec) {
             uint32_t vr[16];
@@ -1277,16 +1275,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int j = jj + u;
-              const float i_ = u ? bf16_hi(gi[jj / 2]) : bf16_lo(gi[jj / 2]);
-              const float f_ = u ? bf16_hi(gf[jj / 2]) : bf16_lo(gf[jj / 2]);
-              const float g_ = u ? bf16_hi(gg[jj / 2]) : bf16_lo(gg[jj / 2]);
-              const float o_ = u ? bf16_hi(go[jj / 2]) : bf16_lo(go[jj / 2]);
-              const float dh = (u ? bf16_hi(dhp[jj / 2]) : bf16_lo(dhp[jj / 2])) + rec[j];
-              const float tc = tanh_approx(ct[j]);
+              const float i_ = u ? bf16_hi(gi[ci][jj / 2]) : bf16_lo(gi[ci][jj / 2]);
+              const float f_ = u ? bf16_hi(gf[ci][jj / 2]) : bf16_lo(gf[ci][jj / 2]);
+              const float g_ = u ? bf16_hi(gg[ci][jj / 2]) : bf16_lo(gg[ci][jj / 2]);
+              const float o_ = u ? bf16_hi(go[ci][jj / 2]) : bf16_lo(go[ci][jj / 2]);
+              const float dh = (u ? bf16_hi(dhp[ci][jj / 2]) : bf16_lo(dhp[ci][jj / 2])) + rec[j];
+              const float c_t = u ? bf16_hi(ct[ci][jj / 2]) : bf16_lo(ct[ci][jj / 2]);
+              const float c_p = u ? bf16_hi(cp[ci][jj / 2]) : bf16_lo(cp[ci][jj / 2]);
+              const float tc = tanh_approx(c_t);
               const float d_o = dh * tc;
               const float dcn = dc[ci * 16 + j] + dh * o_ * (1.f - tc * tc);
               ri[u] = dcn * g_ * i_ * (1.f - i_);
-              rf[u] = dcn * cp[j] * f_ * (1.f - f_);
+              rf[u] = dcn * c_p * f_ * (1.f - f_);
               rg[u] = dcn * i_ * (1.f - g_ * g_);
               ro[u] = d_o * o_ * (1.f - o_);
               dc[ci * 16 + j] = dcn * f_;
@@ -1319,8 +1319,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           if (tid == 64 && ci == 0) BWD_TRACE(2, T - 1 - t, 1);
           if (tid == 64 && ci == 1) BWD_TRACE(2, T - 1 - t, 2);
         }
-        // inputs of this set's first chunk of the next step: independent of the exchange below
-        if (t > 0) load_chunk(tile, b, valid, t - 1, set);
+        // inputs of both chunks of the next step: independent of the exchange below
+        if (t > 0) {
+          load_chunk(0, tile, valid, t - 1);
+          load_chunk(1, tile, valid, t - 1);
+        }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
           mbar_wait(&bars->acc_full[gs & 1], (gs >> 1) & 1);

@@ -207,6 +207,66 @@ class ForecasterEngine(object):
         return int(self.lib.lfmq_launch_count())
 
 
+class HostBatchPipeline(object):
+    """Feeds host-resident (pinned) batches to a ForecasterEngine with the H2D copy of step i+1 overlapped with the
+    compute of step i (two device buffers, one copy stream) and an asynchronous D2H read of every step's
+    {loss, mse_0}.  Each step still copies its own inputs host->device and its result device->host.
+
+        pipe = HostBatchPipeline(engine, batch)
+        for i, (x_pinned, y_pinned) in enumerate(batches):
+            loss_mse = pipe.step(x_pinned, y_pinned, i, lr)     # host tensor of the PREVIOUS step (None at i=0)
+        last = pipe.finish()
+    """
+
+    def __init__(self, engine, batch, step_fn=None):
+        self.eng = engine
+        dev = engine.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.x = [torch.empty(batch, engine.T, engine.F, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.y = [torch.empty(batch, engine.T, engine.O, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.out_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.out_ready = [torch.cuda.Event() for _ in range(2)]
+        self.step_fn = step_fn or (lambda x, y, i, lr: engine.train_step(x, y, i, lr))
+        self.n = 0
+        self._staged = None
+
+    def _stage(self, x_host, y_host, slot):
+        with torch.cuda.stream(self.copy_stream):
+            if self.n >= 2:
+                self.copy_stream.wait_event(self.consumed[slot])      # the step that used this buffer is done
+            self.x[slot].copy_(x_host, non_blocking=True)
+            self.y[slot].copy_(y_host, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+
+    def step(self, x_host, y_host, index, lr, next_batch=None):
+        """Runs one step on (x_host, y_host); `next_batch` (optional) is staged while it computes."""
+        slot = self.n & 1
+        if self._staged != self.n:
+            self._stage(x_host, y_host, slot)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.copied[slot])
+        out = self.step_fn(self.x[slot], self.y[slot], index, lr)
+        self.consumed[slot].record(cur)
+        self.out_host[slot].copy_(out, non_blocking=True)
+        self.out_ready[slot].record(cur)
+        self.n += 1
+        if next_batch is not None:
+            self._stage(next_batch[0], next_batch[1], self.n & 1)
+            self._staged = self.n
+        prev = None
+        if self.n >= 2:
+            self.out_ready[slot ^ 1].synchronize()
+            prev = self.out_host[slot ^ 1]
+        return prev
+
+    def finish(self):
+        slot = (self.n - 1) & 1
+        self.out_ready[slot].synchronize()
+        return self.out_host[slot]
+
+
 def gather_batch(table, inp_idx, tar_idx, *, seq_len, stride, inp_cols, fin_cols, seq_norm_col, center, scale,
                  scale_flag, aux_flag, log_squasher=True, aux_masking=False):
     """Device batcher: Dataset.get_batch (scripts/data_processing.py:307-368) over a CUDA-resident fp64 table.
