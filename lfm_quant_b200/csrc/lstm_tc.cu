@@ -82,6 +82,7 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
 struct TcImpl {
   bool enabled = false;
   int maxB = 0, T = 0, I = 0, O = 0;
+  float eps = 1e-3f;
   // parameter offsets in the flat fp32 vector (L = 1)
   int64_t oW, oU, ob, ogamma, obeta, oWo, obo, omean, ovar;
   // workspace
@@ -90,7 +91,9 @@ struct TcImpl {
   float *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
-  CUtensorMap tm_h128;                         // head: 128-row h tiles
+  CUtensorMap tm_h128, tm_wot, tm_wop;         // head: 128-row h tiles, folded head weights
+  __nv_bfloat16 *WoTp, *Wop;
+  float* bop;
   CUtensorMap tm_ubk, tm_px;                   // backward recurrence
   CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
   int max_clusters = 0, bwd_max_clusters = 0;
@@ -655,6 +658,347 @@ __global__ void __launch_bounds__(128, 2) head_rows_kernel(HeadParams p, const _
   }
 }
 
+// Tensor-core head (dropout off): with y = a*h + b (BN inference affine) the Dense layer folds to
+//   pred = h * (diag(a) Wo) + (bo + b Wo),   dy = dpred * Wo^T,   dLoss/dh = dy * a
+// so both row-by-256 contractions become tcgen05 MMAs on the TMA-staged h tile (K-major SW128, exactly the layout the
+// recurrence uses): pred = 16 x (M128 N16 K16), dy = 2 x (M128 N128 K16) with dpred staged as a 128 x 32 bf16 tile.
+// Threads own one row each for the loss terms, the dgamma/dbeta column sums and the dLoss/dh stores.
+struct HeadTcWeights {
+  const __nv_bfloat16* WoTp;   // [16][256]  a_j * Wo[j][n]
+  const __nv_bfloat16* Wop;    // [256][32]  Wo[j][k] (k < 16), zero padded
+  const float* bop;            // [16]       bo + sum_j b_j Wo[j][k]
+};
+
+__global__ void pack_head_kernel(int O, const float* __restrict__ Wo, const float* __restrict__ bo,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                 __nv_bfloat16* __restrict__ WoTp, __nv_bfloat16* __restrict__ Wop,
+                                 float* __restrict__ bop) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < TC_OPAD * TC_H) {
+    const int n = idx / TC_H, j = idx % TC_H;
+    const float a = gamma[j] / sqrtf(var[j] + eps);
+    WoTp[idx] = __float2bfloat16(n < O ? a * Wo[j * O + n] : 0.f);
+  }
+  if (idx < TC_H * 32) {
+    const int j = idx / 32, k = idx % 32;
+    Wop[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
+  }
+  if (idx < TC_OPAD) {
+    float s = (idx < O) ? bo[idx] : 0.f;
+    if (idx < O)
+      for (int j = 0; j < TC_H; ++j) {
+        const float iv = 1.0f / sqrtf(var[j] + eps);
+        s += (beta[j] - gamma[j] * mean[j] * iv) * Wo[j * O + idx];
+      }
+    bop[idx] = s;
+  }
+}
+
+constexpr uint32_t HT_TILE = 0;            // 4 k-blocks x [128 x 128 B]
+constexpr uint32_t HT_WOT = 65536;         // 4 k-blocks x [16 x 128 B]
+constexpr uint32_t HT_WOP = 73728;         // [256 x 64 B]
+constexpr uint32_t HT_DP = 90112;          // [128 x 64 B]
+constexpr uint32_t HT_BARS = 98304;
+constexpr int HT_SMEM = HT_BARS + 128 + 1024;
+constexpr int HT_THREADS = 160;            // warp 0: TMA + MMA issue, warps 1-4: one row per thread
+
+struct HtBars {
+  uint64_t wt_full, tile_full, pred_full, dp_full, dy_full[2], y0_free, tile_free, w_done;
+  uint32_t tmem_base;
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(HT_THREADS, 2)
+    head_tc_kernel(HeadParams p, HeadTcWeights w, const __grid_constant__ CUtensorMap tm_h,
+                   const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_wop, int n_btiles,
+                   int n_tiles_cap, float* __restrict__ wpartial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  HtBars* bars = reinterpret_cast<HtBars*>(smem + HT_BARS);
+  __shared__ __align__(16) float bn_s[3][TC_H];      // gamma*inv | mean | inv
+  __shared__ float red_s[HEAD_PART];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < TC_H; j += HT_THREADS) {
+    const float iv = 1.0f / sqrtf(p.var[j] + p.eps);
+    bn_s[0][j] = p.gamma[j] * iv;
+    bn_s[1][j] = p.mean[j];
+    bn_s[2][j] = iv;
+  }
+  for (int i = tid; i < HEAD_PART; i += HT_THREADS) red_s[i] = 0.f;
+  // zero the dpred staging tile once (padding columns stay zero)
+  for (int i = tid; i < 128 * 64 / 16; i += HT_THREADS) reinterpret_cast<uint4*>(smem + HT_DP)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bars->wt_full, 1);
+    mbar_init(&bars->tile_full, 1);
+    mbar_init(&bars->pred_full, 1);
+    mbar_init(&bars->dp_full, 128);
+    mbar_init(&bars->dy_full[0], 1);
+    mbar_init(&bars->dy_full[1], 1);
+    mbar_init(&bars->y0_free, 128);
+    mbar_init(&bars->tile_free, 128);
+    mbar_init(&bars->w_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&bars->tmem_base, 256);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t acc_p = tmem;             // 16 columns
+  const uint32_t acc_y = tmem + 32;        // 128 columns
+  const uint32_t acc_w = tmem + 160;       // 2 x 16 columns: sum over this CTA's tiles of h^T dpred (rows = hidden unit)
+  const int n_tiles = p.T * n_btiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->wt_full, 8192 + 16384);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + HT_WOT + kb * 2048, &tm_wot, &bars->wt_full, kb * 64, 0);
+      tma_load_2d(smem + HT_WOP, &tm_wop, &bars->wt_full, 0, 0);
+      mbar_wait(&bars->wt_full, 0);
+      const uint32_t idesc_p = make_idesc_bf16(128, 16, false, false);
+      const uint32_t idesc_y = make_idesc_bf16(128, 128, false, false);
+      uint32_t n = 0;
+      for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++n) {
+        const int t = ti / n_btiles, bt = ti % n_btiles;
+        if (n > 0) mbar_wait(&bars->tile_free, (n - 1) & 1);
+        mbar_arrive_expect_tx(&bars->tile_full, 65536);
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(smem + HT_TILE + kb * 16384, &tm_h, &bars->tile_full, (t + 1) * TC_XH_LD + kb * 64, bt * 128);
+        mbar_wait(&bars->tile_full, n & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t da = make_smem_desc(smem_u32(smem + HT_TILE + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+            const uint64_t db = make_smem_desc(smem_u32(smem + HT_WOT + kb * 2048) + k16 * 32, 0, 1024, LAYOUT_SW128);
+            umma_f16(acc_p, da, db, idesc_p, (kb | k16) != 0);
+          }
+        umma_commit(&bars->pred_full);
+        if (TRAIN) {
+          mbar_wait(&bars->dp_full, n & 1);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem + HT_DP), 0, 512, LAYOUT_SW64);
+          umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP), 0, 512, LAYOUT_SW64), idesc_y, 0);
+          umma_commit(&bars->dy_full[0]);
+          // dWo' += h^T dpred: A = the h tile read MN-major (hidden unit = M), B = the dpred tile read MN-major,
+          // K = the 128 rows.  Issued before the second dy half so that dy_full[1] also covers these MMAs.
+          {
+            const uint32_t idesc_w = make_idesc_bf16(128, 16, true, true);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int k16 = 0; k16 < 8; ++k16) {
+                const uint64_t wa = make_smem_desc(smem_u32(smem + HT_TILE + 2 * mb * 16384) + k16 * 2048, 16384, 1024,
+                                                   LAYOUT_SW128);
+                const uint64_t wb = make_smem_desc(smem_u32(smem + HT_DP) + k16 * 1024, 0, 512, LAYOUT_SW64);
+                umma_f16(acc_w + mb * 16, wa, wb, idesc_w, (n > 0 || k16 > 0) ? 1u : 0u);
+              }
+          }
+          mbar_wait(&bars->y0_free, n & 1);
+          tcgen05_fence_after();
+          umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP + 8192), 0, 512, LAYOUT_SW64), idesc_y, 0);
+          umma_commit(&bars->dy_full[1]);
+        }
+      }
+      if (TRAIN) umma_commit(&bars->w_done);
+    }
+  } else {
+    const int m = tid - 32;                 // row of the tile
+    const int wq = warp & 3;                // TMEM lane quadrant of this warp
+    const int mrow = wq * 32 + lane;        // row this thread can reach in TMEM == row it owns
+    (void)m;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
+    if (TRAIN) {
+      const float Bg = p.denom[0], Mg = p.denom[1];
+      c_all = (1.f - p.p1) * (1.f - p.p2) / ((float)p.O * Mg);
+      c_last = (1.f - p.p1) * p.p2 / (Bg * (float)p.O);
+      c_tar = p.p1 / Bg;
+    }
+    float bop[TC_OPAD];
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) bop[k] = w.bop[k];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float accbo[TC_OPAD];
+#pragma unroll
+    for (int k = 0; k < TC_OPAD; ++k) accbo[k] = 0.f;
+    const int sw = mrow & 7;
+    uint32_t n = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++n) {
+      const int t = ti / n_btiles, bt = ti % n_btiles;
+      const long b = (long)bt * 128 + mrow;
+      const bool valid = b < p.B;
+      const long r = b * p.T + t;
+      float yt[TC_OPAD];
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) yt[k] = 0.f;
+      if (p.y && valid) {
+#pragma unroll
+        for (int k = 0; k < TC_OPAD; ++k)
+          if (k < p.O) yt[k] = p.y[r * p.O + k];
+      }
+      mbar_wait(&bars->pred_full, n & 1);
+      tcgen05_fence_after();
+      uint32_t pv[16];
+      tmem_ld_32x32b_x16(acc_p + lane_addr, pv);
+      tmem_ld_wait();
+      float pr[TC_OPAD];
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) pr[k] = __uint_as_float(pv[k]) + bop[k];
+      if (p.preds && valid) {
+#pragma unroll
+        for (int k = 0; k < TC_OPAD; ++k)
+          if (k < p.O) p.preds[r * p.O + k] = pr[k];
+      }
+      if (p.y) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < TC_OPAD; ++k) any |= (yt[k] != 0.0f);          // losses.py:72
+        const float mk = (any && valid) ? 1.f : 0.f;
+        const bool last = (t == p.T - 1);
+        float dp[TC_OPAD];
+#pragma unroll
+        for (int k = 0; k < TC_OPAD; ++k) {
+          const float d = (k < p.O && valid) ? (pr[k] * mk - yt[k]) : 0.f;  // losses.py:75
+          const float d2 = d * d;
+          s2 += d2;
+          float coef = c_all;
+          if (last) {
+            s1 += d2;
+            coef += c_last;
+            if (k == p.target_idx) {
+              s0 += d2;
+              coef += c_tar;
+            }
+          }
+          dp[k] = TRAIN ? 2.f * d * coef * mk : 0.f;
+          if (TRAIN) accbo[k] += dp[k];
+        }
+        if (TRAIN) {
+          if (valid) {
+#pragma unroll
+            for (int k4 = 0; k4 < TC_OPAD; k4 += 4)
+              *reinterpret_cast<float4*>(p.dpred + r * TC_OPAD + k4) = make_float4(dp[k4], dp[k4 + 1], dp[k4 + 2], dp[k4 + 3]);
+          }
+          // dpred row -> A operand tile [128 x 64 B], SWIZZLE_64B: chunk c of row m at m*64 + ((c ^ ((m>>1)&3)) << 4)
+          uint8_t* drow = smem + HT_DP + mrow * 64;
+          const int s64 = (mrow >> 1) & 3;
+          *reinterpret_cast<uint4*>(drow + ((0 ^ s64) << 4)) =
+              make_uint4(pack_bf16x2(dp[0], dp[1]), pack_bf16x2(dp[2], dp[3]), pack_bf16x2(dp[4], dp[5]), pack_bf16x2(dp[6], dp[7]));
+          *reinterpret_cast<uint4*>(drow + ((1 ^ s64) << 4)) =
+              make_uint4(pack_bf16x2(dp[8], dp[9]), pack_bf16x2(dp[10], dp[11]), pack_bf16x2(dp[12], dp[13]), pack_bf16x2(dp[14], dp[15]));
+          fence_proxy_async_smem();
+          mbar_arrive(&bars->dp_full);
+          __nv_bfloat16* dh_base = p.dhout + ((((long)t * n_tiles_cap + bt) * 4) * 4 + wq) * 4 * 32 * 16 + lane * 16;
+          const uint8_t* hrow = smem + HT_TILE + mrow * 128;
+#pragma unroll 1
+          for (int hN = 0; hN < 2; ++hN) {
+            mbar_wait(&bars->dy_full[hN], n & 1);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int g4 = 0; g4 < 4; ++g4) {                 // 32 columns per group
+              const int grp = hN * 4 + g4;
+              uint32_t dv[32];
+              tmem_ld_32x32b_x32(acc_y + lane_addr + g4 * 32, dv);
+              tmem_ld_wait();
+              float dd[32], gd[32];
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int c = grp * 4 + cc;
+                const uint4 raw = *reinterpret_cast<const uint4*>(hrow + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
+                const uint32_t hw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int j = c * 8 + e;
+                  const float hv = valid ? ((e & 1) ? bf16_hi(hw[e >> 1]) : bf16_lo(hw[e >> 1])) : 0.f;
+                  const float d_ = valid ? __uint_as_float(dv[cc * 8 + e]) : 0.f;
+                  dd[cc * 8 + e] = d_;
+                  gd[cc * 8 + e] = d_ * (hv - bn_s[1][j]) * bn_s[2][j];
+                }
+              }
+              if (valid) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int jj = hh * 16 + 2 * e;
+                    pk[e] = pack_bf16x2(dd[jj] * bn_s[0][grp * 32 + jj], dd[jj + 1] * bn_s[0][grp * 32 + jj + 1]);
+                  }
+                  const int c16 = grp * 2 + hh;
+                  st_global_v8(dh_base + ((long)(c16 >> 2) * 4 * 4 + (c16 & 3)) * 32 * 16, pk);
+                }
+              }
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                  const bool up = (lane & off) != 0;
+                  const float sd = up ? dd[i] : dd[i + off];
+                  const float kd = up ? dd[i + off] : dd[i];
+                  dd[i] = kd + __shfl_xor_sync(0xffffffffu, sd, off);
+                  const float sg = up ? gd[i] : gd[i + off];
+                  const float kg = up ? gd[i + off] : gd[i];
+                  gd[i] = kg + __shfl_xor_sync(0xffffffffu, sg, off);
+                }
+              }
+              atomicAdd(&red_s[TC_H + grp * 32 + lane], dd[0]);
+              atomicAdd(&red_s[grp * 32 + lane], gd[0]);
+            }
+            tcgen05_fence_before();
+            if (hN == 0) mbar_arrive(&bars->y0_free);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&bars->tile_free);
+    }
+    if (p.y) {
+      s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+#pragma unroll
+      for (int k = 0; k < TC_OPAD; ++k) accbo[k] = warp_sum(accbo[k]);
+      if (lane == 0) {
+        atomicAdd(&red_s[2 * TC_H + TC_OPAD + 0], s0);
+        atomicAdd(&red_s[2 * TC_H + TC_OPAD + 1], s1);
+        atomicAdd(&red_s[2 * TC_H + TC_OPAD + 2], s2);
+        if (TRAIN)
+          for (int k = 0; k < TC_OPAD; ++k) atomicAdd(&red_s[2 * TC_H + k], accbo[k]);
+      }
+    }
+    if (TRAIN) {
+      // this CTA's h^T dpred: TMEM lane = hidden unit (mod 128), 16 columns per 128-unit block
+      float* wp = wpartial + (long)blockIdx.x * HWG_PART;
+      if (n > 0) {
+        mbar_wait(&bars->w_done, 0);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(acc_w + lane_addr + mb * 16, v);
+          tmem_ld_wait();
+          float* o = wp + (mb * 128 + mrow) * TC_OPAD;
+#pragma unroll
+          for (int k4 = 0; k4 < 16; k4 += 4)
+            *reinterpret_cast<float4*>(o + k4) = make_float4(__uint_as_float(v[k4]), __uint_as_float(v[k4 + 1]),
+                                                             __uint_as_float(v[k4 + 2]), __uint_as_float(v[k4 + 3]));
+        }
+      } else {
+        for (int mb = 0; mb < 2; ++mb)
+          for (int k = 0; k < TC_OPAD; ++k) wp[(mb * 128 + mrow) * TC_OPAD + k] = 0.f;
+      }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (p.y)
+    for (int i = tid; i < HEAD_PART; i += HT_THREADS) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // dWo[j][k] = sum_r y[r][j] * dpred[r][k] with y = Dropout(BN(h)) recomputed from h: CTA tiles of 32 rows staged in
 // shared memory, thread (j-group of 4, k-group of 4) keeps a 4x4 block of the 256 x 16 result.
 __global__ void __launch_bounds__(256, 2) head_wgrad_kernel(HeadParams p, float* __restrict__ wpartial) {
@@ -739,7 +1083,9 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_kernel(HeadParams p, float*
 __global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial, int n_wcta,
                                    const float* __restrict__ wpartial, int O, int B, const float* denom, float p1,
                                    float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
-                                   float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2) {
+                                   float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2,
+                                   int fold, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ var, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < HWG_PART) {
     if (train) {
@@ -747,6 +1093,14 @@ __global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial,
       if (k < O) {
         double s = 0.0;
         for (int c = 0; c < n_wcta; ++c) s += wpartial[(long)c * HWG_PART + i];
+        if (fold) {
+          // wpartial holds h^T dpred; y = a*h + b  =>  dWo = a_j * (h^T dpred) + b_j * colsum(dpred)
+          double dbo = 0.0;
+          for (int c = 0; c < n_cta; ++c) dbo += partial[(long)c * HEAD_PART + 2 * TC_H + k];
+          const double iv = 1.0 / sqrt((double)var[j] + eps);
+          const double a = gamma[j] * iv, bb = beta[j] - gamma[j] * mean[j] * iv;
+          s = a * s + bb * dbo;
+        }
         gWo[j * O + k] = (float)s;
       }
     }
@@ -802,11 +1156,15 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   };
   const size_t B = (size_t)c.max_batch, T = (size_t)c.seq_len, H = TC_H;
   m.maxB = c.max_batch; m.T = c.seq_len; m.I = c.n_inputs; m.O = c.n_outputs;
+  m.eps = c.bn_epsilon;
   m.xh = reinterpret_cast<__nv_bfloat16*>(take(B * (T + 1) * TC_XH_LD * 2));
   m.Up = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.Wp = reinterpret_cast<__nv_bfloat16*>(take(4 * H * 32 * 2));
   m.Ubk = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
+  m.WoTp = reinterpret_cast<__nv_bfloat16*>(take(TC_OPAD * H * 2));
+  m.Wop = reinterpret_cast<__nv_bfloat16*>(take(H * 32 * 2));
+  m.bop = reinterpret_cast<float*>(take(TC_OPAD * 4));
   m.head_ctas = 148 * 2;
   m.head_wctas = 148 * 2;
   m.head_part_elems = (size_t)m.head_ctas * HEAD_PART;
@@ -849,6 +1207,10 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if ((rc = make_map_2d(&m.tm_h, m.xh, xh_row, B, xh_row * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&m.tm_h128, m.xh, xh_row, B, xh_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_wot, m.WoTp, TC_H, TC_OPAD, TC_H * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&m.tm_wop, m.Wop, 32, TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
   if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -891,6 +1253,10 @@ static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   const long n = (long)4 * TC_H * TC_H;
   pack_weights_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(m.I, params + m.oW, params + m.oU, params + m.ob, m.Up,
                                                            m.Wp, m.biasp);
+  LFMQ_LAUNCH_CHECK();
+  pack_head_kernel<<<(TC_H * 32 + 255) / 256, 256, 0, s>>>(m.O, params + m.oWo, params + m.obo, params + m.ogamma,
+                                                        params + m.obeta, params + m.omean, params + m.ovar, m.eps,
+                                                        m.WoTp, m.Wop, m.bop);
   LFMQ_LAUNCH_CHECK();
   if (m.pexch) {   // training handle: K-slices of U for the backward recurrence
     pack_ubk_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(params + m.oU, m.Ubk);
@@ -987,20 +1353,36 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   if (grid > m.head_ctas) grid = m.head_ctas;
   h.partial = m.head_part;
   if (y) LFMQ_CUDA_CHECK(cudaMemsetAsync(m.head_part, 0, m.head_part_elems * sizeof(float), s));
+  HeadTcWeights hw;
+  hw.WoTp = m.WoTp; hw.Wop = m.Wop; hw.bop = m.bop;
+  const bool use_tc = !h.use_dropout;       // the BN fold into the head weights needs y = a*h + b
+  int n_wcta = m.head_wctas;
   if (train) {
-    head_rows_kernel<true><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
-    LFMQ_LAUNCH_CHECK();
-    head_wgrad_kernel<<<m.head_wctas, 256, 0, s>>>(h, m.head_wpart);
-    LFMQ_LAUNCH_CHECK();
+    if (use_tc) {
+      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, n_btiles,
+                                                             n_tiles_cap, m.head_wpart);
+      LFMQ_LAUNCH_CHECK();
+      n_wcta = grid;
+    } else {
+      head_rows_kernel<true><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
+      LFMQ_LAUNCH_CHECK();
+      head_wgrad_kernel<<<m.head_wctas, 256, 0, s>>>(h, m.head_wpart);
+      LFMQ_LAUNCH_CHECK();
+    }
   } else {
-    head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
+    if (use_tc)
+      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, n_btiles,
+                                                              n_tiles_cap, nullptr);
+    else
+      head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
     LFMQ_LAUNCH_CHECK();
   }
   if (y) {
     head_reduce_kernel<<<(HWG_PART + HEAD_PART + 255) / 256, 256, 0, s>>>(
-        m.head_ctas, m.head_part, m.head_wctas, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda,
+        m.head_ctas, m.head_part, n_wcta, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda,
         train ? 1 : 0, grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr,
-        grads ? grads + m.ogamma : nullptr, grads ? grads + m.obeta : nullptr, out2);
+        grads ? grads + m.ogamma : nullptr, grads ? grads + m.obeta : nullptr, out2, (train && use_tc) ? 1 : 0,
+        params + m.ogamma, params + m.obeta, params + m.omean, params + m.ovar, c.bn_epsilon);
     LFMQ_LAUNCH_CHECK();
   }
   return 0;
