@@ -479,11 +479,39 @@ __global__ void loss_final_kernel(int nblk, const double* __restrict__ partial, 
   out[1] = (float)mse0;
 }
 
+// mask count (losses.py:72-73,132): one thread per [b,t] row, warp ballot, one integer atomic per warp
+// (integer adds commute: the count is exact and deterministic).
+__global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, const float* __restrict__ y,
+                                                        unsigned int* __restrict__ counter) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool any = false;
+  if (r < rows) {
+    const float* yr = y + r * O;
+    if ((O & 3) == 0) {
+      for (int k = 0; k < O; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(yr + k);
+        any |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+      }
+    } else {
+      for (int k = 0; k < O; ++k) any |= (yr[k] != 0.f);
+    }
+  }
+  const unsigned int bal = __ballot_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counter, (unsigned int)__popc(bal));
+}
+
+__global__ void mask_final_kernel(int B, const unsigned int* __restrict__ counter, float* __restrict__ out2) {
+  out2[0] = (float)B;
+  out2[1] = (float)(*counter);
+}
+
 int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, float* scratch) {
-  double* partial = reinterpret_cast<double*>(scratch);
-  loss_rows_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(B, T, O, nullptr, y, nullptr, 0, 0.f, 0.f, nullptr, partial);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  LFMQ_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  const long rows = (long)B * T;
+  mask_rows_kernel<<<cdiv(rows, 256), 256, 0, s>>>(rows, O, y, counter);
   LFMQ_LAUNCH_CHECK();
-  loss_final_kernel<<<1, 32, 0, s>>>(LOSS_BLOCKS, partial, nullptr, B, O, 0.f, 0.f, 0, nullptr, out2);
+  mask_final_kernel<<<1, 1, 0, s>>>(B, counter, out2);
   LFMQ_LAUNCH_CHECK();
   return 0;
 }

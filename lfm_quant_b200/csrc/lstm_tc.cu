@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(128, 2) head_rows_kernel(HeadParams p, const _
         for (int k = 0; k < TC_OPAD; ++k) atomicAdd(&red_s[2 * TC_H + k], accbo[k]);
     }
     __syncthreads();
-    for (int i = tid; i < HEAD_PART; i += 128) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
+    for (int i = tid; i < HEAD_PART; i += 128) p.partial[(long)i * gridDim.x + blockIdx.x] = red_s[i];
   }
 }
 
@@ -684,14 +684,23 @@ __global__ void pack_head_kernel(int O, const float* __restrict__ Wo, const floa
     const int j = idx / 32, k = idx % 32;
     Wop[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
   }
-  if (idx < TC_OPAD) {
-    float s = (idx < O) ? bo[idx] : 0.f;
-    if (idx < O)
-      for (int j = 0; j < TC_H; ++j) {
-        const float iv = 1.0f / sqrtf(var[j] + eps);
-        s += (beta[j] - gamma[j] * mean[j] * iv) * Wo[j * O + idx];
-      }
-    bop[idx] = s;
+  // folded bias: block k (< 16) reduces over its 256 threads = 256 hidden units
+  if (blockIdx.x < TC_OPAD) {
+    __shared__ float red[8];
+    const int k = blockIdx.x, j = threadIdx.x;
+    float v = 0.f;
+    if (k < O) {
+      const float iv = 1.0f / sqrtf(var[j] + eps);
+      v = (beta[j] - gamma[j] * mean[j] * iv) * Wo[j * O + k];
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = (k < O) ? bo[k] : 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      bop[k] = t;
+    }
   }
 }
 
@@ -995,7 +1004,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
   tcgen05_fence_before();
   __syncthreads();
   if (p.y)
-    for (int i = tid; i < HEAD_PART; i += HT_THREADS) p.partial[(long)blockIdx.x * HEAD_PART + i] = red_s[i];
+    for (int i = tid; i < HEAD_PART; i += HT_THREADS) p.partial[(long)i * gridDim.x + blockIdx.x] = red_s[i];
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
@@ -1079,56 +1088,63 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_kernel(HeadParams p, float*
       wpartial[(long)blockIdx.x * HWG_PART + (jg * 4 + a) * TC_OPAD + kg * 4 + b] = acc[a][b];
 }
 
-// Sums the per-CTA head partials in a fixed order and scatters them into the flat gradient vector / loss tail.
+// Sums the per-CTA head partials (stored [value][cta]: one warp per value, lanes over CTAs, fixed order) and
+// scatters them into the flat gradient vector / loss tail.  wpartial is [cta][256*16].
 __global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial, int n_wcta,
                                    const float* __restrict__ wpartial, int O, int B, const float* denom, float p1,
                                    float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
-                                   float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2,
-                                   int fold, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ mean, const float* __restrict__ var, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                   float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per output value
+  const int lane = threadIdx.x & 31;
   if (i < HWG_PART) {
-    if (train) {
-      const int j = i / TC_OPAD, k = i % TC_OPAD;
-      if (k < O) {
-        double s = 0.0;
-        for (int c = 0; c < n_wcta; ++c) s += wpartial[(long)c * HWG_PART + i];
-        if (fold) {
-          // wpartial holds h^T dpred; y = a*h + b  =>  dWo = a_j * (h^T dpred) + b_j * colsum(dpred)
-          double dbo = 0.0;
-          for (int c = 0; c < n_cta; ++c) dbo += partial[(long)c * HEAD_PART + 2 * TC_H + k];
-          const double iv = 1.0 / sqrt((double)var[j] + eps);
-          const double a = gamma[j] * iv, bb = beta[j] - gamma[j] * mean[j] * iv;
-          s = a * s + bb * dbo;
-        }
-        gWo[j * O + k] = (float)s;
-      }
-    }
+    if (!train) return;
+    const int j = i / TC_OPAD, k = i % TC_OPAD;
+    double s = 0.0;
+    for (int c = lane; c < n_wcta; c += 32) s += wpartial[(long)c * HWG_PART + i];
+    s = warp_sum(s);
+    if (lane == 0 && k < O) gWo[j * O + k] = (float)s;
     return;
   }
   const int q = i - HWG_PART;
   if (q >= HEAD_PART) return;
   double s = 0.0;
-  for (int c = 0; c < n_cta; ++c) s += partial[(long)c * HEAD_PART + q];
+  for (int c = lane; c < n_cta; c += 32) s += partial[(long)q * n_cta + c];
+  s = warp_sum(s);
   if (q < TC_H) {
-    if (train) ggamma[q] = (float)s;
+    if (train && lane == 0) ggamma[q] = (float)s;
   } else if (q < 2 * TC_H) {
-    if (train) gbeta[q - TC_H] = (float)s;
+    if (train && lane == 0) gbeta[q - TC_H] = (float)s;
   } else if (q < 2 * TC_H + TC_OPAD) {
     const int k = q - 2 * TC_H;
-    if (train && k < O) gbo[k] = (float)s;
+    if (train && lane == 0 && k < O) gbo[k] = (float)s;
   } else if (q == 2 * TC_H + TC_OPAD) {
-    // the three loss sums live in consecutive slots; one thread finishes the loss (losses.py:87-98)
-    double s0 = s, s1 = 0.0, s2 = 0.0;
-    for (int c = 0; c < n_cta; ++c) {
-      s1 += partial[(long)c * HEAD_PART + q + 1];
-      s2 += partial[(long)c * HEAD_PART + q + 2];
+    // the three loss sums live in consecutive slots; this warp finishes the loss (losses.py:87-98)
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = lane; c < n_cta; c += 32) {
+      s1 += partial[(long)(q + 1) * n_cta + c];
+      s2 += partial[(long)(q + 2) * n_cta + c];
     }
-    const double Bg = denom[0], Mg = denom[1];
-    const double mse0 = s0 / Bg, mse1 = s1 / (Bg * O), mse2 = s2 / (Mg * O);
-    out2[0] = (float)(p1 * mse0 + (1.0 - p1) * (p2 * mse1 + (1.0 - p2) * mse2));
-    out2[1] = (float)mse0;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      const double Bg = denom[0], Mg = denom[1];
+      const double mse0 = s / Bg, mse1 = s1 / (Bg * O), mse2 = s2 / (Mg * O);
+      out2[0] = (float)(p1 * mse0 + (1.0 - p1) * (p2 * mse1 + (1.0 - p2) * mse2));
+      out2[1] = (float)mse0;
+    }
   }
+}
+
+// tensor-core head: gWo holds h^T dpred; y = a*h + b  =>  dWo = a_j * (h^T dpred) + b_j * colsum(dpred)
+__global__ void head_fold_kernel(int O, float* __restrict__ gWo, const float* __restrict__ gbo,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= TC_H * O) return;
+  const int j = i / O, k = i % O;
+  const float iv = 1.0f / sqrtf(var[j] + eps);
+  const float a = gamma[j] * iv, bb = beta[j] - gamma[j] * mean[j] * iv;
+  gWo[i] = a * gWo[i] + bb * gbo[k];
 }
 
 // =============================================================================================
@@ -1352,7 +1368,6 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   int grid = m.T * n_btiles;
   if (grid > m.head_ctas) grid = m.head_ctas;
   h.partial = m.head_part;
-  if (y) LFMQ_CUDA_CHECK(cudaMemsetAsync(m.head_part, 0, m.head_part_elems * sizeof(float), s));
   HeadTcWeights hw;
   hw.WoTp = m.WoTp; hw.Wop = m.Wop; hw.bop = m.bop;
   const bool use_tc = !h.use_dropout;       // the BN fold into the head weights needs y = a*h + b
@@ -1378,12 +1393,18 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
     LFMQ_LAUNCH_CHECK();
   }
   if (y) {
-    head_reduce_kernel<<<(HWG_PART + HEAD_PART + 255) / 256, 256, 0, s>>>(
-        m.head_ctas, m.head_part, n_wcta, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda,
-        train ? 1 : 0, grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr,
-        grads ? grads + m.ogamma : nullptr, grads ? grads + m.obeta : nullptr, out2, (train && use_tc) ? 1 : 0,
-        params + m.ogamma, params + m.obeta, params + m.omean, params + m.ovar, c.bn_epsilon);
+    const int n_out = HWG_PART + HEAD_PART;
+    head_reduce_kernel<<<(n_out * 32 + 255) / 256, 256, 0, s>>>(
+        grid, m.head_part, n_wcta, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda, train ? 1 : 0,
+        grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr, grads ? grads + m.ogamma : nullptr,
+        grads ? grads + m.obeta : nullptr, out2);
     LFMQ_LAUNCH_CHECK();
+    if (train && use_tc) {
+      head_fold_kernel<<<(TC_H * m.O + 255) / 256, 256, 0, s>>>(m.O, grads + m.oWo, grads + m.obo, params + m.ogamma,
+                                                              params + m.obeta, params + m.omean, params + m.ovar,
+                                                              c.bn_epsilon);
+      LFMQ_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
