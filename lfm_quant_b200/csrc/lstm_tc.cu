@@ -1671,33 +1671,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) rec[j] = 0.f;
           }
+          // gate-gradient algebra in packed bf16x2 (all operands arrive packed; dz leaves packed); only the carried
+          // dLoss/dc stays in fp32 registers.  SURVEY App. A.4.
           uint32_t zi[8], zf[8], zg[8], zo[8];
 #pragma unroll
-          for (int jj = 0; jj < 16; jj += 2) {
-            float ri[2], rf[2], rg[2], ro[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int j = jj + u;
-              const float i_ = u ? bf16_hi(gi[ci][jj / 2]) : bf16_lo(gi[ci][jj / 2]);
-              const float f_ = u ? bf16_hi(gf[ci][jj / 2]) : bf16_lo(gf[ci][jj / 2]);
-              const float g_ = u ? bf16_hi(gg[ci][jj / 2]) : bf16_lo(gg[ci][jj / 2]);
-              const float o_ = u ? bf16_hi(go[ci][jj / 2]) : bf16_lo(go[ci][jj / 2]);
-              const float dh = (u ? bf16_hi(dhp[ci][jj / 2]) : bf16_lo(dhp[ci][jj / 2])) + rec[j];
-              const float c_t = u ? bf16_hi(ct[ci][jj / 2]) : bf16_lo(ct[ci][jj / 2]);
-              const float c_p = u ? bf16_hi(cp[ci][jj / 2]) : bf16_lo(cp[ci][jj / 2]);
-              const float tc = tanh_approx(c_t);
-              const float d_o = dh * tc;
-              const float dcn = dc[ci * 16 + j] + dh * o_ * (1.f - tc * tc);
-              ri[u] = dcn * g_ * i_ * (1.f - i_);
-              rf[u] = dcn * c_p * f_ * (1.f - f_);
-              rg[u] = dcn * i_ * (1.f - g_ * g_);
-              ro[u] = d_o * o_ * (1.f - o_);
-              dc[ci * 16 + j] = dcn * f_;
-            }
-            zi[jj / 2] = pack_bf16x2(ri[0], ri[1]);
-            zf[jj / 2] = pack_bf16x2(rf[0], rf[1]);
-            zg[jj / 2] = pack_bf16x2(rg[0], rg[1]);
-            zo[jj / 2] = pack_bf16x2(ro[0], ro[1]);
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t i2 = gi[ci][e], f2 = gf[ci][e], g2 = gg[ci][e], o2 = go[ci][e];
+            const uint32_t dh2 = add_bf16x2(dhp[ci][e], pack_bf16x2(rec[2 * e], rec[2 * e + 1]));
+            const uint32_t tc2 = tanh_bf16x2(ct[ci][e]);
+            const uint32_t omtc2 = fma_bf16x2(neg_bf16x2(tc2), tc2, BF16X2_ONE);        // 1 - tanh(c)^2
+            const uint32_t t1 = mul_bf16x2(mul_bf16x2(dh2, o2), omtc2);                 // dh * o * (1 - tc^2)
+            const float dcn0 = dc[ci * 16 + 2 * e] + bf16_lo(t1);
+            const float dcn1 = dc[ci * 16 + 2 * e + 1] + bf16_hi(t1);
+            dc[ci * 16 + 2 * e] = dcn0 * bf16_lo(f2);
+            dc[ci * 16 + 2 * e + 1] = dcn1 * bf16_hi(f2);
+            const uint32_t dcn2 = pack_bf16x2(dcn0, dcn1);
+            const uint32_t omi = fma_bf16x2(neg_bf16x2(i2), i2, i2);                    // i (1 - i)
+            const uint32_t omf = fma_bf16x2(neg_bf16x2(f2), f2, f2);                    // f (1 - f)
+            const uint32_t omg = fma_bf16x2(neg_bf16x2(g2), g2, BF16X2_ONE);            // 1 - g^2
+            const uint32_t omo = fma_bf16x2(neg_bf16x2(o2), o2, o2);                    // o (1 - o)
+            zi[e] = mul_bf16x2(dcn2, mul_bf16x2(g2, omi));
+            zf[e] = mul_bf16x2(dcn2, mul_bf16x2(cp[ci][e], omf));
+            zg[e] = mul_bf16x2(dcn2, mul_bf16x2(i2, omg));
+            zo[e] = mul_bf16x2(mul_bf16x2(dh2, tc2), omo);
           }
           if (valid) {
             st_global_v8(dzrow + jb * 16, zi);
@@ -1722,7 +1718,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           if (tid == 64 && ci == 0) BWD_TRACE(2, T - 1 - t, 1);
           if (tid == 64 && ci == 1) BWD_TRACE(2, T - 1 - t, 2);
         }
-        // inputs of both chunks of the next step: independent of the exchange below
+        // inputs of both chunks of the next step: independent of the exchange below.  Placement matters because the
+        // SM's memory pipe is a FIFO: issued here they delay the export slightly but land before the next step
+        // starts; issued after the export they arrive too late (+9 % kernel time), issued inside the chunk loop they
+        // hold up the chunk's own dz / A-operand stores (+17 %).
         if (t > 0) {
           load_chunk(0, tile, valid, t - 1);
           load_chunk(1, tile, valid, t - 1);
