@@ -264,23 +264,56 @@ def main():
         if os.path.isfile(pk):
             peaks = json.load(open(pk))
         peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
-        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else \
-            'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
-        # dominant kernel: the forward + backward recurrences (persistent gate-GEMM kernels); algorithmic FLOPs
-        # per launch = per-window gate-GEMM FLOPs x the windows one launch processes.
-        fwd_ms, fwd_n = regions['fwd']
-        bwd_ms, bwd_n = regions['bwd']
-        wg_ms, wg_n = regions['wgrad']
+        peak_bw = peaks.get('hbm_gbs') or 6650.0
+        peak_src = 'MEASURED_PEAKS.json (bf16_tflops_sustained for kernels timed inside a long step; hbm_gbs)' if peaks \
+            else 'fallback 1.4 PFLOP/s sustained / 6.65 TB/s (B200_PROFILING.md)'
+        # Gate GEMMs = forward recurrence + backward recurrence + weight-gradient GEMM.  Algorithmic FLOPs per launch =
+        # per-window figure x the windows one launch processes; durations = CUDA events recorded by the
+        # library around each kernel inside the timed region (lfmq_profile_*), on the stream the kernels run on.
+        k = max(args.steps, 1)
+        fwd_ms, bwd_ms, wg_ms, head_ms = (regions[n][0] / k for n in ('fwd', 'bwd', 'wgrad', 'head'))
+        flop_fwd = FLOP_FWD_PER_SEQ * B
+        flop_bwd = 2.0 * T * 4 * H * H * B
+        flop_wg = FLOP_FWD_PER_SEQ * B
+
+        def tf(flop, ms_):
+            return flop / (ms_ * 1e-3) / 1e12 if ms_ > 0 else None
+
         gate_ms = fwd_ms + bwd_ms + wg_ms
-        achieved = (FLOP_TRAIN_PER_SEQ * B * max(fwd_n, 1)) / (gate_ms * 1e-3) / 1e12 if gate_ms > 0 else None
-        fwd_ach = (FLOP_FWD_PER_SEQ * B * max(fwd_n, 1)) / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None
+        achieved = tf(flop_fwd + flop_bwd + flop_wg, gate_ms)
+        # algorithmic HBM bytes of the backward recurrence (the longest kernel): saved gates + 2x cell states + dLoss/dh
+        # read, dz written (bf16)
+        bwd_bytes = B * T * (4 * H * 2 + 2 * H * 2 + H * 2) + B * T * 4 * H * 2
+        head_bytes = B * T * (H * 2 + O * 4) + (B * T * (H * 2 + O * 4) if args.precision == 'bf16' else 0)
+        # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) comes ONLY from a committed
+        # `ncu --set full` capture of these kernels: profiles/r01_ncu_traffic.json is written by tools/ncu_traffic.py from
+        # the .ncu-rep and names the capture it was parsed from.  No file (or a kernel missing from it) -> null.
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+        gate_kernels = ('lstm_fwd_tc_kernel', 'lstm_bwd_tc_kernel', 'wgrad_tc_kernel')
+        if args.precision == 'bf16' and os.path.isfile(tp):
+            tj = json.load(open(tp))
+            per = tj.get('dram_bytes_per_launch', {})
+            if all(kn in per for kn in gate_kernels):
+                traffic = float(sum(per[kn] for kn in gate_kernels))
+                traffic_src = tj.get('source')
         roofline = {
             'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-            'frac': (achieved / peak_tf) if achieved else None, 'traffic': None, 'peak_source': peak_src,
-            'kernel': 'gate GEMMs: LSTM fwd recurrence + bwd recurrence + weight-grad (event-bracketed regions)',
-            'fwd_recurrence': {'achieved': fwd_ach, 'frac': (fwd_ach / peak_tf) if fwd_ach else None,
-                               'ms_per_launch': fwd_ms / max(fwd_n, 1)},
-            'regions_ms_per_step': {k: v[0] / max(args.steps, 1) for k, v in regions.items()},
+            'frac': (achieved / peak_tf) if achieved else None,
+            'traffic': traffic, 'traffic_source': traffic_src,
+            'peak_source': peak_src,
+            'kernel': 'gate GEMMs: lstm_fwd_tc_kernel + lstm_bwd_tc_kernel + wgrad_tc_kernel (one launch each per step)',
+            'per_kernel': {
+                'lstm_fwd_tc_kernel': {'ms': fwd_ms, 'tflops': tf(flop_fwd, fwd_ms), 'frac': (tf(flop_fwd, fwd_ms) or 0) / peak_tf},
+                'lstm_bwd_tc_kernel': {'ms': bwd_ms, 'tflops': tf(flop_bwd, bwd_ms), 'frac': (tf(flop_bwd, bwd_ms) or 0) / peak_tf,
+                                       'hbm_gbs': bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None,
+                                       'hbm_frac': bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak_bw if bwd_ms > 0 else None},
+                'wgrad_tc_kernel': {'ms': wg_ms, 'tflops': tf(flop_wg, wg_ms), 'frac': (tf(flop_wg, wg_ms) or 0) / peak_tf},
+                'head (fused pointwise tail, HBM-bound)': {'ms': head_ms,
+                                                           'hbm_gbs': head_bytes / (head_ms * 1e-3) / 1e9 if head_ms > 0 else None,
+                                                           'hbm_frac': head_bytes / (head_ms * 1e-3) / 1e9 / peak_bw if head_ms > 0 else None},
+            },
+            'regions_ms_per_step': {n: v[0] / k for n, v in regions.items()},
         }
         line = {
             'metric': METRIC, 'value': value, 'unit': 'sequences/s', 'n_gpus': world, 'steps': args.steps,

@@ -211,3 +211,27 @@ def test_bad_arguments_raise():
         eng.forward(x)                              # B > max_batch
     with pytest.raises(LfmqError):
         eng.backward(torch.zeros(4, 3, 4, device='cuda'), torch.zeros(4, 3, 2, device='cuda'))  # forward_only
+
+
+def test_predict_full_size_rows_match_oracle():
+    """BASELINE configs[4]: predict.py path at B=65536, T=48, H=256 in the fp32 parity mode.  Windows are independent,
+    so a random subset of rows is checked against the oracle (<= 1e-4 relative) and the kept scalar
+    pred[:, -1, target_idx] (predict.py:284-291) is what is compared as well."""
+    B, T, F, O, H, L = 65536, 48, 32, 16, 256, 1
+    rng = np.random.RandomState(17)
+    params = [p.astype(np.float32).astype(np.float64) for p in orc.init_params(L, F, O, H, init_scale=1.0, seed=521)]
+    x = rng.standard_normal((B, T, F)).astype(np.float32)
+    eng = make_engine(B, T, F, O, H, L, train=False, forward_only=True)
+    eng.set_weights(params)
+    preds = eng.forward(_cuda(x)).cpu().numpy()
+    rows = rng.choice(B, size=96, replace=False)
+    ref, _ = orc.forward(params, x[rows].astype(np.float64), num_layers=L)
+    assert rel_err(preds[rows], ref) < TOL
+    assert rel_err(preds[rows, -1, 3], ref[:, -1, 3]) < TOL
+    eng.close()
+    # the tensor-core path on the same inputs, bf16 tolerance
+    e16 = make_engine(B, T, F, O, H, L, train=False, forward_only=True, precision='bf16')
+    e16.set_weights(params)
+    p16 = e16.forward(_cuda(x)).cpu().numpy()
+    assert np.isfinite(p16).all()
+    assert np.abs(p16[rows] - ref).max() / np.abs(ref).max() < 6e-2
