@@ -1,5 +1,5 @@
 // LFMQ_PREC_BF16: the gate GEMMs on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 cell
-// state), everything else as fused HBM-streaming kernels.  sm_100a only.
+// state in registers, bf16 when saved), everything else as fused HBM-streaming kernels.  sm_100a only.
 //
 // Data layout in HBM (all carved from the caller's workspace, see tc_layout):
 //   xh    bf16 [maxB][T+1][384]   row (b,t): cols 0..255 = h_{t-1} (zero at t=0), 256..287 = x_t, 288 = 1.0 (t<T),
@@ -14,13 +14,13 @@
 //   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dLoss/dh from the head (after BN/dropout
 //                                 backward), already in the backward kernel's per-thread SoA order
 //
-// Forward recurrence = ONE persistent kernel (lstm_fwd_tc_kernel): clusters of 8 CTAs, CTA r keeps the weight
-// slice of hidden units [32r, 32r+32) (all four gates, 128 gate columns) resident in shared memory for the whole
-// unroll; two independent 128-row batch tiles ("chains") per cluster are in flight so that one chain's
-// tensor-core work hides the other's pointwise tail and h exchange.  h_t is exchanged through global memory
-// (it is an output anyway) and comes back as the next step's A operand via TMA multicast -- measured on B200
+// Forward recurrence = ONE persistent kernel (lstm_fwd_tc_kernel): clusters of 4 CTAs, one 128-row batch tile per
+// cluster, all clusters co-resident.  CTA r keeps the weight slice of hidden units [64r, 64r+64) (all four gates,
+// 256 gate columns) resident in shared memory for the whole unroll.  h_t is exchanged through global memory (it is
+// an output anyway) and comes back as the next step's A operand via TMA multicast -- measured on B200
 // (profiles/r01_tc_probe.txt) that path moves 64 KB into every SM of a cluster in ~1500 cycles while DSMEM stores
-// or bulk copies manage only 9-13 B/cycle/SM.
+// or bulk copies manage only 9-13 B/cycle/SM.  Clusters of 8 were tried first and dropped: only 15 of them are
+// co-resident.  See DESIGN.md section 5 for the per-step cycle budget of both recurrences.
 #include "lstm_tc.h"
 
 #include <cuda.h>
