@@ -235,3 +235,32 @@ def test_predict_full_size_rows_match_oracle():
     p16 = e16.forward(_cuda(x)).cpu().numpy()
     assert np.isfinite(p16).all()
     assert np.abs(p16[rows] - ref).max() / np.abs(ref).max() < 6e-2
+
+
+def test_cfg3_full_size_dropout_block_and_shard_sum():
+    """BASELINE configs[2]: B=4096, T=48, F=32, H=512, L=2 with dropout (rate 0.2) on the fp32 path.
+    The oracle cannot run 4096 windows of this size in seconds, so: (1) a contiguous block of rows of the training-mode
+    forward is checked against the oracle with the same global row offset (dropout masks are keyed by global row);
+    (2) size-independent property: gradients of two row shards taken with the global loss denominators sum to the
+    unsharded gradient (the data-parallel contract)."""
+    B, T, F, O, H, L = 4096, 48, 32, 16, 512, 2
+    kw = dict(dropout=0.2, recurrent_dropout=0.0, seed=521)
+    params, x, y = make_problem(B, T, F, O, H, L, seed=9, init_scale=0.1)
+    eng = make_engine(B, T, F, O, H, L, train=True, target_idx=3, **kw)
+    eng.set_weights(params)
+    xc, yc = _cuda(x), _cuda(y)
+    preds = eng.forward(xc, step=5, row0=0).cpu().numpy()
+    r0, n = 1000, 24
+    ref, _ = orc.forward(params, x[r0:r0 + n].astype(np.float64), num_layers=L, training=True, step=5, row0=r0, **kw)
+    assert rel_err(preds[r0:r0 + n], ref) < TOL
+    eng.backward(xc, yc, step=5)
+    nt = eng.n_trainable
+    full = eng.grads[:nt + 2].clone()
+    denom = eng.mask_count(yc)
+    acc = torch.zeros_like(full)
+    for lo, hi in ((0, 1500), (1500, B)):
+        eng.backward(xc[lo:hi].contiguous(), yc[lo:hi].contiguous(), step=5, row0=lo, denom=denom)
+        acc += eng.grads[:nt + 2]
+    assert torch.isfinite(full).all() and float(full[:nt].abs().max()) > 0
+    assert rel_err(acc.cpu().numpy(), full.cpu().numpy()) < TOL
+    eng.close()
