@@ -24,13 +24,14 @@ int bn_dropout_bwd(cudaStream_t s, int B, int T, int H, const float* dy, const f
                    float* dh_out, float* dgamma, float* dbeta, float* scratch, size_t scratch_elems);
 int add_bias_rows(cudaStream_t s, long rows, int N, float* C, const float* bias);
 int colsum(cudaStream_t s, long rows, int N, const float* A, float* out, float* scratch, size_t scratch_elems);
-int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, float* scratch);
+int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, unsigned int* tickets);
 // out2 = {loss, mse_0}; maskout2 (nullable) = {B, mask_count_local}; dpred may be NULL (validation);
 // denom (nullable) = device {B_global, mask_count_global}.
 int loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const float* y, const float* denom,
               int target_idx, float p1, float p2, float* dpred, float* out2, float* maskout2, float* scratch);
 // scalars[0] = ||g||, scalars[1] = clip scale (1 when clip <= 0)
-int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* scalars, float* scratch);
+int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* scalars, float* scratch,
+                    unsigned int* ticket);
 int opt_update(cudaStream_t s, int opt, long n, float* p, const float* g, float* slot0, float* slot1,
                const float* scalars, float lr, float c1, float c2, float momentum);
 int maxnorm_cols(cudaStream_t s, int I, int N, float* W, float max_norm);

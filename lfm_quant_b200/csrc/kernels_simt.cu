@@ -480,9 +480,11 @@ __global__ void loss_final_kernel(int nblk, const double* __restrict__ partial, 
 }
 
 // mask count (losses.py:72-73,132): one thread per [b,t] row, warp ballot, one integer atomic per warp
-// (integer adds commute: the count is exact and deterministic).
-__global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, const float* __restrict__ y,
-                                                        unsigned int* __restrict__ counter) {
+// (integer adds commute: the count is exact and deterministic).  The last block to finish (ticket) writes
+// {B, count} and resets both counters, so the whole count is one launch and needs no memset.
+__global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, int B, const float* __restrict__ y,
+                                                        unsigned int* __restrict__ tickets,
+                                                        float* __restrict__ out2) {
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
   bool any = false;
   if (r < rows) {
@@ -497,21 +499,23 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, const 
     }
   }
   const unsigned int bal = __ballot_sync(0xffffffffu, any);
-  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counter, (unsigned int)__popc(bal));
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&tickets[0], (unsigned int)__popc(bal));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&tickets[1], 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned int c = atomicExch(&tickets[0], 0u);
+      out2[0] = (float)B;
+      out2[1] = (float)c;
+      tickets[1] = 0u;
+    }
+  }
 }
 
-__global__ void mask_final_kernel(int B, const unsigned int* __restrict__ counter, float* __restrict__ out2) {
-  out2[0] = (float)B;
-  out2[1] = (float)(*counter);
-}
-
-int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, float* scratch) {
-  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
-  LFMQ_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, unsigned int* tickets) {
   const long rows = (long)B * T;
-  mask_rows_kernel<<<cdiv(rows, 256), 256, 0, s>>>(rows, O, y, counter);
-  LFMQ_LAUNCH_CHECK();
-  mask_final_kernel<<<1, 1, 0, s>>>(B, counter, out2);
+  mask_rows_kernel<<<cdiv(rows, 256), 256, 0, s>>>(rows, O, B, y, tickets, out2);
   LFMQ_LAUNCH_CHECK();
   return 0;
 }
@@ -530,33 +534,42 @@ int loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const floa
 // clip_by_global_norm + optimizer + MaxNorm (train.py:195-198, model_utils/optimizers.py:21-27,
 // rnn_point_estimate.py:85).
 // =============================================================================================
-__global__ void __launch_bounds__(256) sumsq_partial_kernel(long n, const float* __restrict__ g,
-                                                            double* __restrict__ partial) {
+// Sum of squares in fp64 partials; the last block to finish (ticket) adds the partials in block order -- the result
+// does not depend on which block that is -- and writes {norm, clip scale}.  One launch, self-resetting ticket.
+__global__ void __launch_bounds__(256) sumsq_norm_kernel(long n, const float* __restrict__ g,
+                                                         double* __restrict__ partial, float clip,
+                                                         float* __restrict__ scalars,
+                                                         unsigned int* __restrict__ ticket) {
   double acc[4] = {0, 0, 0, 0};
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const double v = g[i];
     acc[0] += v * v;
   }
   block_reduce4(acc, partial + (long)blockIdx.x * 4);
-}
-
-__global__ void norm_final_kernel(int nblk, const double* __restrict__ partial, float clip,
-                                  float* __restrict__ scalars) {
+  __shared__ bool last;
+  __syncthreads();                     // block_reduce4's writers (threads 0-3) are done
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x >= 32) return;
+  __threadfence();
   double s = 0;
-  for (int b = threadIdx.x; b < nblk; b += 32) s += partial[(long)b * 4];
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += __ldcg(partial + (long)b * 4);
   s = warp_sum(s);
   if (threadIdx.x != 0) return;
   const float gn = (float)sqrt(s);
   scalars[0] = gn;
   scalars[1] = (clip > 0.f) ? clip / fmaxf(gn, clip) : 1.0f;
+  *ticket = 0u;
 }
 
-int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* scalars, float* scratch) {
+int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* scalars, float* scratch,
+                    unsigned int* ticket) {
   double* partial = reinterpret_cast<double*>(scratch);
   const int nblk = (int)min((long)148, max((long)1, n / 2048));
-  sumsq_partial_kernel<<<nblk, 256, 0, s>>>(n, g, partial);
-  LFMQ_LAUNCH_CHECK();
-  norm_final_kernel<<<1, 32, 0, s>>>(nblk, partial, clip, scalars);
+  sumsq_norm_kernel<<<nblk, 256, 0, s>>>(n, g, partial, clip, scalars, ticket);
   LFMQ_LAUNCH_CHECK();
   return 0;
 }

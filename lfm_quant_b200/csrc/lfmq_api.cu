@@ -39,6 +39,7 @@ struct lfmq_handle_s {
   int64_t oWo, obo;
   // workspace carve
   float *params, *grads, *slots, *scalars, *denom;
+  unsigned int* tickets;
   std::vector<LayerBuf> layers;
   float *z, *hm, *dz, *dy, *dh_out, *hp, *dh_rec, *dc, *dpred, *preds, *scratch;
   size_t scratch_elems;
@@ -138,6 +139,8 @@ size_t layout(lfmq_handle_s* h, char* base) {
   h->slots = c.forward_only ? nullptr : cv.take<float>((size_t)h->n_slots * h->n_train);
   h->scalars = cv.take<float>(16);
   h->denom = h->scalars + 8;
+  h->tickets = reinterpret_cast<unsigned int*>(h->scalars);   // [0] mask count, [1] mask ticket, [2] norm ticket;
+                                                              // zeroed at create, every user resets what it used
   const size_t BT = B * T;
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = h->layers[l];
@@ -468,7 +471,7 @@ int32_t lfmq_mask_count(lfmq_handle h, const float* y, int32_t B, float* out_dev
     LFMQ_SET_ERR("lfmq_mask_count: null pointer");
     return LFMQ_ERR_ARG;
   }
-  return mask_count((cudaStream_t)stream, B, h->cfg.seq_len, h->cfg.n_outputs, y, out_dev, h->scratch);
+  return mask_count((cudaStream_t)stream, B, h->cfg.seq_len, h->cfg.n_outputs, y, out_dev, h->tickets);
 }
 
 int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, int64_t row0, int64_t step,
@@ -488,7 +491,7 @@ int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, 
   h->tc.last_row0 = row0;
   const float* denom = denom_dev;
   if (!denom) {
-    RUN(mask_count(s, B, c.seq_len, c.n_outputs, y, h->denom, h->scratch));
+    RUN(mask_count(s, B, c.seq_len, c.n_outputs, y, h->denom, h->tickets));
     denom = h->denom;
   }
   float* tail = h->grads + h->n_train;
@@ -509,7 +512,7 @@ int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream) {
   const lfmq_config& c = h->cfg;
   float* tail = h->grads + h->n_train;
   h->prof.begin(LFMQ_REGION_OPT, s);
-  RUN(grad_norm_scale(s, h->n_train, h->grads, c.max_grad_norm, tail + 2, h->scratch));
+  RUN(grad_norm_scale(s, h->n_train, h->grads, c.max_grad_norm, tail + 2, h->scratch, h->tickets + 2));
   float lr_eff = lr;
   if (c.optimizer == LFMQ_OPT_ADAM) {
     const double t = (double)(iteration + 1);

@@ -128,11 +128,11 @@ __global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ 
 
 // Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 64r+j is row n = 64g+j of
 // slice r; the three sigmoid gates are pre-scaled by 0.5 (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
-__global__ void pack_weights_kernel(int I, const float* __restrict__ W, const float* __restrict__ U,
+__device__ __forceinline__ void pack_weights_body(int bid, int I, const float* __restrict__ W, const float* __restrict__ U,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ Up,
                                     __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp) {
   const int H = TC_H;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long idx = (long)bid * blockDim.x + threadIdx.x;
   if (idx < (long)4 * H * H) {          // Up: [4][256][256]
     const int k = (int)(idx % H);
     const int n = (int)((idx / H) % TC_NSL);
@@ -669,12 +669,12 @@ struct HeadTcWeights {
   const float* bop;            // [16]       bo + sum_j b_j Wo[j][k]
 };
 
-__global__ void pack_head_kernel(int O, const float* __restrict__ Wo, const float* __restrict__ bo,
+__device__ __forceinline__ void pack_head_body(int bid, int O, const float* __restrict__ Wo, const float* __restrict__ bo,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                  __nv_bfloat16* __restrict__ WoTp, __nv_bfloat16* __restrict__ Wop,
                                  float* __restrict__ bop) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = bid * blockDim.x + threadIdx.x;
   if (idx < TC_OPAD * TC_H) {
     const int n = idx / TC_H, j = idx % TC_H;
     const float a = gamma[j] / sqrtf(var[j] + eps);
@@ -685,9 +685,9 @@ __global__ void pack_head_kernel(int O, const float* __restrict__ Wo, const floa
     Wop[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
   }
   // folded bias: block k (< 16) reduces over its 256 threads = 256 hidden units
-  if (blockIdx.x < TC_OPAD) {
+  if (bid < TC_OPAD) {
     __shared__ float red[8];
-    const int k = blockIdx.x, j = threadIdx.x;
+    const int k = bid, j = threadIdx.x;
     float v = 0.f;
     if (k < O) {
       const float iv = 1.0f / sqrtf(var[j] + eps);
@@ -701,6 +701,38 @@ __global__ void pack_head_kernel(int O, const float* __restrict__ Wo, const floa
       for (int w = 0; w < 8; ++w) t += red[w];
       bop[k] = t;
     }
+  }
+}
+
+// Ubk[r][n][k'] = U[n][g*H + 64r + 16jb + jj], k' = 64jb + 16g + jj   (K-slices of U for the backward recurrence)
+__device__ __forceinline__ void pack_ubk_body(int bid, const float* __restrict__ U, __nv_bfloat16* __restrict__ Ubk) {
+  const long idx = (long)bid * blockDim.x + threadIdx.x;
+  if (idx >= (long)4 * TC_H * TC_H) return;
+  const int kp = (int)(idx % 256);
+  const int n = (int)((idx / 256) % TC_H);
+  const int r = (int)(idx / (256 * TC_H));
+  const int jb = kp / 64, g = (kp % 64) / 16, jj = kp % 16;
+  Ubk[idx] = __float2bfloat16(U[(long)n * 4 * TC_H + g * TC_H + 64 * r + 16 * jb + jj]);
+}
+
+// All weight repacking of one optimizer step in ONE launch: block ranges [0,nb_w) forward slices, [nb_w,nb_w+nb_h)
+// head, the rest the backward K-slices (nb_u = 0 on a forward-only handle).
+struct PackArgs {
+  int I, O, nb_w, nb_h, nb_u;
+  float eps;
+  const float *W, *U, *bias, *Wo, *bo, *gamma, *beta, *mean, *var;
+  __nv_bfloat16 *Up, *Wp, *Ubk, *WoTp, *Wop;
+  float *biasp, *bop;
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(PackArgs a) {
+  const int bid = blockIdx.x;
+  if (bid < a.nb_w) {
+    pack_weights_body(bid, a.I, a.W, a.U, a.bias, a.Up, a.Wp, a.biasp);
+  } else if (bid < a.nb_w + a.nb_h) {
+    pack_head_body(bid - a.nb_w, a.O, a.Wo, a.bo, a.gamma, a.beta, a.mean, a.var, a.eps, a.WoTp, a.Wop, a.bop);
+  } else {
+    pack_ubk_body(bid - a.nb_w - a.nb_h, a.U, a.Ubk);
   }
 }
 
@@ -1261,23 +1293,21 @@ void tc_destroy(TcState& st) {
   st.impl = nullptr;
 }
 
-__global__ void pack_ubk_kernel(const float* __restrict__ U, __nv_bfloat16* __restrict__ Ubk);
-
 static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   TcImpl& m = *st.impl;
   if (!st.weights_dirty) return 0;
-  const long n = (long)4 * TC_H * TC_H;
-  pack_weights_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(m.I, params + m.oW, params + m.oU, params + m.ob, m.Up,
-                                                           m.Wp, m.biasp);
+  const int nblk = (int)(((long)4 * TC_H * TC_H + 255) / 256);
+  PackArgs a;
+  a.I = m.I; a.O = m.O; a.eps = m.eps;
+  a.nb_w = nblk;
+  a.nb_h = (TC_H * 32 + 255) / 256;
+  a.nb_u = m.pexch ? nblk : 0;      // training handle: K-slices of U for the backward recurrence
+  a.W = params + m.oW; a.U = params + m.oU; a.bias = params + m.ob;
+  a.Wo = params + m.oWo; a.bo = params + m.obo; a.gamma = params + m.ogamma; a.beta = params + m.obeta;
+  a.mean = params + m.omean; a.var = params + m.ovar;
+  a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.Wop = m.Wop; a.biasp = m.biasp; a.bop = m.bop;
+  pack_all_kernel<<<a.nb_w + a.nb_h + a.nb_u, 256, 0, s>>>(a);
   LFMQ_LAUNCH_CHECK();
-  pack_head_kernel<<<(TC_H * 32 + 255) / 256, 256, 0, s>>>(m.O, params + m.oWo, params + m.obo, params + m.ogamma,
-                                                        params + m.obeta, params + m.omean, params + m.ovar, m.eps,
-                                                        m.WoTp, m.Wop, m.bop);
-  LFMQ_LAUNCH_CHECK();
-  if (m.pexch) {   // training handle: K-slices of U for the backward recurrence
-    pack_ubk_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(params + m.oU, m.Ubk);
-    LFMQ_LAUNCH_CHECK();
-  }
   st.weights_dirty = 0;
   return 0;
 }
@@ -1489,17 +1519,6 @@ struct BwdBars {
   uint64_t w_full, a_full[2], a_empty[2], acc_full[2], recv_full, recv_free, exp_ready;
   uint32_t tmem_base;
 };
-
-// Ubk[r][n][k'] = U[n][g*H + 64r + 16jb + jj], k' = 64jb + 16g + jj
-__global__ void pack_ubk_kernel(const float* __restrict__ U, __nv_bfloat16* __restrict__ Ubk) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)4 * TC_H * TC_H) return;
-  const int kp = (int)(idx % 256);
-  const int n = (int)((idx / 256) % TC_H);
-  const int r = (int)(idx / (256 * TC_H));
-  const int jb = kp / 64, g = (kp % 64) / 16, jj = kp % 16;
-  Ubk[idx] = __float2bfloat16(U[(long)n * 4 * TC_H + g * TC_H + 64 * r + 16 * jb + jj]);
-}
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     lstm_bwd_tc_kernel(BwdParams p, const __grid_constant__ CUtensorMap tm_ubk,
