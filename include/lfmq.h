@@ -24,13 +24,17 @@
 extern "C" {
 #endif
 
-#define LFMQ_ABI_VERSION 1
+#define LFMQ_ABI_VERSION 2
 
 enum { LFMQ_OK = 0, LFMQ_ERR_ARG = 1, LFMQ_ERR_CUDA = 2, LFMQ_ERR_UNSUPPORTED = 3, LFMQ_ERR_WORKSPACE = 4 };
 enum { LFMQ_OPT_ADADELTA = 0, LFMQ_OPT_ADAM = 1, LFMQ_OPT_RMSPROP = 2, LFMQ_OPT_SGD = 3 };
 /* LFMQ_PREC_FP32: fp32 SIMT arithmetic everywhere (the parity mode, <=1e-4 rel vs the oracle).
  * LFMQ_PREC_BF16: gate GEMMs on tcgen05 tensor cores with bf16 operands, fp32 accumulate, fp32 cell state. */
 enum { LFMQ_PREC_FP32 = 0, LFMQ_PREC_BF16 = 1 };
+
+/* config.rnn_cell (lfm_quant.py:39; rnn_point_estimate.py:80-102).  GRU is Keras' default reset_after=True cell:
+ * 3 gate blocks z|r|h, bias [2][3H] (input row, recurrent row).  LFMQ_PREC_BF16 supports the LSTM cell only. */
+enum { LFMQ_CELL_LSTM = 0, LFMQ_CELL_GRU = 1 };
 
 typedef struct lfmq_handle_s* lfmq_handle;
 
@@ -49,6 +53,8 @@ typedef struct lfmq_config {
   int32_t precision;         /* LFMQ_PREC_* */
   int32_t optimizer;         /* LFMQ_OPT_*                   (optimizers.py:21-27) */
   int32_t forward_only;      /* 1: no backward workspace (predict.py) */
+  int32_t rnn_cell;          /* LFMQ_CELL_*: config.rnn_cell 'lstm' | 'gru' (rnn_point_estimate.py:80,90) */
+  int32_t reserved0;         /* must be 0 (keeps the float block 8-byte aligned without implicit padding) */
   float dropout;             /* lfm_quant.py:61 */
   float recurrent_dropout;   /* lfm_quant.py:62 */
   float target_lambda;       /* lfm_quant.py:69 */
@@ -76,7 +82,7 @@ int32_t lfmq_create(const lfmq_config* cfg, void* workspace, uint64_t workspace_
 int32_t lfmq_destroy(lfmq_handle h);
 
 /* model.trainable_variables / model.weights (train.py:192,198): tensors are listed in Keras order,
- * trainable ones first: per layer lstm_l/{kernel,recurrent_kernel,bias}, batch_normalization[_k]/{gamma,beta};
+ * trainable ones first: per layer lstm_l/{kernel,recurrent_kernel,bias} (gru_l/... with bias [2][3H] for LFMQ_CELL_GRU), batch_normalization[_k]/{gamma,beta};
  * OUTPUT_1/{kernel,bias}; then per layer batch_normalization[_k]/{moving_mean,moving_variance}. */
 int32_t lfmq_param_count(lfmq_handle h, int32_t* n_tensors, int64_t* n_trainable_elems, int64_t* n_total_elems);
 int32_t lfmq_param_spec(lfmq_handle h, int32_t index, char* name, int32_t name_cap, int32_t* ndim,

@@ -11,6 +11,8 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lfmq.so')
 
 OPTIMIZERS = {'Adadelta': 0, 'Adam': 1, 'RMSprop': 2, 'SGD': 3}
 PREC_FP32, PREC_BF16 = 0, 1
+CELLS = {'lstm': 0, 'gru': 1}           # LFMQ_CELL_*
+ABI_VERSION = 2                         # LFMQ_ABI_VERSION in include/lfmq.h (2: rnn_cell added to lfmq_config)
 
 
 class LfmqConfig(C.Structure):
@@ -18,6 +20,7 @@ class LfmqConfig(C.Structure):
                 ('n_inputs', C.c_int32), ('n_outputs', C.c_int32), ('num_hidden', C.c_int32),
                 ('num_layers', C.c_int32), ('target_idx', C.c_int32), ('train', C.c_int32),
                 ('precision', C.c_int32), ('optimizer', C.c_int32), ('forward_only', C.c_int32),
+                ('rnn_cell', C.c_int32), ('reserved0', C.c_int32),
                 ('dropout', C.c_float), ('recurrent_dropout', C.c_float), ('target_lambda', C.c_float),
                 ('rnn_lambda', C.c_float), ('max_grad_norm', C.c_float), ('max_norm', C.c_float),
                 ('sgd_momentum', C.c_float), ('bn_epsilon', C.c_float), ('seed', C.c_uint64)]
@@ -85,7 +88,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lfmq_abi_version() != 1:
+    if lib.lfmq_abi_version() != ABI_VERSION:
         raise LfmqError('ABI version mismatch: %d' % lib.lfmq_abi_version())
     _lib = lib
     return lib

@@ -14,6 +14,11 @@ int lstm_pointwise_fwd(cudaStream_t s, int B, int T, int H, int t, const float* 
                        float* c, float* h, const float* rmask, float* hm);
 int lstm_pointwise_bwd(cudaStream_t s, int B, int T, int H, int t, const float* gates, const float* c,
                        const float* dh_out, const float* dh_rec, const float* rmask, float* dc, float* dz);
+int gru_pointwise_fwd(cudaStream_t s, int B, int T, int H, int t, const float* zx, const float* zh, const float* bias,
+                      float* gates, float* h, const float* rmask, float* hm);
+int gru_pointwise_bwd(cudaStream_t s, int B, int T, int H, int t, const float* gates, const float* h,
+                      const float* dh_out, const float* dh_rec, const float* rmask, float* dcarry, float* dxz,
+                      float* dhz);
 int gen_row_mask(cudaStream_t s, int B, int H, DropoutKey key, int64_t row0, float* rmask);
 int shift_mask(cudaStream_t s, int B, int T, int H, const float* h, const float* rmask, float* hp);
 int bn_dropout_fwd(cudaStream_t s, int B, int T, int H, const float* h, const float* gamma, const float* beta,

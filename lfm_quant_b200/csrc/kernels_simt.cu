@@ -194,6 +194,84 @@ int lstm_pointwise_bwd(cudaStream_t s, int B, int T, int H, int t, const float* 
   return 0;
 }
 
+// =============================================================================================
+// GRU cell (Keras GRU, reset_after=True, implementation=2; rnn_point_estimate.py:89-98), pointwise halves of one step.
+//   zx = x_t W  [B,3H]   zh = (h_{t-1} * mask) U  [B,3H] (absent at t = 0)   bias [2][3H] = input row | recurrent row
+//   z = sig(zx_z + zh_z + b), r = sig(zx_r + zh_r + b), q = zh_h + b_rh, hh = tanh(zx_h + b_ih + r q)
+//   h_t = z h_{t-1} + (1 - z) hh.   Saved per step (same 4H slot as the LSTM gates): z | r | hh | q.
+// =============================================================================================
+__global__ void gru_pointwise_fwd_kernel(int B, int T, int H, int t, const float* __restrict__ zx,
+                                         const float* __restrict__ zh, const float* __restrict__ bias,
+                                         float* __restrict__ gates, float* __restrict__ h,
+                                         const float* __restrict__ rmask, float* __restrict__ hm) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const float* xr = zx + (long)b * 3 * H;
+  const float* bi = bias;
+  const float* br = bias + 3 * H;
+  float hz = br[j], hr = br[H + j], q = br[2 * H + j];
+  if (zh) {
+    const float* hrw = zh + (long)b * 3 * H;
+    hz += hrw[j]; hr += hrw[H + j]; q += hrw[2 * H + j];
+  }
+  const float gz = sigmoid_f(xr[j] + bi[j] + hz);
+  const float gr = sigmoid_f(xr[H + j] + bi[H + j] + hr);
+  const float hh = tanhf(xr[2 * H + j] + bi[2 * H + j] + gr * q);
+  const long o = ((long)b * T + t) * H + j;
+  const float hp = (t > 0) ? h[o - H] : 0.f;
+  const float hn = fmaf(gz, hp - hh, hh);
+  h[o] = hn;
+  if (gates) {
+    float* g = gates + ((long)b * T + t) * 4 * H;
+    g[j] = gz; g[H + j] = gr; g[2 * H + j] = hh; g[3 * H + j] = q;
+  }
+  if (hm) hm[idx] = rmask ? hn * rmask[idx] : hn;
+}
+
+int gru_pointwise_fwd(cudaStream_t s, int B, int T, int H, int t, const float* zx, const float* zh, const float* bias,
+                      float* gates, float* h, const float* rmask, float* hm) {
+  gru_pointwise_fwd_kernel<<<cdiv((long)B * H, 256), 256, 0, s>>>(B, T, H, t, zx, zh, bias, gates, h, rmask, hm);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// Gradients w.r.t. the input projection (dxz) and the recurrent projection (dhz) of step t; the part of dLoss/dh that
+// reaches h_{t-1} through z * h_{t-1} is carried in place in `dcarry`.
+__global__ void gru_pointwise_bwd_kernel(int B, int T, int H, int t, const float* __restrict__ gates,
+                                         const float* __restrict__ h, const float* __restrict__ dh_out,
+                                         const float* __restrict__ dh_rec, const float* __restrict__ rmask,
+                                         float* __restrict__ dcarry, float* __restrict__ dxz,
+                                         float* __restrict__ dhz) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const long o = ((long)b * T + t) * H + j;
+  const float* g = gates + ((long)b * T + t) * 4 * H;
+  const float gz = g[j], gr = g[H + j], hh = g[2 * H + j], q = g[3 * H + j];
+  float dh = dh_out[o];
+  if (t < T - 1) dh += dcarry[idx];
+  if (dh_rec) dh += rmask ? dh_rec[idx] * rmask[idx] : dh_rec[idx];
+  const float hp = (t > 0) ? h[o - H] : 0.f;
+  const float da_h = dh * (1.f - gz) * (1.f - hh * hh);
+  const float da_z = dh * (hp - hh) * gz * (1.f - gz);
+  const float da_r = da_h * q * gr * (1.f - gr);
+  dcarry[idx] = dh * gz;
+  float* dx = dxz + ((long)b * T + t) * 3 * H;
+  float* dr = dhz + ((long)b * T + t) * 3 * H;
+  dx[j] = da_z; dx[H + j] = da_r; dx[2 * H + j] = da_h;
+  dr[j] = da_z; dr[H + j] = da_r; dr[2 * H + j] = da_h * gr;
+}
+
+int gru_pointwise_bwd(cudaStream_t s, int B, int T, int H, int t, const float* gates, const float* h,
+                      const float* dh_out, const float* dh_rec, const float* rmask, float* dcarry, float* dxz,
+                      float* dhz) {
+  gru_pointwise_bwd_kernel<<<cdiv((long)B * H, 256), 256, 0, s>>>(B, T, H, t, gates, h, dh_out, dh_rec, rmask, dcarry,
+                                                                  dxz, dhz);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
 // recurrent_dropout mask [B,H], one per call, shared by all T steps (rnn_point_estimate.py:86).
 __global__ void gen_row_mask_kernel(int B, int H, DropoutKey key, int64_t row0, float* __restrict__ rmask) {
   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;

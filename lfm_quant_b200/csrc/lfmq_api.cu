@@ -42,6 +42,7 @@ struct lfmq_handle_s {
   unsigned int* tickets;
   std::vector<LayerBuf> layers;
   float *z, *hm, *dz, *dy, *dh_out, *hp, *dh_rec, *dc, *dpred, *preds, *scratch;
+  float *zh, *dz2;   // GRU only: recurrent projection of one step, gradient w.r.t. the recurrent projection
   size_t scratch_elems;
   lfmq::TcState tc;
   lfmq::Profiler prof;
@@ -89,6 +90,11 @@ int validate(const lfmq_config* c) {
     LFMQ_SET_ERR("lfmq_config: dropout rates must be in [0,1)");
     return LFMQ_ERR_ARG;
   }
+  if ((c->rnn_cell != LFMQ_CELL_LSTM && c->rnn_cell != LFMQ_CELL_GRU) || c->reserved0 != 0) {
+    LFMQ_SET_ERR("lfmq_config: rnn_cell must be LFMQ_CELL_LSTM or LFMQ_CELL_GRU and reserved0 zero (got %d, %d)", c->rnn_cell,
+                 c->reserved0);
+    return LFMQ_ERR_ARG;
+  }
   if (c->precision != LFMQ_PREC_FP32 && c->precision != LFMQ_PREC_BF16) {
     LFMQ_SET_ERR("lfmq_config: unknown precision %d", c->precision);
     return LFMQ_ERR_ARG;
@@ -113,11 +119,13 @@ size_t layout(lfmq_handle_s* h, char* base) {
   for (int l = 0; l < L; ++l) {
     LayerBuf& lb = h->layers[l];
     lb.I = (l == 0) ? c.n_inputs : H;
-    const std::string ls = "lstm_" + std::to_string(l + 1);
+    const bool gru = c.rnn_cell == LFMQ_CELL_GRU;
+    const int NG = gru ? 3 : 4;
+    const std::string ls = std::string(gru ? "gru_" : "lstm_") + std::to_string(l + 1);
     const std::string bn = (l == 0) ? "batch_normalization" : "batch_normalization_" + std::to_string(l);
-    lb.oW = add(ls + "/kernel", 2, lb.I, 4 * H, 1);
-    lb.oU = add(ls + "/recurrent_kernel", 2, H, 4 * H, 1);
-    lb.ob = add(ls + "/bias", 1, 4 * H, 1, 1);
+    lb.oW = add(ls + "/kernel", 2, lb.I, NG * H, 1);
+    lb.oU = add(ls + "/recurrent_kernel", 2, H, NG * H, 1);
+    lb.ob = gru ? add(ls + "/bias", 2, 2, 3 * H, 1) : add(ls + "/bias", 1, 4 * H, 1, 1);
     lb.ogamma = add(bn + "/gamma", 1, H, 1, 1);
     lb.obeta = add(bn + "/beta", 1, H, 1, 1);
   }
@@ -151,11 +159,13 @@ size_t layout(lfmq_handle_s* h, char* base) {
     lb.rmask = cv.take<float>(B * H);
   }
   h->z = cv.take<float>(B * 4 * H);
+  h->zh = (c.rnn_cell == LFMQ_CELL_GRU) ? cv.take<float>(B * 3 * H) : nullptr;
   h->hm = cv.take<float>(B * H);
   h->preds = cv.take<float>(BT * O);
   size_t scratch = (size_t)4 << 20;
   if (!c.forward_only) {
     h->dz = cv.take<float>(BT * 4 * H);
+    h->dz2 = (c.rnn_cell == LFMQ_CELL_GRU) ? cv.take<float>(BT * 3 * H) : nullptr;
     h->dy = cv.take<float>(BT * H);
     h->dh_out = cv.take<float>(BT * H);
     h->hp = cv.take<float>(BT * H);
@@ -165,7 +175,7 @@ size_t layout(lfmq_handle_s* h, char* base) {
     const size_t bn_need = ((BT + 127) / 128) * 2 * H + (size_t)1024 * 2 * H;
     if (bn_need > scratch) scratch = bn_need;
   } else {
-    h->dz = h->dy = h->dh_out = h->hp = h->dh_rec = h->dc = h->dpred = nullptr;
+    h->dz = h->dz2 = h->dy = h->dh_out = h->hp = h->dh_rec = h->dc = h->dpred = nullptr;
   }
   h->scratch_elems = scratch;
   h->scratch = cv.take<float>(scratch);
@@ -217,7 +227,17 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
       RUN(gen_row_mask(s, B, H, make_key(c, 2 * l + 1, step, c.recurrent_dropout), row0, lb.rmask));
       rmask = lb.rmask;
     }
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < T && c.rnn_cell == LFMQ_CELL_GRU; ++t) {
+      RUN(sgemm(s, B, 3 * H, I, in + (long)t * I, (long)T * I, 1, P + lb.oW, 3 * H, 1, h->z, 3 * H, 0.f, nullptr, 0));
+      if (t > 0) {
+        const float* hp = rmask ? h->hm : lb.h + (long)(t - 1) * H;
+        const long ld = rmask ? H : (long)T * H;
+        RUN(sgemm(s, B, 3 * H, H, hp, ld, 1, P + lb.oU, 3 * H, 1, h->zh, 3 * H, 0.f, nullptr, 0));
+      }
+      RUN(gru_pointwise_fwd(s, B, T, H, t, h->z, t > 0 ? h->zh : nullptr, P + lb.ob, lb.gates, lb.h, rmask,
+                            rmask ? h->hm : nullptr));
+    }
+    for (int t = 0; t < T && c.rnn_cell == LFMQ_CELL_LSTM; ++t) {
       RUN(sgemm(s, B, 4 * H, I, in + (long)t * I, (long)T * I, 1, P + lb.oW, 4 * H, 1, h->z, 4 * H, 0.f, nullptr, 0));
       if (t > 0) {
         const float* hp = rmask ? h->hm : lb.h + (long)(t - 1) * H;
@@ -261,7 +281,16 @@ int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
     RUN(bn_dropout_bwd(s, B, T, H, h->dy, lb.h, P + lb.ogamma, P + lb.omean, P + lb.ovar, c.bn_epsilon, drop,
                        make_key(c, 2 * l, h->tc.last_step, c.dropout), h->tc.last_row0, h->dh_out, G + lb.ogamma,
                        G + lb.obeta, h->scratch, h->scratch_elems));
-    for (int t = T - 1; t >= 0; --t) {
+    const bool gru = c.rnn_cell == LFMQ_CELL_GRU;
+    const int NG = gru ? 3 : 4;
+    for (int t = T - 1; t >= 0 && gru; --t) {
+      RUN(gru_pointwise_bwd(s, B, T, H, t, lb.gates, lb.h, h->dh_out, (t < T - 1) ? h->dh_rec : nullptr, rmask, h->dc,
+                            h->dz, h->dz2));
+      if (t > 0)
+        RUN(sgemm(s, B, H, 3 * H, h->dz2 + (long)t * 3 * H, (long)T * 3 * H, 1, P + lb.oU, 1, 3 * H, h->dh_rec, H, 0.f,
+                  nullptr, 0));
+    }
+    for (int t = T - 1; t >= 0 && !gru; --t) {
       RUN(lstm_pointwise_bwd(s, B, T, H, t, lb.gates, lb.c, h->dh_out, (t < T - 1) ? h->dh_rec : nullptr, rmask, h->dc,
                              h->dz));
       if (t > 0)
@@ -271,12 +300,17 @@ int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
     h->prof.end(LFMQ_REGION_BWD, s);
     h->prof.begin(LFMQ_REGION_WGRAD, s);
     const float* in = (l == 0) ? x : h->layers[l - 1].y;
-    RUN(sgemm(s, I, 4 * H, (int)BT, in, 1, I, h->dz, 4 * H, 1, G + lb.oW, 4 * H, 0.f, h->scratch, h->scratch_elems));
+    // LSTM: one gradient buffer feeds dW, dU and db.  GRU: dz = d(input projection), dz2 = d(recurrent projection),
+    // bias rows [2][3H] = colsum of each.
+    const float* dzr = gru ? h->dz2 : h->dz;
+    const int GH = NG * H;
+    RUN(sgemm(s, I, GH, (int)BT, in, 1, I, h->dz, GH, 1, G + lb.oW, GH, 0.f, h->scratch, h->scratch_elems));
     RUN(shift_mask(s, B, T, H, lb.h, rmask, h->hp));
-    RUN(sgemm(s, H, 4 * H, (int)BT, h->hp, 1, H, h->dz, 4 * H, 1, G + lb.oU, 4 * H, 0.f, h->scratch, h->scratch_elems));
-    RUN(colsum(s, BT, 4 * H, h->dz, G + lb.ob, h->scratch, h->scratch_elems));
+    RUN(sgemm(s, H, GH, (int)BT, h->hp, 1, H, dzr, GH, 1, G + lb.oU, GH, 0.f, h->scratch, h->scratch_elems));
+    RUN(colsum(s, BT, GH, h->dz, G + lb.ob, h->scratch, h->scratch_elems));
+    if (gru) RUN(colsum(s, BT, GH, h->dz2, G + lb.ob + GH, h->scratch, h->scratch_elems));
     if (l > 0)
-      RUN(sgemm(s, (int)BT, I, 4 * H, h->dz, 4 * H, 1, P + lb.oW, 1, 4 * H, h->dy, I, 0.f, nullptr, 0));
+      RUN(sgemm(s, (int)BT, I, GH, h->dz, GH, 1, P + lb.oW, 1, GH, h->dy, I, 0.f, nullptr, 0));
     h->prof.end(LFMQ_REGION_WGRAD, s);
   }
   return 0;
@@ -521,7 +555,8 @@ int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream) {
   RUN(opt_update(s, c.optimizer, h->n_train, h->params, h->grads, h->slots,
                  h->n_slots > 1 ? h->slots + h->n_train : nullptr, tail + 2, lr_eff, 0.f, 0.f, c.sgd_momentum));
   for (int l = 0; l < c.num_layers; ++l)
-    RUN(maxnorm_cols(s, h->layers[l].I, 4 * c.num_hidden, h->params + h->layers[l].oW, c.max_norm));
+    RUN(maxnorm_cols(s, h->layers[l].I, (c.rnn_cell == LFMQ_CELL_GRU ? 3 : 4) * c.num_hidden, h->params + h->layers[l].oW,
+                     c.max_norm));
   h->prof.end(LFMQ_REGION_OPT, s);
   h->tc.weights_dirty = 1;
   return LFMQ_OK;

@@ -32,7 +32,7 @@ class ForecasterEngine(object):
     def __init__(self, *, max_batch, seq_len, n_inputs, n_outputs, num_hidden, num_layers=1, target_idx=0,
                  train=True, precision='fp32', optimizer='Adadelta', dropout=0.0, recurrent_dropout=0.0,
                  target_lambda=0.5, rnn_lambda=0.7, max_grad_norm=50.0, max_norm=3.0, sgd_momentum=0.0,
-                 seed=521, forward_only=False, device=None):
+                 seed=521, forward_only=False, device=None, rnn_cell='lstm'):
         if not torch.cuda.is_available():
             raise N.LfmqError('ForecasterEngine needs a CUDA device (no CPU fallback)')
         self.lib = N.load()
@@ -47,6 +47,9 @@ class ForecasterEngine(object):
         cfg.precision = {'fp32': N.PREC_FP32, 'bf16': N.PREC_BF16}[precision]
         cfg.optimizer = N.OPTIMIZERS[optimizer]
         cfg.forward_only = 1 if forward_only else 0
+        if rnn_cell not in N.CELLS:
+            raise NotImplementedError('rnn_cell=%s (rnn_point_estimate.py:80-102 knows lstm and gru)' % rnn_cell)
+        cfg.rnn_cell = N.CELLS[rnn_cell]
         cfg.dropout, cfg.recurrent_dropout = dropout, recurrent_dropout
         cfg.target_lambda, cfg.rnn_lambda = target_lambda, rnn_lambda
         cfg.max_grad_norm, cfg.max_norm, cfg.sgd_momentum = max_grad_norm, max_norm, sgd_momentum

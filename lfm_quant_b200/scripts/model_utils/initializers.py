@@ -42,9 +42,9 @@ class Initializer(object):
         out = []
         for name, shape in specs:
             leaf = name.split('/')[-1]
-            if name.startswith('lstm') and leaf == 'kernel':
+            if name.startswith(('lstm', 'gru')) and leaf == 'kernel':
                 w = kernel_init(shape, rng)
-            elif leaf == 'recurrent_kernel':            # keras Orthogonal on [H, 4H]
+            elif leaf == 'recurrent_kernel':            # keras Orthogonal on [H, 4H] (GRU: [H, 3H])
                 a = rng.normal(size=(shape[1], shape[0]))
                 q, r = np.linalg.qr(a)
                 w = (q * np.sign(np.diag(r))).T

@@ -32,8 +32,8 @@ class NativeForecaster(object):
     def __init__(self, config, seq_len, n_inputs, n_outputs, target_idx):
         from ....engine import ForecasterEngine
         self.config = config
-        if config.rnn_cell != 'lstm':
-            raise NotImplementedError('rnn_cell=%s: only the LSTM cell is built (GRU is a "next" row)' % config.rnn_cell)
+        if config.rnn_cell not in ('lstm', 'gru'):
+            raise NotImplementedError                    # rnn_point_estimate.py:101-102
         if config.forecast_steps != 1:
             raise NotImplementedError('forecast_steps > 1 is a "next" row of the scope table')
         self.engine = ForecasterEngine(
@@ -42,7 +42,8 @@ class NativeForecaster(object):
             train=bool(config.train), precision=getattr(config, 'precision', 'fp32'), optimizer=config.optimizer,
             dropout=config.dropout, recurrent_dropout=config.recurrent_dropout, target_lambda=config.target_lambda,
             rnn_lambda=config.rnn_lambda, max_grad_norm=config.max_grad_norm, max_norm=float(config.max_norm),
-            sgd_momentum=config.sgd_momentum, seed=config.seed, forward_only=not config.train)
+            sgd_momentum=config.sgd_momentum, seed=config.seed, forward_only=not config.train,
+            rnn_cell=config.rnn_cell)
         specs = [(n, s) for (n, s, _, tr) in self.engine.specs if tr]
         self.engine.set_weights(Initializer(config).initial_weights(specs))
         self.trainable_variables = [_Variable(self, i, n, s) for i, (n, s) in enumerate(specs)]

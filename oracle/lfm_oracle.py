@@ -216,45 +216,55 @@ def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
-def param_names(num_layers):
-    """Keras ``model.trainable_variables`` order for RNNPointEstimate (rnn_point_estimate.py:76-105)."""
+N_GATES = {'lstm': 4, 'gru': 3}
+
+
+def param_names(num_layers, rnn_cell='lstm'):
+    """Keras ``model.trainable_variables`` order for RNNPointEstimate (rnn_point_estimate.py:76-105);
+    layers are named lstm_k or gru_k after config.rnn_cell (:80-102)."""
     names = []
     for l in range(1, num_layers + 1):
         bn = 'batch_normalization' if l == 1 else 'batch_normalization_%d' % (l - 1)
-        names += ['lstm_%d/kernel' % l, 'lstm_%d/recurrent_kernel' % l, 'lstm_%d/bias' % l,
-                  bn + '/gamma', bn + '/beta']
+        names += ['%s_%d/kernel' % (rnn_cell, l), '%s_%d/recurrent_kernel' % (rnn_cell, l),
+                  '%s_%d/bias' % (rnn_cell, l), bn + '/gamma', bn + '/beta']
     names += ['OUTPUT_1/kernel', 'OUTPUT_1/bias']
     return names
 
 
-def param_shapes(num_layers, n_inputs, n_outputs, num_hidden):
+def param_shapes(num_layers, n_inputs, n_outputs, num_hidden, rnn_cell='lstm'):
+    """GRU (Keras default reset_after=True): 3 gate blocks z|r|h and a [2, 3H] bias (input row, recurrent row)."""
     H = num_hidden
+    G = N_GATES[rnn_cell]
     shapes = []
     for l in range(num_layers):
         I = n_inputs if l == 0 else H
-        shapes += [(I, 4 * H), (H, 4 * H), (4 * H,), (H,), (H,)]
+        shapes += [(I, G * H), (H, G * H), (4 * H,) if rnn_cell == 'lstm' else (2, 3 * H), (H,), (H,)]
     shapes += [(H, n_outputs), (n_outputs,)]
     return shapes
 
 
 def init_params(num_layers, n_inputs, n_outputs, num_hidden, init_scale=1.0, seed=521,
-                dtype=np.float32):
+                dtype=np.float32, rnn_cell='lstm'):
     """Initial weights in the reference's distribution families (initializers.py:14-24 for the
     LSTM kernel; Keras defaults for the rest: orthogonal recurrent kernel, unit forget bias,
     gamma=1, beta=0, Glorot-uniform Dense).  TF's RNG streams cannot be reproduced (SURVEY
     App. B #7) so parity tests always *inject* these numpy-drawn weights on both sides."""
     rng = np.random.RandomState(seed)
     H = num_hidden
+    G = N_GATES[rnn_cell]
     out = []
     for l in range(num_layers):
         I = n_inputs if l == 0 else H
-        out.append(rng.uniform(-init_scale, init_scale, size=(I, 4 * H)))
-        a = rng.normal(size=(4 * H, H))
+        out.append(rng.uniform(-init_scale, init_scale, size=(I, G * H)))
+        a = rng.normal(size=(G * H, H))
         q, r = np.linalg.qr(a)
         q = q * np.sign(np.diag(r))
-        out.append(q.T.copy())                       # [H, 4H], orthonormal rows
-        b = np.zeros(4 * H)
-        b[H:2 * H] = 1.0                             # unit_forget_bias
+        out.append(q.T.copy())                       # [H, G*H], orthonormal rows
+        if rnn_cell == 'lstm':
+            b = np.zeros(4 * H)
+            b[H:2 * H] = 1.0                         # unit_forget_bias
+        else:
+            b = np.zeros((2, 3 * H))                 # Keras GRU: bias_initializer='zeros'
         out.append(b)
         out.append(np.ones(H))
         out.append(np.zeros(H))
@@ -336,8 +346,80 @@ def lstm_backward(dh_out, cache, need_dx):
     return dW, dU, db, dx
 
 
+def gru_forward(x, W, U, b2, rec_mask=None):
+    """Keras GRU(return_sequences=True), reset_after=True (the TF 2.x default), implementation=2
+    (rnn_point_estimate.py:89-98).  Restated from the published cell equations [EXT, SURVEY 8f-1]:
+
+        xz = x_t W + b2[0];  hz = (h_{t-1} * mask) U + b2[1]          gate blocks z|r|h
+        z = sigmoid(xz_z + hz_z);  r = sigmoid(xz_r + hz_r);  hh = tanh(xz_h + r * hz_h)
+        h_t = z * h_{t-1} + (1 - z) * hh                              (the carry uses the unmasked h_{t-1})
+
+    Pinned against torch.nn.GRU (same equations, gate order r|z|n) in tests/test_oracle.py.
+    """
+    B, T, I = x.shape
+    H = U.shape[0]
+    dt = x.dtype
+    h = np.zeros((B, H), dtype=dt)
+    hs = np.empty((B, T, H), dtype=dt)
+    gates = np.empty((B, T, 4 * H), dtype=dt)         # z | r | hh | q = hz_h (kept for the backward pass)
+    for t in range(T):
+        hm = h if rec_mask is None else h * rec_mask
+        xz = x[:, t, :] @ W + b2[0]
+        hz = hm @ U + b2[1]
+        z = sigmoid(xz[:, :H] + hz[:, :H])
+        r = sigmoid(xz[:, H:2 * H] + hz[:, H:2 * H])
+        q = hz[:, 2 * H:]
+        hh = np.tanh(xz[:, 2 * H:] + r * q)
+        h = z * h + (1.0 - z) * hh
+        hs[:, t] = h
+        gates[:, t, :H] = z
+        gates[:, t, H:2 * H] = r
+        gates[:, t, 2 * H:3 * H] = hh
+        gates[:, t, 3 * H:] = q
+    return hs, (x, W, U, hs, gates, rec_mask)
+
+
+def gru_backward(dh_out, cache, need_dx):
+    """BPTT through ``gru_forward``.  Returns dW, dU, db [2,3H], dx."""
+    x, W, U, hs, gates, rec_mask = cache
+    B, T, I = x.shape
+    H = U.shape[0]
+    dt = x.dtype
+    dxz_all = np.empty((B, T, 3 * H), dtype=dt)
+    dhz_all = np.empty((B, T, 3 * H), dtype=dt)
+    dh_carry = np.zeros((B, H), dtype=dt)             # through z * h_{t-1}
+    dh_rec = np.zeros((B, H), dtype=dt)               # through the recurrent matmul
+    for t in range(T - 1, -1, -1):
+        z = gates[:, t, :H]
+        r = gates[:, t, H:2 * H]
+        hh = gates[:, t, 2 * H:3 * H]
+        q = gates[:, t, 3 * H:]
+        h_prev = hs[:, t - 1] if t > 0 else np.zeros((B, H), dtype=dt)
+        dh = dh_out[:, t] + dh_carry + dh_rec
+        da_h = dh * (1.0 - z) * (1.0 - hh * hh)
+        da_z = dh * (h_prev - hh) * z * (1.0 - z)
+        da_r = da_h * q * r * (1.0 - r)
+        dh_carry = dh * z
+        dxz_all[:, t] = np.concatenate([da_z, da_r, da_h], axis=1)
+        dhz = np.concatenate([da_z, da_r, da_h * r], axis=1)
+        dhz_all[:, t] = dhz
+        dh_rec = dhz @ U.T
+        if rec_mask is not None:
+            dh_rec = dh_rec * rec_mask
+    h_prev = np.concatenate([np.zeros((B, 1, H), dtype=dt), hs[:, :-1]], axis=1)
+    if rec_mask is not None:
+        h_prev = h_prev * rec_mask[:, None, :]
+    dxz2 = dxz_all.reshape(B * T, 3 * H)
+    dhz2 = dhz_all.reshape(B * T, 3 * H)
+    dW = x.reshape(B * T, I).T @ dxz2
+    dU = h_prev.reshape(B * T, H).T @ dhz2
+    db = np.stack([dxz2.sum(axis=0), dhz2.sum(axis=0)])
+    dx = (dxz2 @ W.T).reshape(B, T, I) if need_dx else None
+    return dW, dU, db, dx
+
+
 def forward(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, training=False,
-            seed=0, step=0, row0=0, bn_mean=None, bn_var=None):
+            seed=0, step=0, row0=0, bn_mean=None, bn_var=None, rnn_cell='lstm'):
     """model(inp) for RNNPointEstimate, forecast_steps=1 (rnn_point_estimate.py:66-107).
 
     BatchNormalization runs in inference mode in *both* train and predict;
@@ -356,7 +438,7 @@ def forward(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, traini
         rmask = None
         if training and recurrent_dropout > 0.0:
             rmask = dropout_mask(seed, step, 2 * l + 1, row0, B, H, recurrent_dropout, dtype=dt.type)
-        hs, lc = lstm_forward(cur, W, U, b, rmask)
+        hs, lc = (lstm_forward if rnn_cell == 'lstm' else gru_forward)(cur, W, U, b, rmask)
         inv = (1.0 / np.sqrt(var + dt.type(BN_EPS))).astype(dt)
         y = gamma * (hs - mean) * inv + beta
         dmask = None
@@ -403,7 +485,7 @@ def loss_point_estimate(y_true, y_pred, *, target_idx, target_lambda, rnn_lambda
     return loss, mse_0, dpred, (s0, s1, s2, mask.sum())
 
 
-def backward(dpred, fcache, *, num_layers):
+def backward(dpred, fcache, *, num_layers, rnn_cell='lstm'):
     """Gradients for every trainable variable, Keras order (train.py:192)."""
     caches, y_last, Wo = fcache
     B, T, O = dpred.shape
@@ -419,7 +501,7 @@ def backward(dpred, fcache, *, num_layers):
         grads[5 * l + 3] = np.sum(dy * (hs - mean) * inv, axis=(0, 1))
         grads[5 * l + 4] = np.sum(dy, axis=(0, 1))
         dh_out = dy * gamma * inv
-        dW, dU, db, dx = lstm_backward(dh_out, lc, need_dx=(l > 0))
+        dW, dU, db, dx = (lstm_backward if rnn_cell == 'lstm' else gru_backward)(dh_out, lc, need_dx=(l > 0))
         grads[5 * l], grads[5 * l + 1], grads[5 * l + 2] = dW, dU, db
         dy = dx
     return grads
@@ -524,11 +606,12 @@ def train_step(params, slots, x, y, it, cfg, *, row0=0, batch_global=None, mask_
     L = cfg['num_layers']
     preds, fc = forward(params, x, num_layers=L, dropout=cfg.get('dropout', 0.0),
                         recurrent_dropout=cfg.get('recurrent_dropout', 0.0),
-                        training=cfg.get('train', True), seed=cfg.get('seed', 0), step=it, row0=row0)
+                        training=cfg.get('train', True), seed=cfg.get('seed', 0), step=it, row0=row0,
+                        rnn_cell=cfg.get('rnn_cell', 'lstm'))
     loss, mse, dpred, _ = loss_point_estimate(y.astype(preds.dtype), preds, target_idx=cfg['target_idx'],
                                               target_lambda=cfg['target_lambda'], rnn_lambda=cfg['rnn_lambda'],
                                               batch_global=batch_global, mask_count_global=mask_count_global)
-    grads = backward(dpred, fc, num_layers=L)
+    grads = backward(dpred, fc, num_layers=L, rnn_cell=cfg.get('rnn_cell', 'lstm'))
     raw = [g.copy() for g in grads]
     gn = None
     if cfg.get('max_grad_norm', 0.0) > 0:

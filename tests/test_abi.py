@@ -23,12 +23,12 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lfmq_abi_version() == 1
+    assert lib.lfmq_abi_version() == N.ABI_VERSION == 2
 
 
 def test_struct_sizes_match_header_layout():
     # 12 int32 + 8 float + uint64, naturally aligned
-    assert C.sizeof(N.LfmqConfig) == 12 * 4 + 8 * 4 + 8
+    assert C.sizeof(N.LfmqConfig) == 14 * 4 + 8 * 4 + 8
     assert C.sizeof(N.LfmqGatherArgs) == 11 * 4 + 4 + 12 * 8
 
 

@@ -82,3 +82,24 @@ def test_dataset_get_batch_matches_oracle(workdir):
         np.testing.assert_array_equal(md[:, 2].astype(np.float64), ref[2])
         assert (x.cpu().numpy()[:, :-1, 16:] == 0).all()          # aux masking
     configs.reset()
+
+
+def test_cli_trains_and_predicts_with_the_gru_cell(workdir):
+    """config.rnn_cell = 'gru' (lfm_quant.py:39, rnn_point_estimate.py:89-98) through the same CLI flow."""
+    conf = str(workdir / 'config' / 'system-test.conf')
+    extra = ['--rnn_cell', 'gru', '--model_dir', 'system-test-gru']
+    configs.reset()
+    valid_mse = cli.main(['--config=' + conf, '--train=True'] + extra)
+    mdir = workdir / 'experiments' / 'system-test-gru'
+    assert np.isfinite(valid_mse)
+    ep = pd.read_csv(mdir / 'train_log' / 'system-test-train-logs-epoch.csv')
+    assert len(ep) == 2 and ep['mse'].iloc[1] < ep['mse'].iloc[0]
+    w = np.load(mdir / 'chkpts' / 'chkpt.lfmq.npz')
+    assert set(orc.param_names(1, 'gru')) <= set(w.files)
+    assert w['gru_1/kernel'].shape == (32, 192) and w['gru_1/bias'].shape == (2, 192)
+    assert np.linalg.norm(w['gru_1/kernel'], axis=0).max() <= 3.0 * (1 + 1e-5)
+    configs.reset()
+    df = cli.main(['--config=' + conf, '--train=False'] + extra)
+    out = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
+    assert len(out) == len(df) > 100 and np.isfinite(out['norm_preds_1']).all()
+    configs.reset()

@@ -264,3 +264,54 @@ def test_cfg3_full_size_dropout_block_and_shard_sum():
     assert torch.isfinite(full).all() and float(full[:nt].abs().max()) > 0
     assert rel_err(acc.cpu().numpy(), full.cpu().numpy()) < TOL
     eng.close()
+
+
+# ---- GRU cell through the C ABI (LFMQ_CELL_GRU; rnn_point_estimate.py:89-98) ----
+GRU_SHAPES = [(32, 20, 32, 16, 64, 1), (5, 6, 7, 3, 8, 2), (1, 1, 4, 2, 4, 1), (130, 9, 33, 17, 132, 2)]
+
+
+@pytest.mark.parametrize('shape', GRU_SHAPES)
+def test_gru_forward_and_gradients_match_oracle(shape):
+    B, T, F, O, H, L = shape
+    params, x, y = make_problem(B, T, F, O, H, L, seed=13, rnn_cell='gru')
+    eng = make_engine(B, T, F, O, H, L, target_idx=O - 1, rnn_cell='gru')
+    assert [n for n, _, _, _ in eng.trainable_specs][:3] == ['gru_1/kernel', 'gru_1/recurrent_kernel', 'gru_1/bias']
+    eng.set_weights(params)
+    preds = eng.forward(_cuda(x)).cpu().numpy()
+    ref, fc = orc.forward(params, x.astype(np.float64), num_layers=L, rnn_cell='gru')
+    assert rel_err(preds, ref) < TOL
+    eng.backward(_cuda(x), _cuda(y))
+    loss, mse, dpred, _ = orc.loss_point_estimate(y.astype(np.float64), ref, target_idx=O - 1, target_lambda=0.5,
+                                                  rnn_lambda=0.7)
+    gref = orc.backward(dpred, fc, num_layers=L, rnn_cell='gru')
+    tail = eng.grads[eng.n_trainable:eng.n_trainable + 2].cpu().numpy()
+    assert tail[0] == pytest.approx(loss, rel=TOL) and tail[1] == pytest.approx(mse, rel=TOL)
+    for (name, _, _, _), g, r in zip(eng.trainable_specs, eng.grads_list(), gref):
+        assert g.shape == r.shape and rel_err(g, r) < TOL, name
+
+
+def test_gru_dropout_and_train_steps_match_oracle():
+    B, T, F, O, H, L = 16, 6, 8, 4, 16, 2
+    params, x, y = make_problem(B, T, F, O, H, L, seed=14, rnn_cell='gru')
+    kw = dict(dropout=0.3, recurrent_dropout=0.2, seed=521)
+    cfg = dict(num_layers=L, target_idx=1, target_lambda=0.5, rnn_lambda=0.7, max_grad_norm=0.05, optimizer='Adam',
+               max_norm=0.8, sgd_momentum=0.0, train=True, rnn_cell='gru', **kw)
+    eng = make_engine(B, T, F, O, H, L, target_idx=1, optimizer='Adam', max_grad_norm=0.05, max_norm=0.8,
+                      rnn_cell='gru', **kw)
+    eng.set_weights(params)
+    p = [q.copy() for q in params]
+    slots = orc.zero_slots('Adam', p)
+    xc, yc = _cuda(x), _cuda(y)
+    for it in range(3):
+        out = eng.train_step(xc, yc, it, 0.01).cpu().numpy()
+        p, mse, loss, raw, gn = orc.train_step(p, slots, x.astype(np.float64), y.astype(np.float64), it, cfg, lr=0.01)
+        assert out[0] == pytest.approx(loss, rel=TOL) and out[1] == pytest.approx(mse, rel=TOL), it
+    for (name, _, _, _), w, r in zip(eng.trainable_specs, eng.get_weights(), p):
+        assert rel_err(w, r) < 5 * TOL, name
+    assert np.linalg.norm(eng.get_weights()[0], axis=0).max() <= 0.8 * (1 + 1e-5)       # MaxNorm on gru_1/kernel
+
+
+def test_gru_is_refused_loudly_on_the_bf16_path():
+    from lfm_quant_b200 import _native as N
+    with pytest.raises(N.LfmqError, match='LSTM cell only'):
+        make_engine(256, 8, 32, 16, 256, 1, precision='bf16', rnn_cell='gru')

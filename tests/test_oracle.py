@@ -247,3 +247,68 @@ def test_tf_pin_script_degrades_when_tensorflow_is_absent():
         assert r.returncode == 0 and 'TF oracle unavailable' in r.stdout
     else:
         assert r.returncode == 0 and 'PINNED against tensorflow' in r.stdout, r.stdout + r.stderr
+
+
+# ---- GRU cell (rnn_point_estimate.py:89-98).  torch.nn.GRU implements the same reset-after equations
+# with gate order r|z|n, so it pins the oracle's z|r|h restatement forward and backward.
+def _torch_gru(W, U, b2):
+    H = U.shape[0]
+    perm = np.concatenate([np.arange(H, 2 * H), np.arange(0, H), np.arange(2 * H, 3 * H)])
+    m = torch.nn.GRU(W.shape[0], H, batch_first=True).double()
+    with torch.no_grad():
+        m.weight_ih_l0.copy_(torch.from_numpy(W[:, perm].T.copy()))
+        m.weight_hh_l0.copy_(torch.from_numpy(U[:, perm].T.copy()))
+        m.bias_ih_l0.copy_(torch.from_numpy(b2[0][perm].copy()))
+        m.bias_hh_l0.copy_(torch.from_numpy(b2[1][perm].copy()))
+    return m, perm
+
+
+def test_gru_matches_torch_nn_gru_forward_and_backward():
+    B, T, F, H = 6, 9, 5, 12
+    rng = np.random.RandomState(2)
+    W, U = rng.normal(size=(F, 3 * H)) * 0.4, rng.normal(size=(H, 3 * H)) * 0.4
+    b2 = rng.normal(size=(2, 3 * H)) * 0.3
+    x = rng.normal(size=(B, T, F))
+    dh = rng.normal(size=(B, T, H))
+    hs, cache = orc.gru_forward(x, W, U, b2)
+    m, perm = _torch_gru(W, U, b2)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    out = m(xt)[0]
+    assert np.abs(hs - out.detach().numpy()).max() < 1e-12
+    out.backward(torch.from_numpy(dh))
+    dW, dU, db, dx = orc.gru_backward(dh, cache, need_dx=True)
+    inv = np.argsort(perm)
+    assert np.abs(dW - m.weight_ih_l0.grad.numpy().T[:, inv]).max() < 1e-10
+    assert np.abs(dU - m.weight_hh_l0.grad.numpy().T[:, inv]).max() < 1e-10
+    assert np.abs(db[0] - m.bias_ih_l0.grad.numpy()[inv]).max() < 1e-10
+    assert np.abs(db[1] - m.bias_hh_l0.grad.numpy()[inv]).max() < 1e-10
+    assert np.abs(dx - xt.grad.numpy()).max() < 1e-10
+
+
+def test_gru_stack_finite_differences_with_dropout():
+    B, T, F, O, H, L = 4, 5, 6, 3, 8, 2
+    rng = np.random.RandomState(4)
+    P = orc.init_params(L, F, O, H, seed=7, dtype=np.float64, rnn_cell='gru')
+    for l in range(L):
+        P[5 * l + 2] = rng.normal(size=(2, 3 * H)) * 0.3
+    assert orc.param_names(L, 'gru')[:3] == ['gru_1/kernel', 'gru_1/recurrent_kernel', 'gru_1/bias']
+    assert [p.shape for p in P] == [tuple(s) for s in orc.param_shapes(L, F, O, H, 'gru')]
+    x = rng.normal(size=(B, T, F))
+    y = rng.normal(size=(B, T, O))
+    y[0, :2] = 0.0
+    kw = dict(num_layers=L, rnn_cell='gru', training=True, dropout=0.25, recurrent_dropout=0.2, seed=9, step=3, row0=40)
+
+    def loss_of(Q):
+        pr, fc = orc.forward(Q, x, **kw)
+        return orc.loss_point_estimate(y, pr, target_idx=1, target_lambda=0.5, rnn_lambda=0.7), fc
+
+    (l0, _, dp, _), fc = loss_of(P)
+    g = orc.backward(dp, fc, num_layers=L, rnn_cell='gru')
+    for k in range(len(P)):
+        for _ in range(4):
+            idx = tuple(rng.randint(s) for s in P[k].shape)
+            Qp, Qm = [q.copy() for q in P], [q.copy() for q in P]
+            Qp[k][idx] += 1e-6
+            Qm[k][idx] -= 1e-6
+            fd = (loss_of(Qp)[0][0] - loss_of(Qm)[0][0]) / 2e-6
+            assert abs(fd - g[k][idx]) < 1e-6 * max(1.0, abs(fd)), (k, idx)

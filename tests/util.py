@@ -4,11 +4,11 @@ import numpy as np
 import lfm_oracle as orc
 
 
-def make_problem(B, T, F, O, H, L, seed=0, zero_rows=True, init_scale=0.5):
+def make_problem(B, T, F, O, H, L, seed=0, zero_rows=True, init_scale=0.5, rnn_cell='lstm'):
     rng = np.random.RandomState(seed)
-    params = orc.init_params(L, F, O, H, init_scale=init_scale, seed=seed + 1, dtype=np.float64)
+    params = orc.init_params(L, F, O, H, init_scale=init_scale, seed=seed + 1, dtype=np.float64, rnn_cell=rnn_cell)
     for l in range(L):
-        params[5 * l + 2] = params[5 * l + 2] + rng.normal(size=4 * H) * 0.1
+        params[5 * l + 2] = params[5 * l + 2] + rng.normal(size=params[5 * l + 2].shape) * 0.1
         params[5 * l + 3] = params[5 * l + 3] + rng.normal(size=H) * 0.1
         params[5 * l + 4] = params[5 * l + 4] + rng.normal(size=H) * 0.1
     params[5 * L + 1] = params[5 * L + 1] + rng.normal(size=O) * 0.1
