@@ -219,7 +219,7 @@ def sigmoid(x):
 N_GATES = {'lstm': 4, 'gru': 3}
 
 
-def param_names(num_layers, rnn_cell='lstm'):
+def param_names(num_layers, rnn_cell='lstm', uq=False):
     """Keras ``model.trainable_variables`` order for RNNPointEstimate (rnn_point_estimate.py:76-105);
     layers are named lstm_k or gru_k after config.rnn_cell (:80-102)."""
     names = []
@@ -227,11 +227,14 @@ def param_names(num_layers, rnn_cell='lstm'):
         bn = 'batch_normalization' if l == 1 else 'batch_normalization_%d' % (l - 1)
         names += ['%s_%d/kernel' % (rnn_cell, l), '%s_%d/recurrent_kernel' % (rnn_cell, l),
                   '%s_%d/bias' % (rnn_cell, l), bn + '/gamma', bn + '/beta']
-    names += ['OUTPUT_1/kernel', 'OUTPUT_1/bias']
+    if uq:      # RNNUqRangeEstimate (rnn_uq_range_estimate.py:104-108): target head, then variance head
+        names += ['OUTPUT_TARGET_1/kernel', 'OUTPUT_TARGET_1/bias', 'OUTPUT_VARIANCE_1/kernel', 'OUTPUT_VARIANCE_1/bias']
+    else:
+        names += ['OUTPUT_1/kernel', 'OUTPUT_1/bias']
     return names
 
 
-def param_shapes(num_layers, n_inputs, n_outputs, num_hidden, rnn_cell='lstm'):
+def param_shapes(num_layers, n_inputs, n_outputs, num_hidden, rnn_cell='lstm', uq=False):
     """GRU (Keras default reset_after=True): 3 gate blocks z|r|h and a [2, 3H] bias (input row, recurrent row)."""
     H = num_hidden
     G = N_GATES[rnn_cell]
@@ -239,12 +242,12 @@ def param_shapes(num_layers, n_inputs, n_outputs, num_hidden, rnn_cell='lstm'):
     for l in range(num_layers):
         I = n_inputs if l == 0 else H
         shapes += [(I, G * H), (H, G * H), (4 * H,) if rnn_cell == 'lstm' else (2, 3 * H), (H,), (H,)]
-    shapes += [(H, n_outputs), (n_outputs,)]
+    shapes += [(H, n_outputs), (n_outputs,)] * (2 if uq else 1)
     return shapes
 
 
 def init_params(num_layers, n_inputs, n_outputs, num_hidden, init_scale=1.0, seed=521,
-                dtype=np.float32, rnn_cell='lstm'):
+                dtype=np.float32, rnn_cell='lstm', uq=False):
     """Initial weights in the reference's distribution families (initializers.py:14-24 for the
     LSTM kernel; Keras defaults for the rest: orthogonal recurrent kernel, unit forget bias,
     gamma=1, beta=0, Glorot-uniform Dense).  TF's RNG streams cannot be reproduced (SURVEY
@@ -269,8 +272,9 @@ def init_params(num_layers, n_inputs, n_outputs, num_hidden, init_scale=1.0, see
         out.append(np.ones(H))
         out.append(np.zeros(H))
     lim = np.sqrt(6.0 / (H + n_outputs))
-    out.append(rng.uniform(-lim, lim, size=(H, n_outputs)))
-    out.append(np.zeros(n_outputs))
+    for _ in range(2 if uq else 1):
+        out.append(rng.uniform(-lim, lim, size=(H, n_outputs)))
+        out.append(np.zeros(n_outputs))
     return [p.astype(dtype) for p in out]
 
 
@@ -418,14 +422,10 @@ def gru_backward(dh_out, cache, need_dx):
     return dW, dU, db, dx
 
 
-def forward(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, training=False,
-            seed=0, step=0, row0=0, bn_mean=None, bn_var=None, rnn_cell='lstm'):
-    """model(inp) for RNNPointEstimate, forecast_steps=1 (rnn_point_estimate.py:66-107).
-
-    BatchNormalization runs in inference mode in *both* train and predict (SURVEY App. B #1);
-    Dropout / recurrent dropout are active iff ``training`` (= config.train, :87,89).
-    Returns preds [B,T,O] and the cache for ``backward``.
-    """
+def _trunk(params, x, *, num_layers, dropout, recurrent_dropout, training, seed, step, row0, bn_mean, bn_var,
+           rnn_cell):
+    """The recurrent stack shared by RNNPointEstimate and RNNUqRangeEstimate: per layer LSTM|GRU ->
+    BatchNormalization (inference-mode affine, SURVEY App. B #1) -> Dropout."""
     B, T, _ = x.shape
     dt = x.dtype
     cur = x
@@ -447,9 +447,77 @@ def forward(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, traini
             y = y * dmask
         caches.append((lc, hs, mean, inv, gamma, dmask))
         cur = y
+    return cur, caches
+
+
+def forward(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, training=False,
+            seed=0, step=0, row0=0, bn_mean=None, bn_var=None, rnn_cell='lstm'):
+    """model(inp) for RNNPointEstimate, forecast_steps=1 (rnn_point_estimate.py:66-107).
+
+    BatchNormalization runs in inference mode in *both* train and predict (SURVEY App. B #1);
+    Dropout / recurrent dropout are active iff ``training`` (= config.train, :87,89).
+    Returns preds [B,T,O] and the cache for ``backward``.
+    """
+    cur, caches = _trunk(params, x, num_layers=num_layers, dropout=dropout, recurrent_dropout=recurrent_dropout,
+                         training=training, seed=seed, step=step, row0=row0, bn_mean=bn_mean, bn_var=bn_var,
+                         rnn_cell=rnn_cell)
     Wo, bo = params[5 * num_layers], params[5 * num_layers + 1]
     preds = cur @ Wo + bo
     return preds, (caches, cur, Wo)
+
+
+VAR_FLOOR = 1e-6
+
+
+def softplus(a):
+    return np.logaddexp(a, 0.0)
+
+
+def forward_uq(params, x, *, num_layers, dropout=0.0, recurrent_dropout=0.0, seed=0, step=0, row0=0,
+               bn_mean=None, bn_var=None, rnn_cell='lstm'):
+    """model(inp) for RNNUqRangeEstimate, forecast_steps=1 (rnn_uq_range_estimate.py:66-110): the same trunk with
+    Dropout / recurrent dropout ALWAYS active (``training=True`` is a literal there, :86,88 -- MC dropout, also in
+    predict), a target head and a variance head ``max(softplus(.), 1e-6)`` (model_utils/custom_layers.py:12-13).
+    Returns (pred [B,T,O], var [B,T,O]) and the cache for ``backward_uq``."""
+    cur, caches = _trunk(params, x, num_layers=num_layers, dropout=dropout, recurrent_dropout=recurrent_dropout,
+                         training=True, seed=seed, step=step, row0=row0, bn_mean=bn_mean, bn_var=bn_var,
+                         rnn_cell=rnn_cell)
+    Wt, bt, Wv, bv = params[5 * num_layers:5 * num_layers + 4]
+    pred = cur @ Wt + bt
+    a = cur @ Wv + bv
+    var = np.maximum(softplus(a), x.dtype.type(VAR_FLOOR))
+    return pred, var, (caches, cur, Wt, Wv, a)
+
+
+def loss_uq_estimate(y_true, y_pred, y_var, *, target_idx, target_lambda, rnn_lambda):
+    """losses.py:180-247 + :249-284, 'RNN' branch.  Returns (uq_loss, uq_loss_last_tar, mse_0, dLoss/dpred, dLoss/dvar).
+
+    Per element the loss term is (p*m - y)^2 / (v*m) + log(v*m) with m the [b,t] mask (:197-201, :272): a zero-padded
+    step therefore contributes 0 * inf + log 0 = NaN and the reference's loss (and every gradient) is NaN as soon as a
+    batch holds one -- reproduced here by plain IEEE arithmetic, not special-cased.  Denominators: number of unmasked
+    rows in the slice times the slice's last dimension (:270-271), i.e. 1 for the target-field slice, O otherwise."""
+    B, T, K = y_true.shape
+    dt = y_pred.dtype
+    mask = (~np.all(y_true == 0.0, axis=-1)).astype(dt)
+    m3 = mask[..., None]
+    pm, vm = y_pred * m3, y_var * m3
+    with np.errstate(divide='ignore', invalid='ignore'):
+        diff = (pm - y_true) ** 2
+        term = diff * (1.0 / vm) + np.log(vm)
+        ms_last = mask[:, -1].sum()
+        ms_all = mask.sum()
+        uq0 = np.sum(term[:, -1, target_idx]) / (ms_last * 1)
+        uq1 = np.sum(term[:, -1, :]) / (ms_last * K)
+        uq2 = np.sum(term) / (ms_all * K)
+        mse_0 = np.mean((y_true[:, -1, target_idx] - pm[:, -1, target_idx]) ** 2)
+        p1, p2 = dt.type(target_lambda), dt.type(rnn_lambda)
+        loss = p1 * uq0 + (1 - p1) * (p2 * uq1 + (1 - p2) * uq2)
+        coef = np.full((B, T, K), (1 - p1) * (1 - p2) / (ms_all * K), dtype=dt)
+        coef[:, -1, :] += (1 - p1) * p2 / (ms_last * K)
+        coef[:, -1, target_idx] += p1 / ms_last
+        dpred = coef * (2.0 * (pm - y_true) / vm) * m3
+        dvar = coef * (-diff / (vm * vm) + 1.0 / vm) * m3
+    return loss, uq0, mse_0, dpred.astype(dt), dvar.astype(dt)
 
 
 def loss_point_estimate(y_true, y_pred, *, target_idx, target_lambda, rnn_lambda,
@@ -485,15 +553,7 @@ def loss_point_estimate(y_true, y_pred, *, target_idx, target_lambda, rnn_lambda
     return loss, mse_0, dpred, (s0, s1, s2, mask.sum())
 
 
-def backward(dpred, fcache, *, num_layers, rnn_cell='lstm'):
-    """Gradients for every trainable variable, Keras order (train.py:192)."""
-    caches, y_last, Wo = fcache
-    B, T, O = dpred.shape
-    H = Wo.shape[0]
-    grads = [None] * (5 * num_layers + 2)
-    grads[5 * num_layers] = y_last.reshape(B * T, H).T @ dpred.reshape(B * T, O)
-    grads[5 * num_layers + 1] = dpred.reshape(B * T, O).sum(axis=0)
-    dy = dpred @ Wo.T
+def _trunk_backward(dy, caches, grads, *, num_layers, rnn_cell):
     for l in range(num_layers - 1, -1, -1):
         lc, hs, mean, inv, gamma, dmask = caches[l]
         if dmask is not None:
@@ -505,6 +565,35 @@ def backward(dpred, fcache, *, num_layers, rnn_cell='lstm'):
         grads[5 * l], grads[5 * l + 1], grads[5 * l + 2] = dW, dU, db
         dy = dx
     return grads
+
+
+def backward(dpred, fcache, *, num_layers, rnn_cell='lstm'):
+    """Gradients for every trainable variable, Keras order (train.py:192)."""
+    caches, y_last, Wo = fcache
+    B, T, O = dpred.shape
+    H = Wo.shape[0]
+    grads = [None] * (5 * num_layers + 2)
+    grads[5 * num_layers] = y_last.reshape(B * T, H).T @ dpred.reshape(B * T, O)
+    grads[5 * num_layers + 1] = dpred.reshape(B * T, O).sum(axis=0)
+    dy = dpred @ Wo.T
+    return _trunk_backward(dy, caches, grads, num_layers=num_layers, rnn_cell=rnn_cell)
+
+
+def backward_uq(dpred, dvar, fcache, *, num_layers, rnn_cell='lstm'):
+    """tape.gradient(uq_loss, trainable_variables) (train.py:218).  The variance head's activation passes the gradient
+    through softplus where it is above the 1e-6 floor and blocks it below (tf.maximum)."""
+    caches, y_last, Wt, Wv, a = fcache
+    B, T, O = dpred.shape
+    H = Wt.shape[0]
+    da = dvar * np.where(softplus(a) > VAR_FLOOR, sigmoid(a), 0.0)
+    grads = [None] * (5 * num_layers + 4)
+    y2 = y_last.reshape(B * T, H)
+    grads[5 * num_layers] = y2.T @ dpred.reshape(B * T, O)
+    grads[5 * num_layers + 1] = dpred.reshape(B * T, O).sum(axis=0)
+    grads[5 * num_layers + 2] = y2.T @ da.reshape(B * T, O)
+    grads[5 * num_layers + 3] = da.reshape(B * T, O).sum(axis=0)
+    dy = dpred @ Wt.T + da @ Wv.T
+    return _trunk_backward(dy, caches, grads, num_layers=num_layers, rnn_cell=rnn_cell)
 
 
 # --------------------------------------------------------------------------------------
@@ -604,6 +693,8 @@ def train_step(params, slots, x, y, it, cfg, *, row0=0, batch_global=None, mask_
     Returns (new_params, mse_0, loss, grads_before_clip, grad_norm).
     """
     L = cfg['num_layers']
+    if cfg.get('uq', False):
+        return _train_step_uq(params, slots, x, y, it, cfg, row0=row0, lr=lr)
     preds, fc = forward(params, x, num_layers=L, dropout=cfg.get('dropout', 0.0),
                         recurrent_dropout=cfg.get('recurrent_dropout', 0.0),
                         training=cfg.get('train', True), seed=cfg.get('seed', 0), step=it, row0=row0,
@@ -625,3 +716,30 @@ def train_step(params, slots, x, y, it, cfg, *, row0=0, batch_global=None, mask_
     for l in range(L):
         new[5 * l] = max_norm_constraint(new[5 * l], cfg.get('max_norm', 3))
     return new, mse, loss, raw, gn
+
+
+
+def _train_step_uq(params, slots, x, y, it, cfg, *, row0=0, lr=None):
+    """Train._train_step_uq_range (train.py:201-225).  Returns (new_params, mse_0, uq_loss, grads_before_clip,
+    grad_norm, uq_loss_last_tar); the reference's step returns (uq_loss_last_tar, mse)."""
+    L = cfg['num_layers']
+    cell = cfg.get('rnn_cell', 'lstm')
+    pred, var, fc = forward_uq(params, x, num_layers=L, dropout=cfg.get('dropout', 0.0),
+                               recurrent_dropout=cfg.get('recurrent_dropout', 0.0), seed=cfg.get('seed', 0), step=it,
+                               row0=row0, rnn_cell=cell)
+    loss, uq0, mse, dpred, dvar = loss_uq_estimate(y.astype(pred.dtype), pred, var, target_idx=cfg['target_idx'],
+                                                   target_lambda=cfg['target_lambda'], rnn_lambda=cfg['rnn_lambda'])
+    grads = backward_uq(dpred, dvar, fc, num_layers=L, rnn_cell=cell)
+    raw = [g.copy() for g in grads]
+    gn = None
+    if cfg.get('max_grad_norm', 0.0) > 0:
+        grads, gn = clip_by_global_norm(grads, cfg['max_grad_norm'])
+    if lr is None:
+        keys = ('lr_schedule', 'learning_rate', 'lr_decay', 'decay_steps', 'end_learning_rate', 'decay_power',
+                'piecewise_lr_boundaries', 'piecewise_lr_values')
+        lr = learning_rate(it, **{k: cfg[k] for k in keys if k in cfg})
+    new = optimizer_update(cfg.get('optimizer', 'Adadelta'), params, grads, slots, lr, it,
+                           sgd_momentum=cfg.get('sgd_momentum', 0.0))
+    for l in range(L):
+        new[5 * l] = max_norm_constraint(new[5 * l], cfg.get('max_norm', 3))
+    return new, mse, loss, raw, gn, uq0

@@ -312,3 +312,68 @@ def test_gru_stack_finite_differences_with_dropout():
             Qm[k][idx] -= 1e-6
             fd = (loss_of(Qp)[0][0] - loss_of(Qm)[0][0]) / 2e-6
             assert abs(fd - g[k][idx]) < 1e-6 * max(1.0, abs(fd)), (k, idx)
+
+
+# ---- RNNUqRangeEstimate: rnn_uq_range_estimate.py:66-110, losses.py:180-284, train.py:201-225 ----
+def _uq_problem(seed=0, L=2):
+    B, T, F, O, H = 5, 6, 7, 3, 8
+    rng = np.random.RandomState(seed)
+    P = orc.init_params(L, F, O, H, seed=3, dtype=np.float64, uq=True)
+    P[-1] = rng.normal(size=O) * 0.5
+    P[-3] = rng.normal(size=O) * 0.5
+    return P, rng.normal(size=(B, T, F)), rng.normal(size=(B, T, O)), L, O
+
+
+def test_uq_loss_and_gradients_match_torch_autograd():
+    P, x, y, L, O = _uq_problem()
+    assert orc.param_names(L, uq=True)[-4:] == ['OUTPUT_TARGET_1/kernel', 'OUTPUT_TARGET_1/bias',
+                                                'OUTPUT_VARIANCE_1/kernel', 'OUTPUT_VARIANCE_1/bias']
+    p, v, _ = orc.forward_uq(P, x, num_layers=L, dropout=0.2, recurrent_dropout=0.1, seed=5, step=2, row0=10)
+    assert v.min() >= orc.VAR_FLOOR
+    loss, uq0, mse0, dp, dv = orc.loss_uq_estimate(y, p, v, target_idx=1, target_lambda=0.5, rnn_lambda=0.7)
+    tp, tv, ty = torch.tensor(p, requires_grad=True), torch.tensor(v, requires_grad=True), torch.tensor(y)
+    m = (~(ty == 0).all(-1)).double()
+    term = (tp * m[..., None] - ty) ** 2 / (tv * m[..., None]) + torch.log(tv * m[..., None])
+    t0 = term[:, -1, 1].sum() / m[:, -1].sum()
+    t1 = term[:, -1, :].sum() / (m[:, -1].sum() * O)
+    t2 = term.sum() / (m.sum() * O)
+    lt = 0.5 * t0 + 0.5 * (0.7 * t1 + 0.3 * t2)
+    lt.backward()
+    assert abs(lt.item() - loss) < 1e-12 and abs(t0.item() - uq0) < 1e-12
+    assert mse0 == pytest.approx(np.mean((y[:, -1, 1] - p[:, -1, 1]) ** 2), rel=1e-12)
+    assert np.abs(tp.grad.numpy() - dp).max() < 1e-12 and np.abs(tv.grad.numpy() - dv).max() < 1e-12
+
+
+def test_uq_stack_finite_differences_and_dropout_is_always_on():
+    P, x, y, L, O = _uq_problem(seed=1)
+    kw = dict(num_layers=L, dropout=0.3, recurrent_dropout=0.2, seed=5, step=2, row0=10)
+
+    def loss_of(Q):
+        p, v, fc = orc.forward_uq(Q, x, **kw)
+        return orc.loss_uq_estimate(y, p, v, target_idx=1, target_lambda=0.5, rnn_lambda=0.7), fc
+
+    (l0, _, _, dp, dv), fc = loss_of(P)
+    g = orc.backward_uq(dp, dv, fc, num_layers=L)
+    rng = np.random.RandomState(3)
+    for k in range(len(P)):
+        for _ in range(4):
+            idx = tuple(rng.randint(s) for s in P[k].shape)
+            Qp, Qm = [q.copy() for q in P], [q.copy() for q in P]
+            Qp[k][idx] += 1e-6
+            Qm[k][idx] -= 1e-6
+            fd = (loss_of(Qp)[0][0] - loss_of(Qm)[0][0]) / 2e-6
+            assert abs(fd - g[k][idx]) < 1e-6 * max(1.0, abs(fd)), (k, idx)
+    # training=True is a literal in the reference's UQ model: a different step draws different masks
+    p_a = orc.forward_uq(P, x, **kw)[0]
+    p_b = orc.forward_uq(P, x, **dict(kw, step=3))[0]
+    assert np.abs(p_a - p_b).max() > 1e-3
+
+
+def test_uq_loss_is_nan_with_a_padded_step_like_the_reference_formula():
+    """losses.py:200-201 multiplies the variance by the mask, :272 divides by it and takes its log."""
+    P, x, y, L, O = _uq_problem(seed=2)
+    p, v, _ = orc.forward_uq(P, x, num_layers=L)
+    y[0, :2] = 0.0
+    loss, uq0, mse0, dp, dv = orc.loss_uq_estimate(y, p, v, target_idx=1, target_lambda=0.5, rnn_lambda=0.7)
+    assert np.isnan(loss) and np.isfinite(uq0) and np.isfinite(mse0)
+    assert np.isnan(dp[0, 0]).all() and np.isnan(dv[0, 0]).all()
