@@ -54,7 +54,9 @@ typedef struct lfmq_config {
   int32_t optimizer;         /* LFMQ_OPT_*                   (optimizers.py:21-27) */
   int32_t forward_only;      /* 1: no backward workspace (predict.py) */
   int32_t rnn_cell;          /* LFMQ_CELL_*: config.rnn_cell 'lstm' | 'gru' (rnn_point_estimate.py:80,90) */
-  int32_t reserved0;         /* must be 0 (keeps the float block 8-byte aligned without implicit padding) */
+  int32_t uq;                /* config.UQ: 0 = RNNPointEstimate, 1 = RNNUqRangeEstimate (model_utils/model.py:25-33):
+                              * target + variance heads, Gaussian-NLL loss, dropout always active
+                              * (rnn_uq_range_estimate.py:86,88,104-108).  fp32 path, single GPU. */
   float dropout;             /* lfm_quant.py:61 */
   float recurrent_dropout;   /* lfm_quant.py:62 */
   float target_lambda;       /* lfm_quant.py:69 */
@@ -83,13 +85,14 @@ int32_t lfmq_destroy(lfmq_handle h);
 
 /* model.trainable_variables / model.weights (train.py:192,198): tensors are listed in Keras order,
  * trainable ones first: per layer lstm_l/{kernel,recurrent_kernel,bias} (gru_l/... with bias [2][3H] for LFMQ_CELL_GRU), batch_normalization[_k]/{gamma,beta};
- * OUTPUT_1/{kernel,bias}; then per layer batch_normalization[_k]/{moving_mean,moving_variance}. */
+ * OUTPUT_1/{kernel,bias} (uq: OUTPUT_TARGET_1/{kernel,bias}, OUTPUT_VARIANCE_1/{kernel,bias}); then per layer batch_normalization[_k]/{moving_mean,moving_variance}. */
 int32_t lfmq_param_count(lfmq_handle h, int32_t* n_tensors, int64_t* n_trainable_elems, int64_t* n_total_elems);
 int32_t lfmq_param_spec(lfmq_handle h, int32_t index, char* name, int32_t name_cap, int32_t* ndim,
                         int64_t shape[2], int64_t* offset_elems, int32_t* trainable);
 /* Device pointers into the workspace: flat fp32 parameters [n_total]; flat gradients
- * [n_trainable + 4] whose tail holds {loss, mse_0} contributions of the last lfmq_backward and
- * {grad_norm, clip_scale} of the last lfmq_apply; optimizer slots [n_slots * n_trainable]. */
+ * [n_trainable + 8] whose tail holds {loss, mse_0} contributions of the last lfmq_backward,
+ * {grad_norm, clip_scale} of the last lfmq_apply and, on a uq handle, [4] = uq_loss_last_tar (tail[0] is then the
+ * weighted uq loss); optimizer slots [n_slots * n_trainable]. */
 int32_t lfmq_params_ptr(lfmq_handle h, float** dev);
 int32_t lfmq_grads_ptr(lfmq_handle h, float** dev);
 int32_t lfmq_opt_state_ptr(lfmq_handle h, float** dev, int64_t* n_elems);
@@ -102,10 +105,19 @@ int32_t lfmq_get_params(lfmq_handle h, float* host, int64_t n_elems, void* strea
  * Dropout is active iff cfg.train (rnn_point_estimate.py:87,89); `step` and `row0` (global index of
  * the first row of this shard) key the dropout streams so masks are independent of the GPU count. */
 int32_t lfmq_forward(lfmq_handle h, const float* x, int32_t B, int64_t row0, int64_t step, float* preds, void* stream);
+/* model(inp) / model.predict(inp) of RNNUqRangeEstimate (train.py:204-206, predict.py:135-138): preds[0] -> preds,
+ * preds[1] -> var, both [B,T,O].  Dropout masks are drawn for (step, row0) on every call, also with train = 0
+ * (rnn_uq_range_estimate.py:86,88 pass training=True literally).  uq handles only; lfmq_forward refuses them. */
+int32_t lfmq_forward_uq(lfmq_handle h, const float* x, int32_t B, int64_t row0, int64_t step, float* preds, float* var,
+                        void* stream);
 
 /* Losses.weight_adjusted_mse([y],[pred]) (model_utils/losses.py:19-135), RNN branch, forecast_steps=1.
  * out_dev[0] = loss, out_dev[1] = mse_0 (device floats).  Used for validation (train.py:329). */
 int32_t lfmq_loss(lfmq_handle h, const float* preds, const float* y, int32_t B, float* out_dev, void* stream);
+/* Losses.weight_adjusted_uq_loss([y],[pred],[var]) (model_utils/losses.py:137-284), RNN branch, forecast_steps=1.
+ * out_dev = {uq_loss, uq_loss_last_tar, mse_0}.  A zero-padded step makes uq_loss NaN, as the reference's formula does. */
+int32_t lfmq_loss_uq(lfmq_handle h, const float* preds, const float* var, const float* y, int32_t B, float* out_dev,
+                     void* stream);
 
 /* Number of unmasked [b,t] rows of y (losses.py:72-73,132): out_dev[0] = B, out_dev[1] = sum(mask).
  * Under data parallelism the host all-reduces these two floats once per batch and passes the result
@@ -123,7 +135,8 @@ int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, 
  * `iteration` = optimizer.iterations before this update. */
 int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream);
 
-/* Whole step for one GPU: lfmq_backward + lfmq_apply.  loss_out_dev (may be NULL) receives {loss, mse_0}. */
+/* Whole step for one GPU: lfmq_backward + lfmq_apply.  loss_out_dev (may be NULL) receives {loss, mse_0}; on a uq
+ * handle {uq_loss_last_tar, mse_0}, the pair Train._train_step_uq_range returns (train.py:225). */
 int32_t lfmq_train_step(lfmq_handle h, const float* x, const float* y, int32_t B, int64_t row0, int64_t step,
                         float lr, float* loss_out_dev, void* stream);
 

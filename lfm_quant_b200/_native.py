@@ -20,7 +20,7 @@ class LfmqConfig(C.Structure):
                 ('n_inputs', C.c_int32), ('n_outputs', C.c_int32), ('num_hidden', C.c_int32),
                 ('num_layers', C.c_int32), ('target_idx', C.c_int32), ('train', C.c_int32),
                 ('precision', C.c_int32), ('optimizer', C.c_int32), ('forward_only', C.c_int32),
-                ('rnn_cell', C.c_int32), ('reserved0', C.c_int32),
+                ('rnn_cell', C.c_int32), ('uq', C.c_int32),
                 ('dropout', C.c_float), ('recurrent_dropout', C.c_float), ('target_lambda', C.c_float),
                 ('rnn_lambda', C.c_float), ('max_grad_norm', C.c_float), ('max_norm', C.c_float),
                 ('sgd_momentum', C.c_float), ('bn_epsilon', C.c_float), ('seed', C.c_uint64)]
@@ -53,7 +53,9 @@ SYMBOLS = {
     'lfmq_set_params': (C.c_int32, [_P, _P, C.c_int64, _P]),
     'lfmq_get_params': (C.c_int32, [_P, _P, C.c_int64, _P]),
     'lfmq_forward': (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    'lfmq_forward_uq': (C.c_int32, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),
     'lfmq_loss': (C.c_int32, [_P, _P, _P, C.c_int32, _P, _P]),
+    'lfmq_loss_uq': (C.c_int32, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     'lfmq_mask_count': (C.c_int32, [_P, _P, C.c_int32, _P, _P]),
     'lfmq_backward': (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     'lfmq_apply': (C.c_int32, [_P, C.c_float, C.c_int64, _P]),

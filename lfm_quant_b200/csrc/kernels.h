@@ -29,6 +29,10 @@ int bn_dropout_bwd(cudaStream_t s, int B, int T, int H, const float* dy, const f
                    float* dh_out, float* dgamma, float* dbeta, float* scratch, size_t scratch_elems);
 int add_bias_rows(cudaStream_t s, long rows, int N, float* C, const float* bias);
 int colsum(cudaStream_t s, long rows, int N, const float* A, float* out, float* scratch, size_t scratch_elems);
+int softplus_floor(cudaStream_t s, long n, const float* a, float* var);
+int uq_loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const float* var, const float* apre,
+                 const float* y, const float* counts_in, int target_idx, float p1, float p2, float* dpred, float* da,
+                 float* out_loss, float* out_uq0, float* out_mse0, float* counts_out, float* scratch);
 int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, unsigned int* tickets);
 // out2 = {loss, mse_0}; maskout2 (nullable) = {B, mask_count_local}; dpred may be NULL (validation);
 // denom (nullable) = device {B_global, mask_count_global}.

@@ -557,6 +557,117 @@ __global__ void loss_final_kernel(int nblk, const double* __restrict__ partial, 
   out[1] = (float)mse0;
 }
 
+// =============================================================================================
+// RNNUqRangeEstimate head and loss (rnn_uq_range_estimate.py:104-108, model_utils/custom_layers.py:12-13,
+// model_utils/losses.py:180-284).
+// =============================================================================================
+__device__ __forceinline__ float softplus_f(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
+
+// var = max(softplus(a), 1e-6); in place when var == a
+__global__ void softplus_floor_kernel(long n, const float* __restrict__ a, float* __restrict__ var) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) var[i] = fmaxf(softplus_f(a[i]), 1e-6f);
+}
+
+int softplus_floor(cudaStream_t s, long n, const float* a, float* var) {
+  softplus_floor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, a, var);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// One thread per [b,t] row.  Per element (losses.py:197-201,268-273): pm = p*m, vm = v*m, term = (pm-y)^2 * (1/vm) +
+// log(vm) in fp32 exactly as written there -- a masked row gives 0*inf + log 0 = NaN, as in the reference; sums are
+// carried in fp64.  pred == nullptr: only the two mask counts.  dpred != nullptr: gradients w.r.t. pred and w.r.t. the
+// variance head's pre-activation `apre` (tf.maximum passes the gradient to softplus above the floor), using the counts
+// of a previous pass.
+__global__ void __launch_bounds__(256) uq_loss_rows_kernel(int B, int T, int O, const float* __restrict__ pred,
+                                                           const float* __restrict__ var,
+                                                           const float* __restrict__ apre,
+                                                           const float* __restrict__ y,
+                                                           const float* __restrict__ counts, int target_idx, float p1,
+                                                           float p2, float* __restrict__ dpred,
+                                                           float* __restrict__ da, double* __restrict__ partial) {
+  double acc[4] = {0, 0, 0, 0};   // uq_0, uq_1, uq_2 numerators, mse_0 numerator
+  double cnt[4] = {0, 0, 0, 0};   // unmasked rows, unmasked last-step rows
+  float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
+  if (dpred) {
+    const float ms_all = counts[0], ms_last = counts[1];
+    c_all = (1.f - p1) * (1.f - p2) / (ms_all * (float)O);
+    c_last = (1.f - p1) * p2 / (ms_last * (float)O);
+    c_tar = p1 / ms_last;
+  }
+  const long rows = (long)B * T;
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long)gridDim.x * blockDim.x) {
+    const float* yr = y + r * O;
+    bool any = false;
+    for (int k = 0; k < O; ++k) any |= (yr[k] != 0.0f);
+    const float m = any ? 1.f : 0.f;
+    const bool last = ((int)(r % T) == T - 1);
+    cnt[0] += m;
+    if (last) cnt[1] += m;
+    if (!pred) continue;
+    for (int k = 0; k < O; ++k) {
+      const float pm = pred[r * O + k] * m, vm = var[r * O + k] * m;
+      const float d = pm - yr[k];
+      const float diff = d * d;
+      const float term = diff * (1.f / vm) + logf(vm);
+      acc[2] += term;
+      float coef = c_all;
+      if (last) {
+        acc[1] += term;
+        coef += c_last;
+        if (k == target_idx) { acc[0] += term; acc[3] += diff; coef += c_tar; }
+      }
+      if (dpred) {
+        dpred[r * O + k] = coef * (2.f * d / vm) * m;
+        const float dv = coef * (-diff / (vm * vm) + 1.f / vm) * m;
+        const float a = apre[r * O + k];
+        da[r * O + k] = dv * ((softplus_f(a) > 1e-6f) ? sigmoid_f(a) : 0.f);
+      }
+    }
+  }
+  block_reduce4(acc, partial + (long)blockIdx.x * 8);
+  __syncthreads();
+  block_reduce4(cnt, partial + (long)blockIdx.x * 8 + 4);
+}
+
+__global__ void uq_loss_final_kernel(int nblk, const double* __restrict__ partial, const float* __restrict__ counts_in,
+                                     int B, int O, float p1, float p2, float* __restrict__ out_loss,
+                                     float* __restrict__ out_uq0, float* __restrict__ out_mse0,
+                                     float* __restrict__ counts_out) {
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblk; b += 32)
+    for (int i = 0; i < 8; ++i) s[i] += partial[(long)b * 8 + i];
+  for (int i = 0; i < 8; ++i) s[i] = warp_sum(s[i]);
+  if (threadIdx.x != 0) return;
+  if (counts_out) {
+    counts_out[0] = (float)s[4];
+    counts_out[1] = (float)s[5];
+  }
+  if (!out_loss) return;
+  const double ms_all = counts_in ? (double)counts_in[0] : s[4];
+  const double ms_last = counts_in ? (double)counts_in[1] : s[5];
+  const double uq0 = s[0] / ms_last, uq1 = s[1] / (ms_last * O), uq2 = s[2] / (ms_all * O);
+  *out_loss = (float)(p1 * uq0 + (1.0 - p1) * (p2 * uq1 + (1.0 - p2) * uq2));
+  *out_uq0 = (float)uq0;
+  *out_mse0 = (float)(s[3] / (double)B);
+}
+
+// pred == nullptr: counts only -> counts_out.  Otherwise the three scalars; with dpred also the gradients (counts_in
+// from a counts-only pass is then required).
+int uq_loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const float* var, const float* apre,
+                 const float* y, const float* counts_in, int target_idx, float p1, float p2, float* dpred, float* da,
+                 float* out_loss, float* out_uq0, float* out_mse0, float* counts_out, float* scratch) {
+  double* partial = reinterpret_cast<double*>(scratch);
+  uq_loss_rows_kernel<<<LOSS_BLOCKS, 256, 0, s>>>(B, T, O, pred, var, apre, y, counts_in, target_idx, p1, p2, dpred, da,
+                                                  partial);
+  LFMQ_LAUNCH_CHECK();
+  uq_loss_final_kernel<<<1, 32, 0, s>>>(LOSS_BLOCKS, partial, counts_in, B, O, p1, p2, out_loss, out_uq0, out_mse0,
+                                        counts_out);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
 // mask count (losses.py:72-73,132): one thread per [b,t] row, warp ballot, one integer atomic per warp
 // (integer adds commute: the count is exact and deterministic).  The last block to finish (ticket) writes
 // {B, count} and resets both counters, so the whole count is one launch and needs no memset.

@@ -37,11 +37,13 @@ struct lfmq_handle_s {
   int64_t n_train, n_total, n_grad_buf;
   int n_slots;
   int64_t oWo, obo;
+  int64_t oWv, obv;          // uq: OUTPUT_VARIANCE_1 (oWo/obo are OUTPUT_TARGET_1 then)
   // workspace carve
   float *params, *grads, *slots, *scalars, *denom;
   unsigned int* tickets;
   std::vector<LayerBuf> layers;
   float *z, *hm, *dz, *dy, *dh_out, *hp, *dh_rec, *dc, *dpred, *preds, *scratch;
+  float *var, *apre, *da;   // uq only: variance output, its pre-activation, gradient w.r.t. the pre-activation
   float *zh, *dz2;   // GRU only: recurrent projection of one step, gradient w.r.t. the recurrent projection
   size_t scratch_elems;
   lfmq::TcState tc;
@@ -90,9 +92,9 @@ int validate(const lfmq_config* c) {
     LFMQ_SET_ERR("lfmq_config: dropout rates must be in [0,1)");
     return LFMQ_ERR_ARG;
   }
-  if ((c->rnn_cell != LFMQ_CELL_LSTM && c->rnn_cell != LFMQ_CELL_GRU) || c->reserved0 != 0) {
-    LFMQ_SET_ERR("lfmq_config: rnn_cell must be LFMQ_CELL_LSTM or LFMQ_CELL_GRU and reserved0 zero (got %d, %d)", c->rnn_cell,
-                 c->reserved0);
+  if ((c->rnn_cell != LFMQ_CELL_LSTM && c->rnn_cell != LFMQ_CELL_GRU) || (c->uq != 0 && c->uq != 1)) {
+    LFMQ_SET_ERR("lfmq_config: rnn_cell must be LFMQ_CELL_LSTM or LFMQ_CELL_GRU and uq 0 or 1 (got %d, %d)", c->rnn_cell,
+                 c->uq);
     return LFMQ_ERR_ARG;
   }
   if (c->precision != LFMQ_PREC_FP32 && c->precision != LFMQ_PREC_BF16) {
@@ -129,8 +131,16 @@ size_t layout(lfmq_handle_s* h, char* base) {
     lb.ogamma = add(bn + "/gamma", 1, H, 1, 1);
     lb.obeta = add(bn + "/beta", 1, H, 1, 1);
   }
-  h->oWo = add("OUTPUT_1/kernel", 2, H, O, 1);
-  h->obo = add("OUTPUT_1/bias", 1, O, 1, 1);
+  if (c.uq) {
+    h->oWo = add("OUTPUT_TARGET_1/kernel", 2, H, O, 1);
+    h->obo = add("OUTPUT_TARGET_1/bias", 1, O, 1, 1);
+    h->oWv = add("OUTPUT_VARIANCE_1/kernel", 2, H, O, 1);
+    h->obv = add("OUTPUT_VARIANCE_1/bias", 1, O, 1, 1);
+  } else {
+    h->oWo = add("OUTPUT_1/kernel", 2, H, O, 1);
+    h->obo = add("OUTPUT_1/bias", 1, O, 1, 1);
+    h->oWv = h->obv = -1;
+  }
   h->n_train = off;
   for (int l = 0; l < L; ++l) {
     const std::string bn = (l == 0) ? "batch_normalization" : "batch_normalization_" + std::to_string(l);
@@ -138,7 +148,7 @@ size_t layout(lfmq_handle_s* h, char* base) {
     h->layers[l].ovar = add(bn + "/moving_variance", 1, H, 1, 0);
   }
   h->n_total = off;
-  h->n_grad_buf = (h->n_train + 4 + 3) / 4 * 4;
+  h->n_grad_buf = (h->n_train + 8 + 3) / 4 * 4;
   h->n_slots = (c.optimizer == LFMQ_OPT_ADADELTA || c.optimizer == LFMQ_OPT_ADAM) ? 2 : 1;
 
   Carver cv{base, 0};
@@ -162,6 +172,8 @@ size_t layout(lfmq_handle_s* h, char* base) {
   h->zh = (c.rnn_cell == LFMQ_CELL_GRU) ? cv.take<float>(B * 3 * H) : nullptr;
   h->hm = cv.take<float>(B * H);
   h->preds = cv.take<float>(BT * O);
+  h->var = c.uq ? cv.take<float>(BT * O) : nullptr;
+  h->apre = (c.uq && !c.forward_only) ? cv.take<float>(BT * O) : nullptr;
   size_t scratch = (size_t)4 << 20;
   if (!c.forward_only) {
     h->dz = cv.take<float>(BT * 4 * H);
@@ -172,10 +184,11 @@ size_t layout(lfmq_handle_s* h, char* base) {
     h->dh_rec = cv.take<float>(B * H);
     h->dc = cv.take<float>(B * H);
     h->dpred = cv.take<float>(BT * O);
+    h->da = c.uq ? cv.take<float>(BT * O) : nullptr;
     const size_t bn_need = ((BT + 127) / 128) * 2 * H + (size_t)1024 * 2 * H;
     if (bn_need > scratch) scratch = bn_need;
   } else {
-    h->dz = h->dz2 = h->dy = h->dh_out = h->hp = h->dh_rec = h->dc = h->dpred = nullptr;
+    h->dz = h->dz2 = h->dy = h->dh_out = h->hp = h->dh_rec = h->dc = h->dpred = h->da = nullptr;
   }
   h->scratch_elems = scratch;
   h->scratch = cv.take<float>(scratch);
@@ -213,7 +226,9 @@ int check_batch(lfmq_handle h, int32_t B) {
 }
 
 // fp32 SIMT forward of all layers; fills layers[l].{h,c,y,(gates)} and `preds`.
-int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t step, float* preds, cudaStream_t s) {
+// uq handles also fill `var` [B,T,O] (and keep the variance head's pre-activation when a backward pass can follow).
+int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t step, float* preds, float* var,
+                 cudaStream_t s) {
   const lfmq_config& c = h->cfg;
   const int H = c.num_hidden, T = c.seq_len, O = c.n_outputs, L = c.num_layers;
   const float* P = h->params;
@@ -223,7 +238,8 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
     const float* in = (l == 0) ? x : h->layers[l - 1].y;
     const int I = lb.I;
     const float* rmask = nullptr;
-    if (c.train && c.recurrent_dropout > 0.f) {
+    const bool stochastic = c.train || c.uq;       // rnn_uq_range_estimate.py:86,88: training=True is a literal there
+    if (stochastic && c.recurrent_dropout > 0.f) {
       RUN(gen_row_mask(s, B, H, make_key(c, 2 * l + 1, step, c.recurrent_dropout), row0, lb.rmask));
       rmask = lb.rmask;
     }
@@ -246,7 +262,7 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
       }
       RUN(lstm_pointwise_fwd(s, B, T, H, t, h->z, P + lb.ob, lb.gates, lb.c, lb.h, rmask, rmask ? h->hm : nullptr));
     }
-    const bool drop = c.train && c.dropout > 0.f;
+    const bool drop = stochastic && c.dropout > 0.f;
     RUN(bn_dropout_fwd(s, B, T, H, lb.h, P + lb.ogamma, P + lb.obeta, P + lb.omean, P + lb.ovar, c.bn_epsilon, drop,
                        make_key(c, 2 * l, step, c.dropout), row0, lb.y));
   }
@@ -255,6 +271,12 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
   const float* yl = h->layers[L - 1].y;
   RUN(sgemm(s, B * T, O, H, yl, H, 1, P + h->oWo, O, 1, preds, O, 0.f, nullptr, 0));
   RUN(add_bias_rows(s, (long)B * T, O, preds, P + h->obo));
+  if (c.uq) {
+    float* a = h->apre ? h->apre : var;           // forward-only handles activate in place
+    RUN(sgemm(s, B * T, O, H, yl, H, 1, P + h->oWv, O, 1, a, O, 0.f, nullptr, 0));
+    RUN(add_bias_rows(s, (long)B * T, O, a, P + h->obv));
+    RUN(softplus_floor(s, (long)B * T * O, a, var));
+  }
   h->prof.end(LFMQ_REGION_HEAD, s);
   return 0;
 }
@@ -271,12 +293,17 @@ int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
   RUN(sgemm(s, H, O, (int)BT, yl, 1, H, h->dpred, O, 1, G + h->oWo, O, 0.f, h->scratch, h->scratch_elems));
   RUN(colsum(s, BT, O, h->dpred, G + h->obo, h->scratch, h->scratch_elems));
   RUN(sgemm(s, (int)BT, H, O, h->dpred, O, 1, P + h->oWo, 1, O, h->dy, H, 0.f, nullptr, 0));
+  if (c.uq) {      // variance head: same three products on da, dy accumulates
+    RUN(sgemm(s, H, O, (int)BT, yl, 1, H, h->da, O, 1, G + h->oWv, O, 0.f, h->scratch, h->scratch_elems));
+    RUN(colsum(s, BT, O, h->da, G + h->obv, h->scratch, h->scratch_elems));
+    RUN(sgemm(s, (int)BT, H, O, h->da, O, 1, P + h->oWv, 1, O, h->dy, H, 1.f, nullptr, 0));
+  }
   h->prof.end(LFMQ_REGION_HEAD, s);
   for (int l = L - 1; l >= 0; --l) {
     LayerBuf& lb = h->layers[l];
     const int I = lb.I;
-    const float* rmask = (c.train && c.recurrent_dropout > 0.f) ? lb.rmask : nullptr;
-    const bool drop = c.train && c.dropout > 0.f;
+    const float* rmask = ((c.train || c.uq) && c.recurrent_dropout > 0.f) ? lb.rmask : nullptr;
+    const bool drop = (c.train || c.uq) && c.dropout > 0.f;
     h->prof.begin(LFMQ_REGION_BWD, s);
     RUN(bn_dropout_bwd(s, B, T, H, h->dy, lb.h, P + lb.ogamma, P + lb.omean, P + lb.ovar, c.bn_epsilon, drop,
                        make_key(c, 2 * l, h->tc.last_step, c.dropout), h->tc.last_row0, h->dh_out, G + lb.ogamma,
@@ -479,9 +506,29 @@ int32_t lfmq_forward(lfmq_handle h, const float* x, int32_t B, int64_t row0, int
   cudaStream_t s = (cudaStream_t)stream;
   h->tc.last_step = step;
   h->tc.last_row0 = row0;
+  if (h->cfg.uq) {
+    LFMQ_SET_ERR("lfmq_forward: uq handle, call lfmq_forward_uq");
+    return LFMQ_ERR_ARG;
+  }
   if (h->cfg.precision == LFMQ_PREC_BF16)
     return lfmq::tc_forward(h->tc, h->cfg, h->params, x, B, row0, step, preds, /*save=*/false, s);
-  return forward_fp32(h, x, B, row0, step, preds, s);
+  return forward_fp32(h, x, B, row0, step, preds, nullptr, s);
+}
+
+int32_t lfmq_forward_uq(lfmq_handle h, const float* x, int32_t B, int64_t row0, int64_t step, float* preds, float* var,
+                        void* stream) {
+  RUN(check_batch(h, B));
+  if (!x || !preds || !var) {
+    LFMQ_SET_ERR("lfmq_forward_uq: null pointer");
+    return LFMQ_ERR_ARG;
+  }
+  if (!h->cfg.uq) {
+    LFMQ_SET_ERR("lfmq_forward_uq: handle was created with uq = 0");
+    return LFMQ_ERR_ARG;
+  }
+  h->tc.last_step = step;
+  h->tc.last_row0 = row0;
+  return forward_fp32(h, x, B, row0, step, preds, var, (cudaStream_t)stream);
 }
 
 int32_t lfmq_loss(lfmq_handle h, const float* preds, const float* y, int32_t B, float* out_dev, void* stream) {
@@ -497,6 +544,18 @@ int32_t lfmq_loss(lfmq_handle h, const float* preds, const float* y, int32_t B, 
   const lfmq_config& c = h->cfg;
   return loss_grad((cudaStream_t)stream, B, c.seq_len, c.n_outputs, preds, y, nullptr, c.target_idx, c.target_lambda,
                    c.rnn_lambda, nullptr, out_dev, nullptr, h->scratch);
+}
+
+int32_t lfmq_loss_uq(lfmq_handle h, const float* preds, const float* var, const float* y, int32_t B, float* out_dev,
+                     void* stream) {
+  if (!h || B <= 0 || !preds || !var || !y || !out_dev) {
+    LFMQ_SET_ERR("lfmq_loss_uq: bad handle, batch %d or null pointer", B);
+    return LFMQ_ERR_ARG;
+  }
+  const lfmq_config& c = h->cfg;
+  return uq_loss_grad((cudaStream_t)stream, B, c.seq_len, c.n_outputs, preds, var, nullptr, y, nullptr, c.target_idx,
+                      c.target_lambda, c.rnn_lambda, nullptr, nullptr, out_dev, out_dev + 1, out_dev + 2, nullptr,
+                      h->scratch);
 }
 
 int32_t lfmq_mask_count(lfmq_handle h, const float* y, int32_t B, float* out_dev, void* stream) {
@@ -523,6 +582,19 @@ int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, 
   const lfmq_config& c = h->cfg;
   h->tc.last_step = step;
   h->tc.last_row0 = row0;
+  if (c.uq) {
+    if (denom_dev) {
+      LFMQ_SET_ERR("lfmq_backward: data-parallel denominators are not built for uq handles");
+      return LFMQ_ERR_UNSUPPORTED;
+    }
+    float* t = h->grads + h->n_train;
+    RUN(forward_fp32(h, x, B, row0, step, h->preds, h->var, s));
+    RUN(uq_loss_grad(s, B, c.seq_len, c.n_outputs, nullptr, nullptr, nullptr, y, nullptr, c.target_idx, c.target_lambda,
+                     c.rnn_lambda, nullptr, nullptr, nullptr, nullptr, nullptr, h->denom, h->scratch));
+    RUN(uq_loss_grad(s, B, c.seq_len, c.n_outputs, h->preds, h->var, h->apre, y, h->denom, c.target_idx, c.target_lambda,
+                     c.rnn_lambda, h->dpred, h->da, t, t + 4, t + 1, nullptr, h->scratch));
+    return backward_fp32(h, x, B, s);
+  }
   const float* denom = denom_dev;
   if (!denom) {
     RUN(mask_count(s, B, c.seq_len, c.n_outputs, y, h->denom, h->tickets));
@@ -531,7 +603,7 @@ int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, 
   float* tail = h->grads + h->n_train;
   if (c.precision == LFMQ_PREC_BF16)
     return lfmq::tc_backward(h->tc, c, h->params, h->grads, x, y, B, row0, step, denom, tail, s);
-  RUN(forward_fp32(h, x, B, row0, step, h->preds, s));
+  RUN(forward_fp32(h, x, B, row0, step, h->preds, nullptr, s));
   RUN(loss_grad(s, B, c.seq_len, c.n_outputs, h->preds, y, denom, c.target_idx, c.target_lambda, c.rnn_lambda,
                 h->dpred, tail, nullptr, h->scratch));
   return backward_fp32(h, x, B, s);
@@ -566,9 +638,15 @@ int32_t lfmq_train_step(lfmq_handle h, const float* x, const float* y, int32_t B
                         float* loss_out_dev, void* stream) {
   RUN(lfmq_backward(h, x, y, B, row0, step, nullptr, stream));
   RUN(lfmq_apply(h, lr, step, stream));
-  if (loss_out_dev)
+  if (loss_out_dev && !h->cfg.uq)
     LFMQ_CUDA_CHECK(cudaMemcpyAsync(loss_out_dev, h->grads + h->n_train, 2 * sizeof(float), cudaMemcpyDeviceToDevice,
                                     (cudaStream_t)stream));
+  if (loss_out_dev && h->cfg.uq) {      // {uq_loss_last_tar, mse_0}
+    LFMQ_CUDA_CHECK(cudaMemcpyAsync(loss_out_dev, h->grads + h->n_train + 4, sizeof(float), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+    LFMQ_CUDA_CHECK(cudaMemcpyAsync(loss_out_dev + 1, h->grads + h->n_train + 1, sizeof(float), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+  }
   return LFMQ_OK;
 }
 

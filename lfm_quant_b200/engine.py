@@ -32,7 +32,7 @@ class ForecasterEngine(object):
     def __init__(self, *, max_batch, seq_len, n_inputs, n_outputs, num_hidden, num_layers=1, target_idx=0,
                  train=True, precision='fp32', optimizer='Adadelta', dropout=0.0, recurrent_dropout=0.0,
                  target_lambda=0.5, rnn_lambda=0.7, max_grad_norm=50.0, max_norm=3.0, sgd_momentum=0.0,
-                 seed=521, forward_only=False, device=None, rnn_cell='lstm'):
+                 seed=521, forward_only=False, device=None, rnn_cell='lstm', uq=False):
         if not torch.cuda.is_available():
             raise N.LfmqError('ForecasterEngine needs a CUDA device (no CPU fallback)')
         self.lib = N.load()
@@ -50,6 +50,8 @@ class ForecasterEngine(object):
         if rnn_cell not in N.CELLS:
             raise NotImplementedError('rnn_cell=%s (rnn_point_estimate.py:80-102 knows lstm and gru)' % rnn_cell)
         cfg.rnn_cell = N.CELLS[rnn_cell]
+        cfg.uq = 1 if uq else 0
+        self.uq = bool(uq)
         cfg.dropout, cfg.recurrent_dropout = dropout, recurrent_dropout
         cfg.target_lambda, cfg.rnn_lambda = target_lambda, rnn_lambda
         cfg.max_grad_norm, cfg.max_norm, cfg.sgd_momentum = max_grad_norm, max_norm, sgd_momentum
@@ -77,7 +79,7 @@ class ForecasterEngine(object):
             shp = (shape[0], shape[1]) if ndim.value == 2 else (shape[0],)
             self.specs.append((name.value.decode(), shp, off.value, bool(tr.value)))
         self.params = self._view('lfmq_params_ptr', self.n_total)
-        self.grads = self._view('lfmq_grads_ptr', self.n_trainable + 4)
+        self.grads = self._view('lfmq_grads_ptr', self.n_trainable + 8)   # tail: loss, mse_0, grad_norm, clip_scale, uq_loss_last_tar
         self._denom = torch.zeros(2, dtype=torch.float32, device=self.device)
 
     def _view(self, fn, n):
@@ -148,7 +150,13 @@ class ForecasterEngine(object):
         return x.shape[0]
 
     def forward(self, x, step=0, row0=0, out=None):
+        """preds [B,T,O]; on a uq engine the pair (preds, variance) -- model(inp)[0], model(inp)[1] of RNNUqRangeEstimate."""
         B = self._check_x(x)
+        if self.uq:
+            preds = torch.empty(B, self.T, self.O, dtype=torch.float32, device=x.device)
+            var = torch.empty_like(preds)
+            N.check(self.lib.lfmq_forward_uq(self.handle, _ptr(x), B, row0, step, _ptr(preds), _ptr(var), _stream()))
+            return preds, var
         if out is None:
             out = torch.empty(B, self.T, self.O, dtype=torch.float32, device=x.device)
         N.check(self.lib.lfmq_forward(self.handle, _ptr(x), B, row0, step, _ptr(out), _stream()))
@@ -158,6 +166,13 @@ class ForecasterEngine(object):
         out = torch.empty(2, dtype=torch.float32, device=preds.device)
         N.check(self.lib.lfmq_loss(self.handle, _ptr(preds.contiguous()), _ptr(y.contiguous()), preds.shape[0],
                                    _ptr(out), _stream()))
+        return out
+
+    def loss_uq(self, preds, var, y):
+        """Device tensor {uq_loss, uq_loss_last_tar, mse_0} (Losses.weight_adjusted_uq_loss, losses.py:137-284)."""
+        out = torch.empty(3, dtype=torch.float32, device=preds.device)
+        N.check(self.lib.lfmq_loss_uq(self.handle, _ptr(preds.contiguous()), _ptr(var.contiguous()), _ptr(y.contiguous()),
+                                      preds.shape[0], _ptr(out), _stream()))
         return out
 
     def mask_count(self, y):
@@ -174,7 +189,8 @@ class ForecasterEngine(object):
         N.check(self.lib.lfmq_apply(self.handle, float(lr), int(iteration), _stream()))
 
     def train_step(self, x, y, step, lr, out=None):
-        """One Train._train_step_point on this GPU; returns a device tensor {loss, mse_0} (no host sync)."""
+        """One Train._train_step_point on this GPU; returns a device tensor {loss, mse_0} (no host sync).
+        uq engine: one Train._train_step_uq_range, {uq_loss_last_tar, mse_0} (train.py:225)."""
         B = self._check_x(x)
         if out is None:
             out = torch.empty(2, dtype=torch.float32, device=x.device)

@@ -315,3 +315,89 @@ def test_gru_is_refused_loudly_on_the_bf16_path():
     from lfm_quant_b200 import _native as N
     with pytest.raises(N.LfmqError, match='LSTM cell only'):
         make_engine(256, 8, 32, 16, 256, 1, precision='bf16', rnn_cell='gru')
+
+
+# ---- RNNUqRangeEstimate through the C ABI (cfg.uq = 1) ----
+def _uq_problem(B, T, F, O, H, L, seed, rnn_cell='lstm'):
+    rng = np.random.RandomState(seed)
+    params = orc.init_params(L, F, O, H, init_scale=0.5, seed=seed + 1, dtype=np.float64, rnn_cell=rnn_cell, uq=True)
+    params[-1] = rng.normal(size=O) * 0.5
+    params[-3] = rng.normal(size=O) * 0.5
+    params = [p.astype(np.float32).astype(np.float64) for p in params]
+    x = rng.normal(size=(B, T, F)).astype(np.float32)
+    y = rng.normal(size=(B, T, O)).astype(np.float32)          # no zero-padded steps: those make the loss NaN (below)
+    return params, x, y
+
+
+@pytest.mark.parametrize('shape,cell', [((32, 20, 32, 16, 64, 1), 'lstm'), ((5, 6, 7, 3, 8, 2), 'lstm'),
+                                        ((130, 9, 33, 17, 132, 2), 'gru')])
+def test_uq_forward_loss_and_gradients_match_oracle(shape, cell):
+    B, T, F, O, H, L = shape
+    params, x, y = _uq_problem(B, T, F, O, H, L, seed=21, rnn_cell=cell)
+    kw = dict(dropout=0.2, recurrent_dropout=0.1, seed=521)
+    eng = make_engine(B, T, F, O, H, L, target_idx=O - 1, uq=True, rnn_cell=cell, train=False, **kw)   # train=False:
+    assert [n for n, _, _, _ in eng.trainable_specs][-4:] == orc.param_names(L, cell, uq=True)[-4:]    # dropout still on
+    eng.set_weights(params)
+    pred, var = eng.forward(_cuda(x), step=4, row0=64)
+    okw = dict(num_layers=L, rnn_cell=cell, step=4, row0=64, **kw)
+    rp, rv, fc = orc.forward_uq(params, x.astype(np.float64), **okw)
+    assert rel_err(pred.cpu().numpy(), rp) < TOL and rel_err(var.cpu().numpy(), rv) < TOL
+    assert float(var.min()) >= 1e-6
+    out = eng.loss_uq(pred, var, _cuda(y)).cpu().numpy()
+    loss, uq0, mse0, dp, dv = orc.loss_uq_estimate(y.astype(np.float64), rp, rv, target_idx=O - 1, target_lambda=0.5,
+                                                   rnn_lambda=0.7)
+    assert out[0] == pytest.approx(loss, rel=TOL) and out[1] == pytest.approx(uq0, rel=TOL)
+    assert out[2] == pytest.approx(mse0, rel=TOL)
+    eng.backward(_cuda(x), _cuda(y), step=4, row0=64)
+    gref = orc.backward_uq(dp, dv, fc, num_layers=L, rnn_cell=cell)
+    nt = eng.n_trainable
+    tail = eng.grads[nt:nt + 5].cpu().numpy()
+    assert tail[0] == pytest.approx(loss, rel=TOL) and tail[1] == pytest.approx(mse0, rel=TOL)
+    assert tail[4] == pytest.approx(uq0, rel=TOL)
+    for (name, _, _, _), g, r in zip(eng.trainable_specs, eng.grads_list(), gref):
+        assert rel_err(g, r) < TOL, name
+
+
+def test_uq_train_steps_match_oracle():
+    B, T, F, O, H, L = 16, 6, 8, 4, 16, 2
+    params, x, y = _uq_problem(B, T, F, O, H, L, seed=22)
+    kw = dict(dropout=0.3, recurrent_dropout=0.0, seed=521)
+    cfg = dict(num_layers=L, target_idx=1, target_lambda=0.5, rnn_lambda=0.7, max_grad_norm=0.5, optimizer='Adadelta',
+               max_norm=0.8, uq=True, **kw)
+    eng = make_engine(B, T, F, O, H, L, target_idx=1, optimizer='Adadelta', max_grad_norm=0.5, max_norm=0.8, uq=True, **kw)
+    eng.set_weights(params)
+    p = [q.copy() for q in params]
+    slots = orc.zero_slots('Adadelta', p)
+    xc, yc = _cuda(x), _cuda(y)
+    for it in range(3):
+        out = eng.train_step(xc, yc, it, 0.6).cpu().numpy()
+        p, mse, loss, raw, gn, uq0 = orc.train_step(p, slots, x.astype(np.float64), y.astype(np.float64), it, cfg, lr=0.6)
+        assert out[0] == pytest.approx(uq0, rel=TOL) and out[1] == pytest.approx(mse, rel=TOL), it
+        assert float(eng.grads[eng.n_trainable]) == pytest.approx(loss, rel=TOL)
+    for (name, _, _, _), w, r in zip(eng.trainable_specs, eng.get_weights(), p):
+        assert rel_err(w, r) < 5 * TOL, name
+
+
+def test_uq_loss_is_nan_with_a_padded_step_as_in_the_reference():
+    B, T, F, O, H, L = 8, 5, 6, 3, 8, 1
+    params, x, y = _uq_problem(B, T, F, O, H, L, seed=23)
+    y[0, :2] = 0.0
+    eng = make_engine(B, T, F, O, H, L, target_idx=1, uq=True)
+    eng.set_weights(params)
+    pred, var = eng.forward(_cuda(x))
+    out = eng.loss_uq(pred, var, _cuda(y)).cpu().numpy()
+    ref = orc.loss_uq_estimate(y.astype(np.float64), pred.cpu().numpy().astype(np.float64),
+                               var.cpu().numpy().astype(np.float64), target_idx=1, target_lambda=0.5, rnn_lambda=0.7)
+    assert np.isnan(out[0]) and np.isnan(ref[0])
+    assert out[1] == pytest.approx(ref[1], rel=TOL) and out[2] == pytest.approx(ref[2], rel=TOL)
+
+
+def test_uq_handles_refuse_the_point_estimate_entry_points_and_bf16():
+    from lfm_quant_b200 import _native as N
+    eng = make_engine(4, 3, 4, 2, 4, 1, uq=True)
+    out = torch.empty(4, 3, 2, device='cuda')
+    x = torch.zeros(4, 3, 4, device='cuda')
+    rc = eng.lib.lfmq_forward(eng.handle, x.data_ptr(), 4, 0, 0, out.data_ptr(), None)
+    assert rc != 0 and b'lfmq_forward_uq' in eng.lib.lfmq_last_error()
+    with pytest.raises(N.LfmqError, match='point-estimate head only'):
+        make_engine(256, 8, 32, 16, 256, 1, precision='bf16', uq=True)
