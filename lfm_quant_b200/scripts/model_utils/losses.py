@@ -1,6 +1,6 @@
 """Losses(config, target_idx).weight_adjusted_mse (reference: scripts/model_utils/losses.py:19-135), evaluated by
-the native loss kernel (lfmq_loss).  Only the RNN point-estimate branch with forecast_steps == 1 is built; the
-MLP / Huber / UQ branches belong to other model families."""
+the native loss kernel (lfmq_loss), and Losses.weight_adjusted_uq_loss (:137-284) by lfmq_loss_uq.  Only the RNN
+branches with forecast_steps == 1 are built; the MLP / Huber branches belong to other model families."""
 from __future__ import absolute_import, division, print_function
 
 import numpy as np
@@ -52,3 +52,23 @@ class Losses(object):
         yp = to(y_pred).to(dev, torch.float32).contiguous()
         out = self.engine.loss(yp, yt)
         return _Scalar(out[0]), _Scalar(out[1])
+
+    def weight_adjusted_uq_loss(self, y_true, y_pred, y_var):
+        """losses.py:137-178: (uq_loss, uq_loss_last_tar, mse), each with ``.numpy()``."""
+        assert self.config.UQ, "weight_adjusted_mse is only available for uq range estimate models. UQ should be True"
+        assert self.config.forecast_steps > 0, 'forecasts_steps should be a positive integer. %i was provided' % \
+            self.config.forecast_steps
+        for name, v in (('y_true', y_true), ('y_pred', y_pred), ('y_var', y_var)):
+            assert isinstance(v, (list, tuple)), \
+                'arguments to loss function need to be a list [%s], [%s1, %s2, ..]' % (name, name, name)
+        if self.config.forecast_steps != 1 or 'RNN' not in self.config.nn_type:
+            raise NotImplementedError('only RNN uq range estimates with forecast_steps=1 are built on this path')
+        if len(self.config.forecast_steps_weights) == 1:
+            self.config.forecast_steps_weights = [1.0]
+        import torch
+        assert self.engine is not None, 'Losses is not bound to a native engine'
+        dev = self.engine.device
+        to = lambda a: (a if isinstance(a, torch.Tensor) else
+                        torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))).to(dev, torch.float32).contiguous()
+        out = self.engine.loss_uq(to(y_pred[0]), to(y_var[0]), to(y_true[0]))
+        return _Scalar(out[0]), _Scalar(out[1]), _Scalar(out[2])

@@ -4,9 +4,9 @@ from __future__ import absolute_import, division, print_function
 
 # All models should be imported here
 from ..models.point_estimate.rnn_point_estimate import RNNPointEstimate  # noqa: F401
+from ..models.uq_range_estimate.rnn_uq_range_estimate import RNNUqRangeEstimate  # noqa: F401
 
-_NOT_BUILT = ('MLPPointEstimate', 'MLPLinearPointEstimate', 'NaivePointEstimate', 'RNNUqRangeEstimate',
-              'MLPUqRangeEstimate')
+_NOT_BUILT = ('MLPPointEstimate', 'MLPLinearPointEstimate', 'NaivePointEstimate', 'MLPUqRangeEstimate')
 
 
 class Model(object):

@@ -29,9 +29,10 @@ class NativeForecaster(object):
     """Keras-subset model object: __call__, predict, trainable_variables, save/load_weights,
     reset_states, summary -- plus ``train_step`` (the fused native Train._train_step_point)."""
 
-    def __init__(self, config, seq_len, n_inputs, n_outputs, target_idx):
+    def __init__(self, config, seq_len, n_inputs, n_outputs, target_idx, uq=False):
         from ....engine import ForecasterEngine
         self.config = config
+        self.uq = bool(uq)
         if config.rnn_cell not in ('lstm', 'gru'):
             raise NotImplementedError                    # rnn_point_estimate.py:101-102
         if config.forecast_steps != 1:
@@ -43,7 +44,7 @@ class NativeForecaster(object):
             dropout=config.dropout, recurrent_dropout=config.recurrent_dropout, target_lambda=config.target_lambda,
             rnn_lambda=config.rnn_lambda, max_grad_norm=config.max_grad_norm, max_norm=float(config.max_norm),
             sgd_momentum=config.sgd_momentum, seed=config.seed, forward_only=not config.train,
-            rnn_cell=config.rnn_cell)
+            rnn_cell=config.rnn_cell, uq=self.uq)
         specs = [(n, s) for (n, s, _, tr) in self.engine.specs if tr]
         self.engine.set_weights(Initializer(config).initial_weights(specs))
         self.trainable_variables = [_Variable(self, i, n, s) for i, (n, s) in enumerate(specs)]
@@ -57,15 +58,21 @@ class NativeForecaster(object):
         return torch.from_numpy(np.ascontiguousarray(inp, dtype=np.float32)).to(self.engine.device)
 
     def __call__(self, inp, training=None):
-        """model(inp) (train.py:182): preds [B,T,O] on the device; dropout follows config.train."""
+        """model(inp) (train.py:182): preds [B,T,O] on the device; dropout follows config.train.
+        uq model (train.py:204-206): the list [target_preds, variance_preds]; dropout is always on."""
         self._calls += 1
-        return self.engine.forward(self._to_device(inp), step=self._calls)
+        out = self.engine.forward(self._to_device(inp), step=self._calls)
+        return list(out) if self.uq else out
 
     def predict(self, inp, batch_size=None):
         """model.predict(inp) (train.py:289, predict.py:129): ndarray [B,T,O]."""
         x = self._to_device(inp)
         B = x.shape[0]
         mb = self.engine.cfg.max_batch
+        if self.uq:       # every call draws fresh masks: MC dropout (rnn_uq_range_estimate.py:86,88)
+            self._calls += 1
+            outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls, row0=s) for s in range(0, B, mb)]
+            return [np.concatenate([o[k].cpu().numpy() for o in outs], axis=0) for k in (0, 1)]
         outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls).cpu().numpy() for s in range(0, B, mb)]
         return np.concatenate(outs, axis=0)
 
@@ -81,7 +88,8 @@ class NativeForecaster(object):
         return self.engine.n_total
 
     def summary(self):
-        lines = ['Model: "RNNPointEstimate" (native sm_100a, precision=%s)' % self.engine.precision,
+        lines = ['Model: "%s" (native sm_100a, precision=%s)' % ('RNNUqRangeEstimate' if self.uq else 'RNNPointEstimate',
+                                                                   self.engine.precision),
                  '%-44s %-16s %10s' % ('Variable', 'Shape', 'Param #'), '=' * 72]
         for name, shape, _, tr in self.engine.specs:
             lines.append('%-44s %-16s %10d%s' % (name, str(tuple(shape)), int(np.prod(shape)), '' if tr else '  (non-trainable)'))

@@ -50,10 +50,12 @@ class Predict(object):
                 for i, t_step in enumerate(range(1 - self.seq_len, 1)):
                     outputs['inp_t' + str(t_step)].append(self._extract_inputs(inp, i))
             outputs['targets'].append(self._extract_targets(targets))
-            if self.config.UQ:
-                raise NotImplementedError('UQ range estimates are outside the recurrent point-estimate hot path')
-            preds = [self.model.predict(inp_dev)]
-            variance = [np.zeros(x.shape) for x in preds]       # predict.py:133
+            if not self.config.UQ:
+                preds = [self.model.predict(inp_dev)]
+                variance = [np.zeros(x.shape) for x in preds]   # predict.py:133
+            else:                                               # predict.py:135-138
+                model_preds = self.model.predict(inp_dev)
+                preds, variance = model_preds[0::2], model_preds[1::2]
             outputs['norm_preds'].append(self._extract_preds(preds))
             outputs['norm_variance'].append(self._extract_preds(variance))
 

@@ -55,9 +55,18 @@ class ModelExecution(object):
         print("Prediction")
         return Predict(config, dataset).predict()
 
+    def uq_estimate_execution(self):
+        """runtime/model_execution.py:201-241: training, or prediction with one process, is a single execution; the
+        multi-process MC-dropout ensemble (num_procs > 1 at predict time) fans out through files like the other
+        ensembles and is not built."""
+        if self.config.train or self.config.num_procs == 1:
+            return self.single_execution(self.config)
+        raise NotImplementedError('UQ ensemble prediction (num_procs > 1) fans out whole predictions through files; run '
+                                  'one lfm_quant.py per member')
+
     def fixed_dates_execution(self):
         if self.config.UQ:
-            raise NotImplementedError('UQ range estimates are outside the recurrent point-estimate hot path')
+            return self.uq_estimate_execution()
         if self.config.num_procs != 1:
             raise NotImplementedError('ensembles (num_procs > 1) fan out whole trainings through files; run one '
                                       'lfm_quant.py per member')

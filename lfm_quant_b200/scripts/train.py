@@ -77,26 +77,30 @@ class Train(object):
             for (batch_n, cur_batch) in enumerate(self._batches):
                 inp, target = cur_batch[0], cur_batch[1]
                 if self.config.UQ:
-                    raise NotImplementedError('UQ range estimates are outside the recurrent point-estimate hot path')
-                mse = self._train_step_point(inp, target)       # device scalar, no host sync here
-                uq_loss = None
+                    uq_loss, mse = self._train_step_uq_range(inp, target)
+                else:
+                    mse = self._train_step_point(inp, target)   # device scalar, no host sync here
+                    uq_loss = None
                 mse_steps.append(mse)
                 uq_loss_steps.append(uq_loss)
                 if batch_n % self.config.logging_interval == 0:
                     train_logs_batch['batch_n'].append(batch_n)
                     train_logs_batch['time'].append(time.time() - start)
                     train_logs_batch['mse'].append(self._mean(mse_steps))
-                    train_logs_batch['uq_loss'].append(None)
+                    train_logs_batch['uq_loss'].append(self._mean(uq_loss_steps) if self.config.UQ else None)
                     train_logs_batch['valid_mse'].append(None)
                     train_logs_batch['valid_uq_loss'].append(None)
                     self._write_train_logs(train_logs_batch, 'train-logs-batch')
 
             if epoch % self.config.epoch_logging_interval == 0:
-                valid_uq_loss, valid_mse, valid_mse_fcst = self._validation_metrics_point_estimate()
+                if self.config.UQ:
+                    valid_uq_loss, valid_mse, valid_mse_fcst = self._validation_metrics_uq_range_estimate()
+                else:
+                    valid_uq_loss, valid_mse, valid_mse_fcst = self._validation_metrics_point_estimate()
                 train_logs_epoch['epoch'].append(epoch)
                 train_logs_epoch['time'].append(time.time() - start)
                 train_logs_epoch['mse'].append(self._mean(mse_steps))
-                train_logs_epoch['uq_loss'].append(None)
+                train_logs_epoch['uq_loss'].append(self._mean(uq_loss_steps) if self.config.UQ else None)
                 train_logs_epoch['valid_mse'].append(valid_mse)
                 train_logs_epoch['valid_uq_loss'].append(valid_uq_loss)
                 train_logs_epoch['valid_mse_fcst'].append(valid_mse_fcst)
@@ -119,6 +123,14 @@ class Train(object):
         out = self.model.train_step(inp, targets, lr, self.optimizer.iterations)
         self.optimizer.iterations += 1
         return out[1]
+
+    def _train_step_uq_range(self, inp, targets):
+        """train.py:201-225 as one fused native step; returns device scalars (uq_loss_last_tar, mse_0)."""
+        assert self.config.UQ
+        lr = self.optimizer.current_lr()
+        out = self.model.train_step(inp, targets, lr, self.optimizer.iterations)
+        self.optimizer.iterations += 1
+        return out[0], out[1]
 
     def _write_train_logs(self, train_logs, name):
         df = pd.DataFrame.from_dict(train_logs)
@@ -153,6 +165,24 @@ class Train(object):
         _, valid_mse = self.losses.weight_adjusted_mse([target_all], [pred_all], True)
         _, valid_mse_fcst = self.losses.weight_adjusted_mse([target_unscaled], [pred_unscaled], True)
         return None, valid_mse.numpy(), valid_mse_fcst.numpy()
+
+    def _validation_metrics_uq_range_estimate(self):
+        """train.py:338-416: predict every validation batch (dropout stays on), uq loss over the stacked arrays, MSE of
+        the un-scaled target predictions."""
+        preds, var, targets = [], [], []
+        for cur_batch in self._valid_batches:
+            batch_pred = self.model.predict(cur_batch[0])
+            preds.append(batch_pred[0::2][0])
+            var.append(batch_pred[1::2][0])
+            targets.append(cur_batch[1].cpu().numpy())
+        if not preds:
+            return float('nan'), float('nan'), float('nan')
+        pred_all, var_all, target_all = (np.vstack(a).astype('float32') for a in (preds, var, targets))
+        pred_unscaled = self._unscale_preds(copy.deepcopy(pred_all))
+        target_unscaled = self._unscale_preds(copy.deepcopy(target_all))
+        _, valid_uq_loss, valid_mse = self.losses.weight_adjusted_uq_loss([target_all], [pred_all], [var_all])
+        _, valid_mse_fcst = self.losses.weight_adjusted_mse([target_unscaled], [pred_unscaled])
+        return valid_uq_loss.numpy(), valid_mse.numpy(), valid_mse_fcst.numpy()
 
     def _unscale_preds(self, arr):
         """train.py:420-432."""

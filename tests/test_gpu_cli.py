@@ -103,3 +103,27 @@ def test_cli_trains_and_predicts_with_the_gru_cell(workdir):
     out = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
     assert len(out) == len(df) > 100 and np.isfinite(out['norm_preds_1']).all()
     configs.reset()
+
+
+def test_cli_trains_and_predicts_the_uq_range_estimate_model(workdir):
+    """nn_type=RNNUqRangeEstimate, UQ=True (model_utils/model.py:25-33; train.py:201-225,338-416; predict.py:135-138)."""
+    conf = str(workdir / 'config' / 'system-test.conf')
+    extra = ['--nn_type', 'RNNUqRangeEstimate', '--UQ=True', '--dropout', '0.1', '--model_dir', 'system-test-uq']
+    configs.reset()
+    valid_mse = cli.main(['--config=' + conf, '--train=True'] + extra)
+    mdir = workdir / 'experiments' / 'system-test-uq'
+    assert np.isfinite(valid_mse)
+    ep = pd.read_csv(mdir / 'train_log' / 'system-test-train-logs-epoch.csv')
+    assert len(ep) == 2 and np.isfinite(ep['uq_loss']).all() and np.isfinite(ep['valid_uq_loss']).all()
+    assert ep['uq_loss'].iloc[1] < ep['uq_loss'].iloc[0]                     # the NLL goes down
+    bt = pd.read_csv(mdir / 'train_log' / 'system-test-train-logs-batch.csv')
+    assert np.isfinite(bt['uq_loss']).all()
+    w = np.load(mdir / 'chkpts' / 'chkpt.lfmq.npz')
+    assert set(orc.param_names(1, uq=True)) <= set(w.files) and w['OUTPUT_VARIANCE_1/kernel'].shape == (64, 16)
+    configs.reset()
+    df = cli.main(['--config=' + conf, '--train=False'] + extra)
+    out = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
+    assert len(out) == len(df) > 100
+    assert np.isfinite(out['norm_preds_1']).all() and (out['norm_variance_1'] >= 1e-6).all()
+    assert np.isfinite(out['variance_1']).all()
+    configs.reset()
