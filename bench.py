@@ -327,7 +327,8 @@ def main():
                              'input batches' % NB,
                        'precision': args.precision},
             'e2e': {'value': e2e, 'unit': 'sequences/s', 'ms_per_step': ms_e2e / args.steps,
-                    'h2d_bytes_per_step': int(B * T * (F + O) * 4), 'd2h_bytes_per_step': 8},
+                    'h2d_bytes_per_step': int(world * B * T * (F + O) * 4), 'd2h_bytes_per_step': 8 * world,
+                    'h2d_bytes_per_step_per_gpu': int(B * T * (F + O) * 4)},
             'gpu_launches': int(launches),
             'roofline': roofline,
             'clocks': clocks,
