@@ -187,9 +187,13 @@ struct FwdBars {
   uint64_t w_full, x_full, x_empty, h_full, h_written;
   uint64_t acc_full[2];
   uint64_t acc_free;      // deferred saved-state stores have drained the staging TMEM buffer
+  uint64_t tma_issued;    // producer -> epilogue: the fetch of h for the next step has been issued
   uint32_t tmem_base;
 };
 
+// SAVE: training (gates / cell states kept for BPTT).  A template parameter so that the predict kernel carries none of
+// the saved-state logic.
+template <bool SAVE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
     lstm_fwd_tc_kernel(FwdParams p, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_x,
                        const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w) {
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     mbar_init(&bars->acc_full[0], 1);
     mbar_init(&bars->acc_full[1], 1);
     mbar_init(&bars->acc_free, 32 * FWD_EPI_WARPS);
+    mbar_init(&bars->tma_issued, 1);
     fence_mbar_init();
   }
   if (tid < TC_NSL) bias_s[tid] = p.biasp[rank * TC_NSL + tid];
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
               tma_load_2d_mcast(hbuf + kb * 16384 + rank * 4096, &tm_h, &bars->h_full, t * TC_XH_LD + kb * 64,
                                 b0 + 32 * (int)rank, 0xF);
             FWD_TRACE(0, t, 2);
+            if (SAVE) mbar_arrive(&bars->tma_issued);
           }
         }
         mbar_wait_cluster(&bars->h_written, (n_hw++) & 1);       // phase of step T-1 (keeps parities aligned)
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           const uint32_t acc = tmem + (g & 1) * 256;
           mbar_wait(&bars->x_full, (n_xf++) & 1);
           // training: acc[g&1] doubled as the staging buffer of step g-1's saved gates / cell states
-          if (p.gates && g > 0) mbar_wait(&bars->acc_free, (g - 1) & 1);
+          if (SAVE && g > 0) mbar_wait(&bars->acc_free, (g - 1) & 1);
           FWD_TRACE(1, t, 0);
           tcgen05_fence_after();
           for (int k16 = 0; k16 < p.k16_x; ++k16) {
@@ -298,6 +304,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int m = q * 32 + lane;            // row of the 128-row tile
     const bool leader = (warp == 2) && lane == 0;
+    uint32_t n_ti = 0;                      // phases of tma_issued consumed (one per step that has a successor)
     const int fr = 2 * (int)rank + half;    // 32-unit block index (saved-state layout, hidden offset 32*fr)
     float cstate[32];
     for (int it = 0; it < p.n_iters; ++it) {
@@ -317,8 +324,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + fr * 32;
         // saved state, SoA at 32-byte granularity: [(t, tile, fr, quadrant)][piece][lane]
         const long wblk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 4 + q;
-        __nv_bfloat16* grow = p.gates ? p.gates + (wblk * 8 * 32 + lane) * 16 : nullptr;   // + piece * 512
-        __nv_bfloat16* crow = p.cst ? p.cst + (wblk * 2 * 32 + lane) * 16 : nullptr;       // + piece * 512
+        __nv_bfloat16* grow = SAVE ? p.gates + (wblk * 8 * 32 + lane) * 16 : nullptr;      // + piece * 512
+        __nv_bfloat16* crow = SAVE ? p.cst + (wblk * 2 * 32 + lane) * 16 : nullptr;        // + piece * 512
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           uint32_t vi[16], vf[16], vg[16], vo[16];
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
           }
           if (valid) st_global_v8(hrow + jb * 16, ph);   // one full 32-byte sector per store (STG.256)
-          if (grow) {
+          if (SAVE) {
             // Saved gates / cell states are not needed by the h exchange: park them in the idle accumulator
             // buffer (TMEM) and write them to HBM after the publish, off the per-step critical path.
             const uint32_t tst = taddr_other + jb * 40;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             tmem_st_32x32b_x8(tst + 32, cu);
           }
         }
-        if (grow) tmem_st_wait();
+        if (SAVE) tmem_st_wait();
         tcgen05_fence_before();
         if (leader) FWD_TRACE(2, t, 1);
         // Publish this CTA's h slice: CTA-level barrier over the 256 epilogue threads, then 4 lanes of the leader
@@ -377,24 +384,38 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         if (leader) FWD_TRACE(2, t, 4);
         if (warp == 2 && lane < TC_NC)
           mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written), (uint32_t)lane));
-        if (grow) {
+        if (SAVE) {
+          // Saved state of this step, parked in the idle accumulator buffer.  All CTAs reach this point together, so
+          // writing the whole 80 KB per CTA at once is a ~3 K-cycle burst at full HBM write bandwidth: it outlasts the
+          // publish, and the producer's proxy fence + TMA issue for the next step then queue behind it (clock64 trace:
+          // 1.5 K cycles instead of 0.3 K without saved state).  So: first half now (over before the producer needs to
+          // fence), second half out of TMEM into registers -- the MMA may have the staging buffer back -- and to global
+          // only once the producer has issued the next step's h fetch.
           tcgen05_fence_after();
-#pragma unroll
-          for (int jb = 0; jb < 2; ++jb) {
-            uint32_t sg[32], sc[8];
-            tmem_ld_32x32b_x32(taddr_other + jb * 40, sg);
-            tmem_ld_32x32b_x8(taddr_other + jb * 40 + 32, sc);
-            tmem_ld_wait();
-            if (valid) {
-              st_global_v8(grow + (0 * 2 + jb) * 512, sg);
-              st_global_v8(grow + (1 * 2 + jb) * 512, sg + 8);
-              st_global_v8(grow + (2 * 2 + jb) * 512, sg + 16);
-              st_global_v8(grow + (3 * 2 + jb) * 512, sg + 24);
-              st_global_v8(crow + jb * 512, sc);
-            }
+          uint32_t sg[32], sc[8];
+          tmem_ld_32x32b_x32(taddr_other, sg);
+          tmem_ld_32x32b_x8(taddr_other + 32, sc);
+          tmem_ld_wait();
+          if (valid) {
+            st_global_v8(grow + (0 * 2 + 0) * 512, sg);
+            st_global_v8(grow + (1 * 2 + 0) * 512, sg + 8);
+            st_global_v8(grow + (2 * 2 + 0) * 512, sg + 16);
+            st_global_v8(grow + (3 * 2 + 0) * 512, sg + 24);
+            st_global_v8(crow, sc);
           }
+          tmem_ld_32x32b_x32(taddr_other + 40, sg);
+          tmem_ld_32x32b_x8(taddr_other + 40 + 32, sc);
+          tmem_ld_wait();
           tcgen05_fence_before();
           mbar_arrive(&bars->acc_free);
+          if (t < T - 1) mbar_wait(&bars->tma_issued, (n_ti++) & 1);
+          if (valid) {
+            st_global_v8(grow + (0 * 2 + 1) * 512, sg);
+            st_global_v8(grow + (1 * 2 + 1) * 512, sg + 8);
+            st_global_v8(grow + (2 * 2 + 1) * 512, sg + 16);
+            st_global_v8(grow + (3 * 2 + 1) * 512, sg + 24);
+            st_global_v8(crow + 512, sc);
+          }
         }
         if (leader) FWD_TRACE(2, t, 5);
       }
@@ -1265,7 +1286,8 @@ int tc_init(TcState& st, const lfmq_config& c) {
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
   if ((rc = make_map_2d(&m.tm_u, m.Up, TC_H, 4 * TC_H, TC_H * 2, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_w, m.Wp, 32, 4 * TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   // how many 8-CTA clusters can be co-resident (one CTA per SM because of shared memory)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(TC_NC * 37);
@@ -1279,7 +1301,7 @@ int tc_init(TcState& st, const lfmq_config& c) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int nclusters = 0;
-  LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nclusters, lstm_fwd_tc_kernel, &cfg));
+  LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nclusters, lstm_fwd_tc_kernel<true>, &cfg));
   if (nclusters < 1) {
     LFMQ_SET_ERR("no 4-CTA cluster of the forward kernel fits on this device");
     return LFMQ_ERR_UNSUPPORTED;
@@ -1349,7 +1371,10 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
+  if (save)
+    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel<true>, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
+  else
+    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel<false>, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
   g_launches++;
   if (want_trace) {
     long long h[3 * 16 * 8];
