@@ -10,7 +10,9 @@
 //                                 row to one thread, so the state is stored SoA at 32-byte granularity: a warp's
 //                                 256-bit access to `piece` covers 1 KB contiguously instead of 32 scattered sectors
 //   cst   bf16 [T][tiles][8][4][2 pieces][32][16]   cell states (the recurrence itself keeps them in fp32 registers)
-//   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero)
+//   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero); columns in the order the
+//                                 backward kernel stages them as its A operand, [16-unit block][gate][16], so that a
+//                                 chunk goes out with one TMA store; only the weight-gradient GEMM reads it
 //   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dLoss/dh from the head (after BN/dropout
 //                                 backward), already in the backward kernel's per-thread SoA order
 //
@@ -72,6 +74,34 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer
   if (r != CUDA_SUCCESS) {
     LFMQ_SET_ERR("cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu box %u x %u)", (int)r,
                  (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+    return LFMQ_ERR_CUDA;
+  }
+  return 0;
+}
+
+// General tiled map (bf16): dims / box innermost first, strides in bytes for dims 1..rank-1.
+int make_map_nd(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, CUtensorMapSwizzle sw) {
+  static PFN_encodeTiled enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    LFMQ_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    enc = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (!enc) {
+      LFMQ_SET_ERR("cuTensorMapEncodeTiled not available");
+      return LFMQ_ERR_CUDA;
+    }
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    LFMQ_SET_ERR("cuTensorMapEncodeTiled (rank %d) failed with %d", rank, (int)r);
     return LFMQ_ERR_CUDA;
   }
   return 0;
@@ -1549,7 +1579,7 @@ struct BwdBars {
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     lstm_bwd_tc_kernel(BwdParams p, const __grid_constant__ CUtensorMap tm_ubk,
-                       const __grid_constant__ CUtensorMap tm_px) {
+                       const __grid_constant__ CUtensorMap tm_px, const __grid_constant__ CUtensorMap tm_dzst) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + SB_BARS);
@@ -1620,17 +1650,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             if (jb == 0) BWD_TRACE(1, T - 1 - t, 0);
             if (jb == 3) BWD_TRACE(1, T - 1 - t, 1);
             tcgen05_fence_after();
+            // dz_t of this chunk leaves for HBM straight from the staged A operand: one TMA store (128 rows x 128 B,
+            // rows >= B clipped) instead of four STG.256 per pointwise thread.  dz keeps the operand's column order
+            // [16-unit block][gate][16] (see tc_layout); wgrad_reduce_kernel puts the gate columns back in order.
+            tma_store_3d(&tm_dzst, smem + SB_A + st * 16384, (4 * (int)rank + jb) * 64, t,
+                         (it * p.n_clusters + cid) * 128);
+            bulk_commit_group();
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t da = make_smem_desc(smem_u32(smem + SB_A + st * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
               const uint64_t db = make_smem_desc(smem_u32(smem + SB_U + jb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
               umma_f16(acc, da, db, idesc, (jb | k16) != 0);
             }
+            bulk_wait_group_read0();             // the store has read the stage (well inside the MMAs' own time)
             umma_commit(&bars->a_empty[st]);
           }
           umma_commit(&bars->acc_full[gs & 1]);
         }
       }
+      bulk_wait_group0();                        // all dz stores complete before the kernel ends
     }
   } else {
     // ===================== pointwise gate gradients, A-operand staging, partial exchange =====================
@@ -1688,7 +1726,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
         if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
         if (tid == 64) BWD_TRACE(2, T - 1 - t, 0);
-        __nv_bfloat16* dzrow = p.dz + (b * (T + 1) + t) * 4 * TC_H + rank * 64;
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int jb = 2 * ci + set;
@@ -1740,12 +1777,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             zf[e] = mul_bf16x2(dcn2, mul_bf16x2(cp[ci][e], omf));
             zg[e] = mul_bf16x2(dcn2, mul_bf16x2(i2, omg));
             zo[e] = mul_bf16x2(mul_bf16x2(dh2, tc2), omo);
-          }
-          if (valid) {
-            st_global_v8(dzrow + jb * 16, zi);
-            st_global_v8(dzrow + TC_H + jb * 16, zf);
-            st_global_v8(dzrow + 2 * TC_H + jb * 16, zg);
-            st_global_v8(dzrow + 3 * TC_H + jb * 16, zo);
           }
           // A operand k-block jb in stage `set`: row m, chunk 2g+h holds gate g, units 8h..8h+7 (SW128 K-major)
           const uint32_t n_use = gs * 2 + ci;                 // use index of this stage
@@ -1911,12 +1942,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-// Sums the K-split partials and scatters D rows into dU / dW / db of the flat gradient vector.
+// Sums the K-split partials and scatters D rows into dU / dW / db of the flat gradient vector.  D's columns are in
+// dz's order [16-unit block][gate][16]; the gradients want gate-major columns g*H + unit.
 __global__ void wgrad_reduce_kernel(int S, int I, const float* __restrict__ partial, float* __restrict__ gU,
                                     float* __restrict__ gW, float* __restrict__ gb) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)384 * 1024) return;
-  const int row = (int)(idx / 1024), n = (int)(idx % 1024);
+  const int row = (int)(idx / 1024), np = (int)(idx % 1024);
+  const int n = ((np % 64) / 16) * TC_H + (np / 64) * 16 + (np % 16);
   float* dst = nullptr;
   if (row < TC_H) dst = gU + (long)row * 1024 + n;
   else if (row < TC_H + I) dst = gW + (long)(row - TC_H) * 1024 + n;
@@ -1983,7 +2016,15 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, bp, m.tm_ubk, m.tm_px));
+    // dz as [b][t][1024] with columns ordered [16-unit block][gate][16]: one staged chunk = 128 rows x 64 columns
+    CUtensorMap tm_dzst;
+    {
+      const uint64_t dims[3] = {1024, (uint64_t)(T + 1), (uint64_t)B};
+      const uint64_t strides[2] = {2048, (uint64_t)2048 * (T + 1)};
+      const uint32_t box[3] = {64, 1, 128};
+      if ((rc = make_map_nd(&tm_dzst, m.dz, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, bp, m.tm_ubk, m.tm_px, tm_dzst));
     g_launches++;
     if (want_btrace) {
       long long h[3 * 16 * 8];

@@ -550,6 +550,71 @@ __global__ void __launch_bounds__(128, 1) probe_mufu2_kernel(int iters, long lon
   sink[threadIdx.x] = s;
 }
 
+// ---- 3-D TMA store of a K-major SW128 tile (128-byte rows = 4 gates x 16 units) into dz laid out as
+// [b][t][16-unit block][gate][16]: the row of a chunk is 128 contiguous bytes.  (A 5-D map over the gate-major layout
+// -- box 16 x 1 x 4 x 1 x 128, SWIZZLE_128B -- raised an illegal memory access on B200 and is not used.) ----
+__global__ void __launch_bounds__(128, 1) probe_st3d_kernel(const __grid_constant__ CUtensorMap tm, int ublk, int t,
+                                                            int b0) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int m = threadIdx.x;
+  for (int c = 0; c < 8; ++c) {          // 16-byte chunk c = 2*gate + half, XOR-swizzled with the row like the A operand
+    uint16_t v[8];
+    for (int e = 0; e < 8; ++e) v[e] = (uint16_t)(m * 64 + (c / 2) * 16 + (c % 2) * 8 + e);
+    *reinterpret_cast<uint4*>(smem + m * 128 + ((c ^ (m & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (m == 0) {
+    tma_store_3d(&tm, smem, ublk * 64, t, b0);
+    bulk_commit_group();
+    bulk_wait_group0();
+  }
+}
+
+static bool run_st3d() {
+  const int Bcap = 300, B = 150, T1 = 3;
+  const size_t n = (size_t)Bcap * T1 * 1024;
+  uint16_t* d;
+  CK(cudaMalloc(&d, n * 2));
+  CK(cudaMemset(d, 0xFF, n * 2));
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  CUtensorMap tm;
+  cuuint64_t dims[3] = {1024, (cuuint64_t)T1, (cuuint64_t)B};
+  cuuint64_t strides[2] = {2048, (cuuint64_t)2048 * T1};
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { printf("[st3d] encode failed %d\n", (int)r); return false; }
+  CK(cudaFuncSetAttribute(probe_st3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024));
+  probe_st3d_kernel<<<1, 128, 16384 + 1024>>>(tm, 5, 1, 0);
+  probe_st3d_kernel<<<1, 128, 16384 + 1024>>>(tm, 9, 2, 128);
+  CK(cudaDeviceSynchronize());
+  std::vector<uint16_t> h(n);
+  CK(cudaMemcpy(h.data(), d, n * 2, cudaMemcpyDeviceToHost));
+  long bad = 0, written = 0, first = -1;
+  for (int b = 0; b < Bcap; ++b)
+    for (int t = 0; t < T1; ++t)
+      for (int col = 0; col < 1024; ++col) {
+        const int ub = col / 64, g = (col % 64) / 16, jj = col % 16;
+        uint16_t want = 0xFFFF;
+        if (t == 1 && ub == 5 && b < 128) want = (uint16_t)(b * 64 + g * 16 + jj);
+        if (t == 2 && ub == 9 && b >= 128 && b < B) want = (uint16_t)((b - 128) * 64 + g * 16 + jj);
+        const uint16_t got = h[((size_t)b * T1 + t) * 1024 + col];
+        if (got != 0xFFFF) ++written;
+        if (got != want) { if (first < 0) first = ((long)b * T1 + t) * 1024 + col; ++bad; }
+      }
+  printf("[st3d] elements written %ld (expected %d), mismatches %ld", written, 128 * 64 + 22 * 64, bad);
+  if (first >= 0) {
+    const long e = first;
+    printf(", first at b=%ld t=%ld col=%ld got %u", e / (T1 * 1024), (e / 1024) % T1, e % 1024, (unsigned)h[e]);
+  }
+  printf("\n");
+  CK(cudaFree(d));
+  return bad == 0;
+}
+
 static bool want(int argc, char** argv, const char* name) {
   if (argc <= 1) return true;
   for (int i = 1; i < argc; ++i)
@@ -690,6 +755,7 @@ int main(int argc, char** argv) {
     printf("[mufu2] tanh.approx.bf16x2 (+1 HFMA2): %.2f instr = %.2f tanh per cycle per SM\n",
            128.0 * 8 * iters / (double)cy[0], 2 * 128.0 * 8 * iters / (double)cy[0]);
   }
+  if (want(argc, argv, "st3d")) ok &= run_st3d();
   printf("%s\n", ok ? "PROBE ALL OK" : "PROBE HAD MISMATCHES");
   return ok ? 0 : 1;
 }
