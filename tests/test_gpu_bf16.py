@@ -150,3 +150,26 @@ def test_bf16_matches_fp32_path_at_baseline_shape():
     scale = np.abs(p32).max()
     assert np.abs(p16 - p32).max() / scale < 6e-2
     assert np.sqrt(np.mean((p16 - p32) ** 2)) / np.sqrt(np.mean(p32 ** 2)) < 2e-2
+
+
+def test_bf16_training_with_more_tiles_than_resident_clusters():
+    """B = 4500 is 36 batch tiles (the last one ragged): the persistent recurrences run a second iteration per cluster,
+    which exercises the barrier phases carried across tiles (forward tma_issued / acc_free, backward exp_ready) and the
+    dz TMA-store coordinates of later tiles.  Gradients and loss vs the fp32 CUDA path."""
+    B, T, F, O, H, L = 4500, 5, 32, 16, 256, 1
+    params, x, y = make_problem(B, T, F, O, H, L, seed=31, init_scale=0.5)
+    out = {}
+    for prec in ('fp32', 'bf16'):
+        eng = make_engine(B, T, F, O, H, L, target_idx=3, precision=prec)
+        eng.set_weights(params)
+        eng.backward(_cuda(x), _cuda(y))
+        out[prec] = (eng.grads_list(), eng.grads[eng.n_trainable:eng.n_trainable + 2].cpu().numpy(),
+                     [s[0] for s in eng.trainable_specs])
+        eng.close()
+    assert out['bf16'][1][0] == pytest.approx(out['fp32'][1][0], rel=BF16_TOL)
+    assert out['bf16'][1][1] == pytest.approx(out['fp32'][1][1], rel=BF16_TOL)
+    for name, g, r in zip(out['fp32'][2], out['bf16'][0], out['fp32'][0]):
+        assert np.isfinite(g).all(), name
+        cos = float(np.sum(g * r) / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        assert cos > 0.999, (name, cos)
+        assert rel_err(g, r) < 2 * BF16_TOL, name
