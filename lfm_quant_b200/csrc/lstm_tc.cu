@@ -478,7 +478,13 @@ struct HeadParams {
   __nv_bfloat16* dhout;
   float* dpred;         // [B*T][16] dLoss/dpred (training), consumed by head_wgrad_kernel
   float* partial;       // [gridDim.x][HEAD_PART]
+  long long* trace;     // debug (LFMQ_TRACE_HEAD=1): clock64 stamps of CTA 0, first 8 tiles
 };
+
+#define HEAD_TRACE(role, n, pt)                                                                       \
+  do {                                                                                                \
+    if (p.trace && blockIdx.x == 0 && (n) < 8) p.trace[((role) * 8 + (n)) * 8 + (pt)] = clock64();    \
+  } while (0)
 
 constexpr int HEAD_PART = 2 * TC_H + TC_OPAD + 16;   // dgamma | dbeta | dbo | s0 s1 s2 (per CTA of the fused pass)
 constexpr int HEAD_THREADS = 256;
@@ -855,10 +861,12 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
       for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++n) {
         const int t = ti / n_btiles, bt = ti % n_btiles;
         if (n > 0) mbar_wait(&bars->tile_free, (n - 1) & 1);
+        HEAD_TRACE(0, n, 0);
         mbar_arrive_expect_tx(&bars->tile_full, 65536);
         for (int kb = 0; kb < 4; ++kb)
           tma_load_2d(smem + HT_TILE + kb * 16384, &tm_h, &bars->tile_full, (t + 1) * TC_XH_LD + kb * 64, bt * 128);
         mbar_wait(&bars->tile_full, n & 1);
+        HEAD_TRACE(0, n, 1);
         tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
@@ -871,6 +879,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
         umma_commit(&bars->pred_full);
         if (TRAIN) {
           mbar_wait(&bars->dp_full, n & 1);
+          HEAD_TRACE(0, n, 2);
           tcgen05_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem + HT_DP), 0, 512, LAYOUT_SW64);
           umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP), 0, 512, LAYOUT_SW64), idesc_y, 0);
@@ -890,6 +899,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
               }
           }
           mbar_wait(&bars->y0_free, n & 1);
+          HEAD_TRACE(0, n, 3);
           tcgen05_fence_after();
           umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP + 8192), 0, 512, LAYOUT_SW64), idesc_y, 0);
           umma_commit(&bars->dy_full[1]);
@@ -917,7 +927,6 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
     float accbo[TC_OPAD];
 #pragma unroll
     for (int k = 0; k < TC_OPAD; ++k) accbo[k] = 0.f;
-    const int sw = mrow & 7;
     uint32_t n = 0;
     for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++n) {
       const int t = ti / n_btiles, bt = ti % n_btiles;
@@ -933,6 +942,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           if (k < p.O) yt[k] = p.y[r * p.O + k];
       }
       mbar_wait(&bars->pred_full, n & 1);
+      if (tid == 32) HEAD_TRACE(1, n, 0);
       tcgen05_fence_after();
       uint32_t pv[16];
       tmem_ld_32x32b_x16(acc_p + lane_addr, pv);
@@ -984,11 +994,12 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
               make_uint4(pack_bf16x2(dp[8], dp[9]), pack_bf16x2(dp[10], dp[11]), pack_bf16x2(dp[12], dp[13]), pack_bf16x2(dp[14], dp[15]));
           fence_proxy_async_smem();
           mbar_arrive(&bars->dp_full);
+          if (tid == 32) HEAD_TRACE(1, n, 1);
           __nv_bfloat16* dh_base = p.dhout + ((((long)t * n_tiles_cap + bt) * 4) * 4 + wq) * 4 * 32 * 16 + lane * 16;
-          const uint8_t* hrow = smem + HT_TILE + mrow * 128;
 #pragma unroll 1
           for (int hN = 0; hN < 2; ++hN) {
             mbar_wait(&bars->dy_full[hN], n & 1);
+            if (tid == 32) HEAD_TRACE(1, n, 2 + 2 * hN);
             tcgen05_fence_after();
 #pragma unroll 1
             for (int g4 = 0; g4 < 4; ++g4) {                 // 32 columns per group
@@ -996,21 +1007,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
               uint32_t dv[32];
               tmem_ld_32x32b_x32(acc_y + lane_addr + g4 * 32, dv);
               tmem_ld_wait();
-              float dd[32], gd[32];
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc) {
-                const int c = grp * 4 + cc;
-                const uint4 raw = *reinterpret_cast<const uint4*>(hrow + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4));
-                const uint32_t hw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int j = c * 8 + e;
-                  const float hv = valid ? ((e & 1) ? bf16_hi(hw[e >> 1]) : bf16_lo(hw[e >> 1])) : 0.f;
-                  const float d_ = valid ? __uint_as_float(dv[cc * 8 + e]) : 0.f;
-                  dd[cc * 8 + e] = d_;
-                  gd[cc * 8 + e] = d_ * (hv - bn_s[1][j]) * bn_s[2][j];
-                }
-              }
+              // dLoss/dh = dy * gamma * inv.  The BatchNorm gradients need no per-tile reduction here: with
+              // dy = dpred Wo^T, sum_r dy[r][j] = sum_k Wo[j][k] colsum(dpred)[k] and sum_r dy[r][j] h[r][j] =
+              // sum_k Wo[j][k] (h^T dpred)[j][k] -- both right-hand sides are already accumulated (dbo, and the
+              // tensor-core h^T dpred for dWo); head_fold_kernel finishes dgamma / dbeta from them.
               if (valid) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -1018,29 +1018,16 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     const int jj = hh * 16 + 2 * e;
-                    pk[e] = pack_bf16x2(dd[jj] * bn_s[0][grp * 32 + jj], dd[jj + 1] * bn_s[0][grp * 32 + jj + 1]);
+                    pk[e] = pack_bf16x2(__uint_as_float(dv[jj]) * bn_s[0][grp * 32 + jj],
+                                        __uint_as_float(dv[jj + 1]) * bn_s[0][grp * 32 + jj + 1]);
                   }
                   const int c16 = grp * 2 + hh;
                   st_global_v8(dh_base + ((long)(c16 >> 2) * 4 * 4 + (c16 & 3)) * 32 * 16, pk);
                 }
               }
-#pragma unroll
-              for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                  const bool up = (lane & off) != 0;
-                  const float sd = up ? dd[i] : dd[i + off];
-                  const float kd = up ? dd[i + off] : dd[i];
-                  dd[i] = kd + __shfl_xor_sync(0xffffffffu, sd, off);
-                  const float sg = up ? gd[i] : gd[i + off];
-                  const float kg = up ? gd[i + off] : gd[i];
-                  gd[i] = kg + __shfl_xor_sync(0xffffffffu, sg, off);
-                }
-              }
-              atomicAdd(&red_s[TC_H + grp * 32 + lane], dd[0]);
-              atomicAdd(&red_s[grp * 32 + lane], gd[0]);
             }
             tcgen05_fence_before();
+            if (tid == 32) HEAD_TRACE(1, n, 3 + 2 * hN);
             if (hN == 0) mbar_arrive(&bars->y0_free);
           }
         }
@@ -1218,16 +1205,28 @@ __global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial,
   }
 }
 
-// tensor-core head: gWo holds h^T dpred; y = a*h + b  =>  dWo = a_j * (h^T dpred) + b_j * colsum(dpred)
+// tensor-core head, one thread per hidden unit j.  In: G = h^T dpred (in gWo), cs = colsum(dpred) (in gbo).
+// With y = a_j h + c_j (a = gamma*inv, c = beta - gamma*mean*inv) and dy = dpred Wo^T:
+//   dWo[j][k] = a_j G[j][k] + c_j cs[k]
+//   dbeta_j   = sum_r dy[r][j]           = sum_k Wo[j][k] cs[k]
+//   dgamma_j  = sum_r dy[r][j] xhat[r][j] = inv_j (sum_k Wo[j][k] G[j][k] - mean_j dbeta_j)
 __global__ void head_fold_kernel(int O, float* __restrict__ gWo, const float* __restrict__ gbo,
+                                 float* __restrict__ ggamma, float* __restrict__ gbeta, const float* __restrict__ Wo,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= TC_H * O) return;
-  const int j = i / O, k = i % O;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= TC_H) return;
   const float iv = 1.0f / sqrtf(var[j] + eps);
-  const float a = gamma[j] * iv, bb = beta[j] - gamma[j] * mean[j] * iv;
-  gWo[i] = a * gWo[i] + bb * gbo[k];
+  const float a = gamma[j] * iv, c = beta[j] - gamma[j] * mean[j] * iv;
+  float db = 0.f, sg = 0.f;
+  for (int k = 0; k < O; ++k) {
+    const float w = Wo[j * O + k], g = gWo[j * O + k], cs = gbo[k];
+    db = fmaf(w, cs, db);
+    sg = fmaf(w, g, sg);
+    gWo[j * O + k] = fmaf(a, g, c * cs);
+  }
+  gbeta[j] = db;
+  ggamma[j] = iv * (sg - mean[j] * db);
 }
 
 // =============================================================================================
@@ -1439,6 +1438,11 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   h.Wo = params + m.oWo; h.bo = params + m.obo;
   h.y = y; h.denom = denom; h.p1 = c.target_lambda; h.p2 = c.rnn_lambda;
   h.use_dropout = (c.train && c.dropout > 0.f) ? 1 : 0;
+  static long long* htrace = nullptr;
+  static const bool want_htrace = getenv("LFMQ_TRACE_HEAD") != nullptr;
+  if (want_htrace && !htrace) LFMQ_CUDA_CHECK(cudaMalloc(&htrace, 2 * 8 * 8 * sizeof(long long)));
+  if (want_htrace) LFMQ_CUDA_CHECK(cudaMemsetAsync(htrace, 0, 2 * 8 * 8 * sizeof(long long), s));
+  h.trace = want_htrace ? htrace : nullptr;
   h.key.k0 = (uint32_t)(c.seed & 0xffffffffu);
   h.key.k1 = (uint32_t)(c.seed >> 32);
   h.key.stream = 0;
@@ -1465,6 +1469,19 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
                                                              n_tiles_cap, m.head_wpart);
       LFMQ_LAUNCH_CHECK();
       n_wcta = grid;
+      if (want_htrace) {
+        long long hh[2 * 8 * 8];
+        LFMQ_CUDA_CHECK(cudaStreamSynchronize(s));
+        LFMQ_CUDA_CHECK(cudaMemcpy(hh, htrace, sizeof(hh), cudaMemcpyDeviceToHost));
+        const long long t0 = hh[0];
+        for (int k = 0; k < 8; ++k) {
+          fprintf(stderr, "[htrace tile %d]  ctl:", k);
+          for (int q = 0; q < 4; ++q) fprintf(stderr, " %lld", hh[(0 * 8 + k) * 8 + q] ? hh[(0 * 8 + k) * 8 + q] - t0 : -1LL);
+          fprintf(stderr, "  row:");
+          for (int q = 0; q < 6; ++q) fprintf(stderr, " %lld", hh[(1 * 8 + k) * 8 + q] ? hh[(1 * 8 + k) * 8 + q] - t0 : -1LL);
+          fprintf(stderr, "\n");
+        }
+      }
     } else {
       head_rows_kernel<true><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
       LFMQ_LAUNCH_CHECK();
@@ -1487,9 +1504,10 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
         grads ? grads + m.obeta : nullptr, out2);
     LFMQ_LAUNCH_CHECK();
     if (train && use_tc) {
-      head_fold_kernel<<<(TC_H * m.O + 255) / 256, 256, 0, s>>>(m.O, grads + m.oWo, grads + m.obo, params + m.ogamma,
-                                                              params + m.obeta, params + m.omean, params + m.ovar,
-                                                              c.bn_epsilon);
+      head_fold_kernel<<<(TC_H + 127) / 128, 128, 0, s>>>(m.O, grads + m.oWo, grads + m.obo, grads + m.ogamma,
+                                                        grads + m.obeta, params + m.oWo, params + m.ogamma,
+                                                        params + m.obeta, params + m.omean, params + m.ovar,
+                                                        c.bn_epsilon);
       LFMQ_LAUNCH_CHECK();
     }
   }
