@@ -123,6 +123,9 @@ struct TcImpl {
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
   CUtensorMap tm_h128, tm_wot, tm_wop;         // head: 128-row h tiles, folded head weights
   __nv_bfloat16 *WoTp, *Wop;
+  __nv_bfloat16* WoSp;                         // [256][32]  Wo[j][k] * gamma_j * inv_j (k < 16), zero padded
+  __nv_bfloat16* dpb;                          // [T][tiles][128][32] bf16 dLoss/dpred tiles (cols >= 16 zero)
+  CUtensorMap tm_wos, tm_dpb;
   float* bop;
   CUtensorMap tm_ubk, tm_px;                   // backward recurrence
   CUtensorMap tm_xh_mn, tm_dz_mn;              // weight gradient (MN-major)
@@ -730,7 +733,7 @@ __device__ __forceinline__ void pack_head_body(int bid, int O, const float* __re
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                  __nv_bfloat16* __restrict__ WoTp, __nv_bfloat16* __restrict__ Wop,
-                                 float* __restrict__ bop) {
+                                 __nv_bfloat16* __restrict__ WoSp, float* __restrict__ bop) {
   const int idx = bid * blockDim.x + threadIdx.x;
   if (idx < TC_OPAD * TC_H) {
     const int n = idx / TC_H, j = idx % TC_H;
@@ -740,6 +743,7 @@ __device__ __forceinline__ void pack_head_body(int bid, int O, const float* __re
   if (idx < TC_H * 32) {
     const int j = idx / 32, k = idx % 32;
     Wop[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
+    WoSp[idx] = __float2bfloat16(k < O ? Wo[j * O + k] * gamma[j] / sqrtf(var[j] + eps) : 0.f);
   }
   // folded bias: block k (< 16) reduces over its 256 threads = 256 hidden units
   if (bid < TC_OPAD) {
@@ -778,7 +782,7 @@ struct PackArgs {
   int I, O, nb_w, nb_h, nb_u;
   float eps;
   const float *W, *U, *bias, *Wo, *bo, *gamma, *beta, *mean, *var;
-  __nv_bfloat16 *Up, *Wp, *Ubk, *WoTp, *Wop;
+  __nv_bfloat16 *Up, *Wp, *Ubk, *WoTp, *Wop, *WoSp;
   float *biasp, *bop;
 };
 
@@ -787,7 +791,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(PackArgs a) {
   if (bid < a.nb_w) {
     pack_weights_body(bid, a.I, a.W, a.U, a.bias, a.Up, a.Wp, a.biasp);
   } else if (bid < a.nb_w + a.nb_h) {
-    pack_head_body(bid - a.nb_w, a.O, a.Wo, a.bo, a.gamma, a.beta, a.mean, a.var, a.eps, a.WoTp, a.Wop, a.bop);
+    pack_head_body(bid - a.nb_w, a.O, a.Wo, a.bo, a.gamma, a.beta, a.mean, a.var, a.eps, a.WoTp, a.Wop, a.WoSp, a.bop);
   } else {
     pack_ubk_body(bid - a.nb_w - a.nb_h, a.U, a.Ubk);
   }
@@ -809,8 +813,9 @@ struct HtBars {
 template <bool TRAIN>
 __global__ void __launch_bounds__(HT_THREADS, 2)
     head_tc_kernel(HeadParams p, HeadTcWeights w, const __grid_constant__ CUtensorMap tm_h,
-                   const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_wop, int n_btiles,
-                   int n_tiles_cap, float* __restrict__ wpartial) {
+                   const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_wop,
+                   const __grid_constant__ CUtensorMap tm_dpb, int n_btiles, int n_tiles_cap,
+                   float* __restrict__ wpartial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   HtBars* bars = reinterpret_cast<HtBars*>(smem + HT_BARS);
@@ -881,6 +886,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           mbar_wait(&bars->dp_full, n & 1);
           HEAD_TRACE(0, n, 2);
           tcgen05_fence_after();
+          // the staged dLoss/dpred tile also goes to HBM as it is (128 x 64 B, SW64): the backward recurrence adds
+          // dpred (Wo gamma inv)^T for its own hidden units on its tensor cores
+          tma_store_2d(&tm_dpb, smem + HT_DP, 0, (t * n_tiles_cap + bt) * 128);
+          bulk_commit_group();
           const uint64_t da = make_smem_desc(smem_u32(smem + HT_DP), 0, 512, LAYOUT_SW64);
           umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP), 0, 512, LAYOUT_SW64), idesc_y, 0);
           umma_commit(&bars->dy_full[0]);
@@ -902,10 +911,14 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           HEAD_TRACE(0, n, 3);
           tcgen05_fence_after();
           umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP + 8192), 0, 512, LAYOUT_SW64), idesc_y, 0);
+          bulk_wait_group_read0();          // the store has read the dpred tile before the rows may rewrite it
           umma_commit(&bars->dy_full[1]);
         }
       }
-      if (TRAIN) umma_commit(&bars->w_done);
+      if (TRAIN) {
+        umma_commit(&bars->w_done);
+        bulk_wait_group0();
+      }
     }
   } else {
     const int m = tid - 32;                 // row of the tile
@@ -1264,6 +1277,7 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
   m.WoTp = reinterpret_cast<__nv_bfloat16*>(take(TC_OPAD * H * 2));
   m.Wop = reinterpret_cast<__nv_bfloat16*>(take(H * 32 * 2));
+  m.WoSp = reinterpret_cast<__nv_bfloat16*>(take(H * 32 * 2));
   m.bop = reinterpret_cast<float*>(take(TC_OPAD * 4));
   m.head_ctas = 148 * 2;
   m.head_wctas = 148 * 2;
@@ -1278,12 +1292,13 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
     m.dc = nullptr;
     m.pexch = reinterpret_cast<__nv_bfloat16*>(take(((B + 127) / 128) * 2 * 16 * 128 * 64 * 2));
     m.dpred = reinterpret_cast<float*>(take(B * T * TC_OPAD * 4));
+    m.dpb = reinterpret_cast<__nv_bfloat16*>(take(T * ((B + 127) / 128) * 128 * 32 * 2));
     m.head_wpart = reinterpret_cast<float*>(take((size_t)m.head_wctas * HWG_PART * 4));
     m.wg_part_elems = (size_t)64 * 384 * 1024;
     m.wg_part = reinterpret_cast<float*>(take(m.wg_part_elems * 4));
   } else {
     m.gates = nullptr; m.cst = nullptr; m.dz = nullptr; m.dhout = nullptr; m.dc = nullptr; m.wg_part = nullptr;
-    m.dpred = nullptr; m.head_wpart = nullptr; m.pexch = nullptr;
+    m.dpred = nullptr; m.head_wpart = nullptr; m.pexch = nullptr; m.dpb = nullptr;
     m.wg_part_elems = 0;
   }
   const int64_t I = c.n_inputs, O = c.n_outputs;
@@ -1309,6 +1324,11 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if ((rc = make_map_2d(&m.tm_h128, m.xh, xh_row, B, xh_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_wot, m.WoTp, TC_H, TC_OPAD, TC_H * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_wop, m.Wop, 32, TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&m.tm_wos, m.WoSp, 32, TC_H, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if (m.dpb &&
+      (rc = make_map_2d(&m.tm_dpb, m.dpb, 32, (uint64_t)m.T * ((m.maxB + 127) / 128) * 128, 64, 32, 128,
+                        CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HROWS_SMEM));
@@ -1358,7 +1378,7 @@ static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   a.W = params + m.oW; a.U = params + m.oU; a.bias = params + m.ob;
   a.Wo = params + m.oWo; a.bo = params + m.obo; a.gamma = params + m.ogamma; a.beta = params + m.obeta;
   a.mean = params + m.omean; a.var = params + m.ovar;
-  a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.Wop = m.Wop; a.biasp = m.biasp; a.bop = m.bop;
+  a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.Wop = m.Wop; a.WoSp = m.WoSp; a.biasp = m.biasp; a.bop = m.bop;
   pack_all_kernel<<<a.nb_w + a.nb_h + a.nb_u, 256, 0, s>>>(a);
   LFMQ_LAUNCH_CHECK();
   st.weights_dirty = 0;
@@ -1465,7 +1485,7 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   int n_wcta = m.head_wctas;
   if (train) {
     if (use_tc) {
-      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, n_btiles,
+      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, m.tm_dpb, n_btiles,
                                                              n_tiles_cap, m.head_wpart);
       LFMQ_LAUNCH_CHECK();
       n_wcta = grid;
@@ -1490,7 +1510,7 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
     }
   } else {
     if (use_tc)
-      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, n_btiles,
+      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, m.tm_wop, n_btiles,
                                                               n_tiles_cap, nullptr);
     else
       head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
@@ -1533,7 +1553,8 @@ int tc_forward(TcState& st, const lfmq_config& c, const float* params, const flo
   return 0;
 }
 
-int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, cudaStream_t s);
+int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, bool fused,
+                     cudaStream_t s);
 
 int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* grads, const float* x, const float* y,
                 int B, int64_t row0, int64_t step, const float* denom, float* tail, cudaStream_t s) {
@@ -1549,7 +1570,8 @@ int tc_backward(TcState& st, const lfmq_config& c, const float* params, float* g
   st.prof->begin(LFMQ_REGION_HEAD, s);
   if ((rc = tc_run_head(st, c, params, grads, y, B, row0, step, denom, nullptr, tail, true, s))) return rc;
   st.prof->end(LFMQ_REGION_HEAD, s);
-  return tc_backward_impl(st, c, params, grads, B, s);
+  // the tensor-core head (no dropout) leaves dLoss/dpred tiles for the backward kernel to expand on its own MMAs
+  return tc_backward_impl(st, c, params, grads, B, /*fused=*/!(c.train && c.dropout > 0.f), s);
 }
 
 }  // namespace lfmq
@@ -1587,17 +1609,25 @@ constexpr int BWD_THREADS = 320;   // producer + MMA + 2 sets of 4 pointwise war
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
 constexpr uint32_t SB_R = 163840;               // 3 foreign slices x [128 x 128 B]
-constexpr uint32_t SB_BARS = 212992;
+constexpr uint32_t SB_DPB = 212992;             // FUSED: dLoss/dpred tile of one step [128 x 64 B], SW64
+constexpr uint32_t SB_WOS = 221184;             // FUSED: (Wo gamma inv) rows of this CTA's 64 hidden units [64 x 64 B], SW64
+constexpr uint32_t SB_BARS = 225280;
 constexpr uint32_t BWD_SMEM = SB_BARS + 256 + 1024;
 
 struct BwdBars {
   uint64_t w_full, a_full[2], a_empty[2], acc_full[2], recv_full, recv_free, exp_ready;
+  uint64_t dpb_full, dpb_free;   // FUSED: the dpred tile has landed / the MMA reading it has completed
   uint32_t tmem_base;
 };
 
+// FUSED (no dropout in the head): dLoss/dh of the head is not read from HBM.  With dy = dpred Wo^T it equals
+// dpred (Wo gamma inv)^T; the MMA warp adds that product for this CTA's 64 hidden units (two M128 x N64 x K16 MMAs per
+// step on the 8 KB dpred tile) into the accumulator whose own slice the pointwise warps read anyway.
+template <bool FUSED>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     lstm_bwd_tc_kernel(BwdParams p, const __grid_constant__ CUtensorMap tm_ubk,
-                       const __grid_constant__ CUtensorMap tm_px, const __grid_constant__ CUtensorMap tm_dzst) {
+                       const __grid_constant__ CUtensorMap tm_px, const __grid_constant__ CUtensorMap tm_dzst,
+                       const __grid_constant__ CUtensorMap tm_dpb, const __grid_constant__ CUtensorMap tm_wos) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   BwdBars* bars = reinterpret_cast<BwdBars*>(smem + SB_BARS);
@@ -1616,6 +1646,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     mbar_init(&bars->recv_full, 1);
     mbar_init(&bars->recv_free, 1);
     mbar_init(&bars->exp_ready, BWD_NC - 1);
+    mbar_init(&bars->dpb_full, 1);
+    mbar_init(&bars->dpb_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
@@ -1629,13 +1661,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
     // (an L2 prefetch of the saved activations two steps ahead was tried here and made the kernel 25 % slower)
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->w_full, 131072);
+      mbar_arrive_expect_tx(&bars->w_full, 131072 + (FUSED ? 4096 : 0));
       for (int jb = 0; jb < 4; ++jb) tma_load_2d(smem + SB_U + jb * 32768, &tm_ubk, &bars->w_full, jb * 64, rank * 256);
+      if (FUSED) tma_load_2d(smem + SB_WOS, &tm_wos, &bars->w_full, 0, rank * 64);
     }
-    uint32_t n_er = 0;
+    uint32_t n_er = 0, n_dp = 0;
+    // dpred tile of time step td into the single staging buffer, once the MMA that read the previous one is done
+    auto load_dpred = [&](int tile, int td) {
+      if (n_dp > 0) mbar_wait(&bars->dpb_free, (n_dp - 1) & 1);
+      ++n_dp;
+      mbar_arrive_expect_tx(&bars->dpb_full, 8192);
+      tma_load_2d(smem + SB_DPB, &tm_dpb, &bars->dpb_full, 0, (td * p.n_tiles_cap + min(tile, p.n_tiles_cap - 1)) * 128);
+    };
     for (int it = 0; it < p.n_iters; ++it) {
       const int tile = it * p.n_clusters + cid;
+      if (FUSED && lane == 0) load_dpred(tile, T - 1);
       for (int t = T - 1; t >= 0; --t) {
+        if (FUSED && lane == 0 && t > 0) load_dpred(tile, t - 1);      // for the MMA appended to this step
         if (lane == 0 && t <= T - 2) {               // step t consumes the partials exported after step t+1
           mbar_wait_cluster(&bars->exp_ready, (n_er) & 1);
           mbar_wait(&bars->recv_free, (n_er++) & 1);    // own epilogue is done reading the previous slices
@@ -1656,9 +1698,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256, false, false);
+      const uint32_t idesc_dy = make_idesc_bf16(128, 64, false, false);
       mbar_wait(&bars->w_full, 0);
       uint32_t gs = 0;      // global step counter
+      uint32_t n_dpu = 0;   // dpred tiles consumed
+      // dpred(td) (Wo gamma inv)^T for this CTA's 64 hidden units into `dst` (own columns of an accumulator buffer)
+      auto dy_mma = [&](uint32_t dst, bool accumulate) {
+        mbar_wait(&bars->dpb_full, (n_dpu++) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k16 = 0; k16 < 2; ++k16) {
+          const uint64_t da = make_smem_desc(smem_u32(smem + SB_DPB) + k16 * 32, 0, 512, LAYOUT_SW64);
+          const uint64_t db = make_smem_desc(smem_u32(smem + SB_WOS) + k16 * 32, 0, 512, LAYOUT_SW64);
+          umma_f16(dst, da, db, idesc_dy, (accumulate || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars->dpb_free);
+      };
       for (int it = 0; it < p.n_iters; ++it) {
+        if (FUSED) {        // dLoss/dh of the head for the tile's first step (t = T-1): nothing recurrent to add to yet
+          const uint32_t pb = (gs + 1) & 1;
+          dy_mma(tmem + pb * 256 + rank * 64, false);
+          umma_commit(&bars->acc_full[pb]);
+        }
         for (int t = T - 1; t >= 0; --t, ++gs) {
           const uint32_t acc = tmem + (gs & 1) * 256;
           for (int jb = 0; jb < 4; ++jb) {
@@ -1683,6 +1744,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             bulk_wait_group_read0();             // the store has read the stage (well inside the MMAs' own time)
             umma_commit(&bars->a_empty[st]);
           }
+          if (FUSED && t > 0) dy_mma(acc + rank * 64, true);      // head part of dLoss/dh_{t-1}, read as `rec` next step
           umma_commit(&bars->acc_full[gs & 1]);
         }
       }
@@ -1700,6 +1762,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     const int sw = m & 7;
     float dc[32];
     uint32_t gs = 0, n_rf = 0;
+    uint32_t caf[2] = {0, 0};                // completed phases of acc_full[b] (mirrors the MMA warp's commit sequence)
     // inputs of this set's two chunks of one step (slot ci): loaded ahead of the exchange they do not depend on
     uint32_t gi[2][8], gf[2][8], gg[2][8], go[2][8], dhp[2][8], ct[2][8], cp[2][8];
     const long tstride = (long)p.n_tiles_cap * 8 * 4 * 2 * 32 * 16;   // cst elements per time step
@@ -1715,8 +1778,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         ld_global_v8(grow + (1 * 2 + hb) * 512, gf[ci]);
         ld_global_v8(grow + (2 * 2 + hb) * 512, gg[ci]);
         ld_global_v8(grow + (3 * 2 + hb) * 512, go[ci]);
-        ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16,
-                     dhp[ci]);
+        if (!FUSED)
+          ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16,
+                       dhp[ci]);
         ld_global_v8(crow, ct[ci]);
         if (t > 0) {
           ld_global_v8(crow - tstride, cp[ci]);
@@ -1739,6 +1803,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       for (int j = 0; j < 32; ++j) dc[j] = 0.f;
       load_chunk(0, tile, valid, T - 1);
       load_chunk(1, tile, valid, T - 1);
+      if (FUSED) {                             // the head's dLoss/dh_{T-1} for the own slice is in the accumulator
+        const uint32_t pb = (gs + 1) & 1;
+        mbar_wait(&bars->acc_full[pb], caf[pb] & 1);
+        ++caf[pb];
+      }
       for (int t = T - 1; t >= 0; --t, ++gs) {
         const bool has_rec = t < T - 1;
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
@@ -1748,14 +1817,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         for (int ci = 0; ci < 2; ++ci) {
           const int jb = 2 * ci + set;
           float rec[16];
-          if (has_rec) {
+          if (has_rec || FUSED) {
             uint32_t vr[16];
+            if (!has_rec) tcgen05_fence_after();
             tmem_ld_32x32b_x16(acc_prev + lane_addr + rank * 64 + jb * 16, vr);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) rec[j] = __uint_as_float(vr[j]);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
+            for (int d = 0; d < 3 && has_rec; ++d) {
               const uint8_t* rs = smem + SB_R + d * 16384 + m * 128;
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
@@ -1778,7 +1848,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const uint32_t i2 = gi[ci][e], f2 = gf[ci][e], g2 = gg[ci][e], o2 = go[ci][e];
-            const uint32_t dh2 = add_bf16x2(dhp[ci][e], pack_bf16x2(rec[2 * e], rec[2 * e + 1]));
+            const uint32_t dh2 = FUSED ? pack_bf16x2(rec[2 * e], rec[2 * e + 1])
+                                       : add_bf16x2(dhp[ci][e], pack_bf16x2(rec[2 * e], rec[2 * e + 1]));
             const uint32_t tc2 = tanh_bf16x2(ct[ci][e]);
             const uint32_t omtc2 = fma_bf16x2(neg_bf16x2(tc2), tc2, BF16X2_ONE);        // 1 - tanh(c)^2
             const uint32_t t1 = mul_bf16x2(mul_bf16x2(dh2, o2), omtc2);                 // dh * o * (1 - tc^2)
@@ -1823,7 +1894,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
-          mbar_wait(&bars->acc_full[gs & 1], (gs >> 1) & 1);
+          mbar_wait(&bars->acc_full[gs & 1], caf[gs & 1] & 1);
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 3);
           tcgen05_fence_after();
           const uint32_t acc = tmem + (gs & 1) * 256 + lane_addr;
@@ -1850,6 +1921,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
           }
         }
+        ++caf[gs & 1];                         // the MMA warp commits acc_full[gs & 1] every step, also at t = 0
       }
     }
   }
@@ -1978,11 +2050,13 @@ __global__ void wgrad_reduce_kernel(int S, int I, const float* __restrict__ part
   *dst = s;
 }
 
-int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, cudaStream_t s) {
+int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, float* grads, int B, bool fused,
+                     cudaStream_t s) {
   TcImpl& m = *st.impl;
   int rc;
   if (!m.bwd_ready) {
-    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    LFMQ_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     LFMQ_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     if ((rc = make_map_2d(&m.tm_ubk, m.Ubk, 256, 4 * TC_H, 512, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     const uint64_t px_rows = (uint64_t)((m.maxB + 127) / 128) * 2 * 16 * 128;
@@ -1999,7 +2073,7 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
     qc.attrs = qa;
     qc.numAttrs = 1;
     int ncl = 0;
-    LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&ncl, lstm_bwd_tc_kernel, &qc));
+    LFMQ_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&ncl, lstm_bwd_tc_kernel<true>, &qc));
     if (ncl < 1) {
       LFMQ_SET_ERR("no 4-CTA cluster of the backward kernel fits on this device");
       return LFMQ_ERR_UNSUPPORTED;
@@ -2042,7 +2116,10 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
       const uint32_t box[3] = {64, 1, 128};
       if ((rc = make_map_nd(&tm_dzst, m.dz, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
-    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, bp, m.tm_ubk, m.tm_px, tm_dzst));
+    if (fused)
+      LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel<true>, bp, m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos));
+    else
+      LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel<false>, bp, m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos));
     g_launches++;
     if (want_btrace) {
       long long h[3 * 16 * 8];
