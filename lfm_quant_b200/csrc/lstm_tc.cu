@@ -719,10 +719,11 @@ __global__ void __launch_bounds__(128, 2) head_rows_kernel(HeadParams p, const _
 }
 
 // Tensor-core head (dropout off): with y = a*h + b (BN inference affine) the Dense layer folds to
-//   pred = h * (diag(a) Wo) + (bo + b Wo),   dy = dpred * Wo^T,   dLoss/dh = dy * a
-// so both row-by-256 contractions become tcgen05 MMAs on the TMA-staged h tile (K-major SW128, exactly the layout the
-// recurrence uses): pred = 16 x (M128 N16 K16), dy = 2 x (M128 N128 K16) with dpred staged as a 128 x 32 bf16 tile.
-// Threads own one row each for the loss terms, the dgamma/dbeta column sums and the dLoss/dh stores.
+//   pred = h * (diag(a) Wo) + (bo + b Wo)
+// a tcgen05 MMA on the TMA-staged h tile (K-major SW128, exactly the layout the recurrence uses): 16 x (M128 N16 K16).
+// Threads own one row each for the loss terms and dpred, staged as a 128 x 32 bf16 tile (SW64).  Training: that tile
+// feeds h^T dpred (MN-major MMAs, accumulated in TMEM across tiles -> dWo, dgamma) and goes to HBM by TMA store for the
+// backward recurrence, which forms dLoss/dh = dpred (Wo a)^T on its own tensor cores; colsum(dpred) -> dbo, dbeta.
 struct HeadTcWeights {
   const __nv_bfloat16* WoTp;   // [16][256]  a_j * Wo[j][n]
   const __nv_bfloat16* Wop;    // [256][32]  Wo[j][k] (k < 16), zero padded
@@ -799,14 +800,14 @@ __global__ void __launch_bounds__(256) pack_all_kernel(PackArgs a) {
 
 constexpr uint32_t HT_TILE = 0;            // 4 k-blocks x [128 x 128 B]
 constexpr uint32_t HT_WOT = 65536;         // 4 k-blocks x [16 x 128 B]
-constexpr uint32_t HT_WOP = 73728;         // [256 x 64 B]
+// (73728 .. 90111: unused since dLoss/dh moved to the backward kernel; kept so the tile offsets stay 1024-aligned)
 constexpr uint32_t HT_DP = 90112;          // [128 x 64 B]
 constexpr uint32_t HT_BARS = 98304;
 constexpr int HT_SMEM = HT_BARS + 128 + 1024;
 constexpr int HT_THREADS = 160;            // warp 0: TMA + MMA issue, warps 1-4: one row per thread
 
 struct HtBars {
-  uint64_t wt_full, tile_full, pred_full, dp_full, dy_full[2], y0_free, tile_free, w_done;
+  uint64_t wt_full, tile_full, pred_full, dp_full, dp_free, tile_free, w_done;
   uint32_t tmem_base;
 };
 
@@ -836,9 +837,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
     mbar_init(&bars->tile_full, 1);
     mbar_init(&bars->pred_full, 1);
     mbar_init(&bars->dp_full, 128);
-    mbar_init(&bars->dy_full[0], 1);
-    mbar_init(&bars->dy_full[1], 1);
-    mbar_init(&bars->y0_free, 128);
+    mbar_init(&bars->dp_free, 1);
     mbar_init(&bars->tile_free, 128);
     mbar_init(&bars->w_done, 1);
     fence_mbar_init();
@@ -850,22 +849,19 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
   tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const uint32_t acc_p = tmem;             // 16 columns
-  const uint32_t acc_y = tmem + 32;        // 128 columns
   const uint32_t acc_w = tmem + 160;       // 2 x 16 columns: sum over this CTA's tiles of h^T dpred (rows = hidden unit)
   const int n_tiles = p.T * n_btiles;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->wt_full, 8192 + 16384);
+      mbar_arrive_expect_tx(&bars->wt_full, 8192);
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + HT_WOT + kb * 2048, &tm_wot, &bars->wt_full, kb * 64, 0);
-      tma_load_2d(smem + HT_WOP, &tm_wop, &bars->wt_full, 0, 0);
       mbar_wait(&bars->wt_full, 0);
       const uint32_t idesc_p = make_idesc_bf16(128, 16, false, false);
-      const uint32_t idesc_y = make_idesc_bf16(128, 128, false, false);
       uint32_t n = 0;
       for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++n) {
         const int t = ti / n_btiles, bt = ti % n_btiles;
-        if (n > 0) mbar_wait(&bars->tile_free, (n - 1) & 1);
+        if (n > 0) mbar_wait(TRAIN ? &bars->dp_free : &bars->tile_free, (n - 1) & 1);
         HEAD_TRACE(0, n, 0);
         mbar_arrive_expect_tx(&bars->tile_full, 65536);
         for (int kb = 0; kb < 4; ++kb)
@@ -890,11 +886,8 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           // dpred (Wo gamma inv)^T for its own hidden units on its tensor cores
           tma_store_2d(&tm_dpb, smem + HT_DP, 0, (t * n_tiles_cap + bt) * 128);
           bulk_commit_group();
-          const uint64_t da = make_smem_desc(smem_u32(smem + HT_DP), 0, 512, LAYOUT_SW64);
-          umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP), 0, 512, LAYOUT_SW64), idesc_y, 0);
-          umma_commit(&bars->dy_full[0]);
           // dWo' += h^T dpred: A = the h tile read MN-major (hidden unit = M), B = the dpred tile read MN-major,
-          // K = the 128 rows.  Issued before the second dy half so that dy_full[1] also covers these MMAs.
+          // K = the 128 rows.
           {
             const uint32_t idesc_w = make_idesc_bf16(128, 16, true, true);
 #pragma unroll
@@ -907,12 +900,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
                 umma_f16(acc_w + mb * 16, wa, wb, idesc_w, (n > 0 || k16 > 0) ? 1u : 0u);
               }
           }
-          mbar_wait(&bars->y0_free, n & 1);
+          bulk_wait_group_read0();          // the store has read the dpred tile
+          umma_commit(&bars->dp_free);      // ... and the h^T dpred MMAs are done with it and with the h tile
           HEAD_TRACE(0, n, 3);
-          tcgen05_fence_after();
-          umma_f16(acc_y, da, make_smem_desc(smem_u32(smem + HT_WOP + 8192), 0, 512, LAYOUT_SW64), idesc_y, 0);
-          bulk_wait_group_read0();          // the store has read the dpred tile before the rows may rewrite it
-          umma_commit(&bars->dy_full[1]);
         }
       }
       if (TRAIN) {
@@ -993,12 +983,13 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           if (TRAIN) accbo[k] += dp[k];
         }
         if (TRAIN) {
-          if (valid) {
+          if (valid && p.dpred) {        // fp32 copy: only the dropout path's SIMT weight-gradient kernel reads it
 #pragma unroll
             for (int k4 = 0; k4 < TC_OPAD; k4 += 4)
               *reinterpret_cast<float4*>(p.dpred + r * TC_OPAD + k4) = make_float4(dp[k4], dp[k4 + 1], dp[k4 + 2], dp[k4 + 3]);
           }
           // dpred row -> A operand tile [128 x 64 B], SWIZZLE_64B: chunk c of row m at m*64 + ((c ^ ((m>>1)&3)) << 4)
+          if (n > 0) mbar_wait(&bars->dp_free, (n - 1) & 1);     // MMAs and the TMA store are done with the previous tile
           uint8_t* drow = smem + HT_DP + mrow * 64;
           const int s64 = (mrow >> 1) & 3;
           *reinterpret_cast<uint4*>(drow + ((0 ^ s64) << 4)) =
@@ -1008,45 +999,12 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
           fence_proxy_async_smem();
           mbar_arrive(&bars->dp_full);
           if (tid == 32) HEAD_TRACE(1, n, 1);
-          __nv_bfloat16* dh_base = p.dhout + ((((long)t * n_tiles_cap + bt) * 4) * 4 + wq) * 4 * 32 * 16 + lane * 16;
-#pragma unroll 1
-          for (int hN = 0; hN < 2; ++hN) {
-            mbar_wait(&bars->dy_full[hN], n & 1);
-            if (tid == 32) HEAD_TRACE(1, n, 2 + 2 * hN);
-            tcgen05_fence_after();
-#pragma unroll 1
-            for (int g4 = 0; g4 < 4; ++g4) {                 // 32 columns per group
-              const int grp = hN * 4 + g4;
-              uint32_t dv[32];
-              tmem_ld_32x32b_x32(acc_y + lane_addr + g4 * 32, dv);
-              tmem_ld_wait();
-              // dLoss/dh = dy * gamma * inv.  The BatchNorm gradients need no per-tile reduction here: with
-              // dy = dpred Wo^T, sum_r dy[r][j] = sum_k Wo[j][k] colsum(dpred)[k] and sum_r dy[r][j] h[r][j] =
-              // sum_k Wo[j][k] (h^T dpred)[j][k] -- both right-hand sides are already accumulated (dbo, and the
-              // tensor-core h^T dpred for dWo); head_fold_kernel finishes dgamma / dbeta from them.
-              if (valid) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  uint32_t pk[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int jj = hh * 16 + 2 * e;
-                    pk[e] = pack_bf16x2(__uint_as_float(dv[jj]) * bn_s[0][grp * 32 + jj],
-                                        __uint_as_float(dv[jj + 1]) * bn_s[0][grp * 32 + jj + 1]);
-                  }
-                  const int c16 = grp * 2 + hh;
-                  st_global_v8(dh_base + ((long)(c16 >> 2) * 4 * 4 + (c16 & 3)) * 32 * 16, pk);
-                }
-              }
-            }
-            tcgen05_fence_before();
-            if (tid == 32) HEAD_TRACE(1, n, 3 + 2 * hN);
-            if (hN == 0) mbar_arrive(&bars->y0_free);
-          }
+          // nothing else per tile: dLoss/dh is formed by the backward recurrence from the dpred tile (lstm_bwd_tc_kernel
+          // <FUSED>), dgamma / dbeta by head_fold_kernel from h^T dpred and colsum(dpred)
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(&bars->tile_free);
+      if (!TRAIN) mbar_arrive(&bars->tile_free);
     }
     if (p.y) {
       s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -1471,8 +1429,10 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   h.key.scale = 1.0f / (1.0f - c.dropout);
   h.row0 = row0;
   h.preds = preds;
-  h.dhout = train ? m.dhout : nullptr;
-  h.dpred = train ? m.dpred : nullptr;
+  // dhout / fp32 dpred are only produced on the dropout (SIMT) path; the tensor-core head leaves bf16 dpred tiles (dpb)
+  const bool simt_train = train && c.train && c.dropout > 0.f;
+  h.dhout = simt_train ? m.dhout : nullptr;
+  h.dpred = simt_train ? m.dpred : nullptr;
   h.partial = m.head_part;
   const int n_btiles = (B + 127) / 128;
   const int n_tiles_cap = (m.maxB + 127) / 128;
