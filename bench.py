@@ -281,10 +281,12 @@ def main():
 
         gate_ms = fwd_ms + bwd_ms + wg_ms
         achieved = tf(flop_fwd + flop_bwd + flop_wg, gate_ms)
-        # algorithmic HBM bytes of the backward recurrence (the longest kernel): saved gates + 2x cell states + dLoss/dh
-        # read, dz written (bf16)
-        bwd_bytes = B * T * (4 * H * 2 + 2 * H * 2 + H * 2) + B * T * 4 * H * 2
-        head_bytes = B * T * (H * 2 + O * 4) + (B * T * (H * 2 + O * 4) if args.precision == 'bf16' else 0)
+        # algorithmic HBM bytes of the backward recurrence (the longest kernel): saved gates + 2x cell states + dpred
+        # tile read, dz written (bf16)
+        # (bf16, no dropout: dLoss/dh is not materialised -- the head leaves 64-byte bf16 dpred rows and the backward
+        # kernel expands them on its tensor cores)
+        bwd_bytes = B * T * (4 * H * 2 + 2 * H * 2 + 64) + B * T * 4 * H * 2
+        head_bytes = B * T * (H * 2 + O * 4) + B * T * 64
         # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) comes ONLY from a committed
         # `ncu --set full` capture of these kernels: profiles/r01_ncu_traffic.json is written by tools/ncu_traffic.py from
         # the .ncu-rep and names the capture it was parsed from.  No file (or a kernel missing from it) -> null.
