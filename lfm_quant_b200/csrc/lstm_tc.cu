@@ -13,8 +13,10 @@
 //   dz    bf16 [maxB][T+1][4H]    gate pre-activation gradients (row T stays zero); columns in the order the
 //                                 backward kernel stages them as its A operand, [16-unit block][gate][16], so that a
 //                                 chunk goes out with one TMA store; only the weight-gradient GEMM reads it
-//   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dLoss/dh from the head (after BN/dropout
-//                                 backward), already in the backward kernel's per-thread SoA order
+//   dpb   bf16 [T][tiles][128][32]  dLoss/dpred tiles (cols >= 16 zero): written by the tensor-core head as it stages
+//                                 them, expanded to dLoss/dh by the backward kernel's own MMAs (no dropout)
+//   dhout bf16 [T][tiles][4 ranks][4 warps][4 chunks][32 lanes][16]   dropout > 0 only: dLoss/dh from the SIMT head
+//                                 (after BN/dropout backward), already in the backward kernel's per-thread SoA order
 //
 // Forward recurrence = ONE persistent kernel (lstm_fwd_tc_kernel): clusters of 4 CTAs, one 128-row batch tile per
 // cluster, all clusters co-resident.  CTA r keeps the weight slice of hidden units [64r, 64r+64) (all four gates,
