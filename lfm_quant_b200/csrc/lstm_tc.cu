@@ -123,8 +123,8 @@ struct TcImpl {
   float *biasp, *head_part, *head_wpart, *dpred, *wg_part, *dc;
   size_t head_part_elems, wg_part_elems;
   CUtensorMap tm_h, tm_x, tm_u, tm_w;          // forward
-  CUtensorMap tm_h128, tm_wot, tm_wop;         // head: 128-row h tiles, folded head weights
-  __nv_bfloat16 *WoTp, *Wop;
+  CUtensorMap tm_h128, tm_wot;                 // head: 128-row h tiles, folded head weights
+  __nv_bfloat16* WoTp;
   __nv_bfloat16* WoSp;                         // [256][32]  Wo[j][k] * gamma_j * inv_j (k < 16), zero padded
   __nv_bfloat16* dpb;                          // [T][tiles][128][32] bf16 dLoss/dpred tiles (cols >= 16 zero)
   CUtensorMap tm_wos, tm_dpb;
@@ -728,15 +728,14 @@ __global__ void __launch_bounds__(128, 2) head_rows_kernel(HeadParams p, const _
 // backward recurrence, which forms dLoss/dh = dpred (Wo a)^T on its own tensor cores; colsum(dpred) -> dbo, dbeta.
 struct HeadTcWeights {
   const __nv_bfloat16* WoTp;   // [16][256]  a_j * Wo[j][n]
-  const __nv_bfloat16* Wop;    // [256][32]  Wo[j][k] (k < 16), zero padded
   const float* bop;            // [16]       bo + sum_j b_j Wo[j][k]
 };
 
 __device__ __forceinline__ void pack_head_body(int bid, int O, const float* __restrict__ Wo, const float* __restrict__ bo,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                 __nv_bfloat16* __restrict__ WoTp, __nv_bfloat16* __restrict__ Wop,
-                                 __nv_bfloat16* __restrict__ WoSp, float* __restrict__ bop) {
+                                 __nv_bfloat16* __restrict__ WoTp, __nv_bfloat16* __restrict__ WoSp,
+                                 float* __restrict__ bop) {
   const int idx = bid * blockDim.x + threadIdx.x;
   if (idx < TC_OPAD * TC_H) {
     const int n = idx / TC_H, j = idx % TC_H;
@@ -745,7 +744,6 @@ __device__ __forceinline__ void pack_head_body(int bid, int O, const float* __re
   }
   if (idx < TC_H * 32) {
     const int j = idx / 32, k = idx % 32;
-    Wop[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
     WoSp[idx] = __float2bfloat16(k < O ? Wo[j * O + k] * gamma[j] / sqrtf(var[j] + eps) : 0.f);
   }
   // folded bias: block k (< 16) reduces over its 256 threads = 256 hidden units
@@ -785,7 +783,7 @@ struct PackArgs {
   int I, O, nb_w, nb_h, nb_u;
   float eps;
   const float *W, *U, *bias, *Wo, *bo, *gamma, *beta, *mean, *var;
-  __nv_bfloat16 *Up, *Wp, *Ubk, *WoTp, *Wop, *WoSp;
+  __nv_bfloat16 *Up, *Wp, *Ubk, *WoTp, *WoSp;
   float *biasp, *bop;
 };
 
@@ -794,7 +792,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(PackArgs a) {
   if (bid < a.nb_w) {
     pack_weights_body(bid, a.I, a.W, a.U, a.bias, a.Up, a.Wp, a.biasp);
   } else if (bid < a.nb_w + a.nb_h) {
-    pack_head_body(bid - a.nb_w, a.O, a.Wo, a.bo, a.gamma, a.beta, a.mean, a.var, a.eps, a.WoTp, a.Wop, a.WoSp, a.bop);
+    pack_head_body(bid - a.nb_w, a.O, a.Wo, a.bo, a.gamma, a.beta, a.mean, a.var, a.eps, a.WoTp, a.WoSp, a.bop);
   } else {
     pack_ubk_body(bid - a.nb_w - a.nb_h, a.U, a.Ubk);
   }
@@ -816,8 +814,7 @@ struct HtBars {
 template <bool TRAIN>
 __global__ void __launch_bounds__(HT_THREADS, 2)
     head_tc_kernel(HeadParams p, HeadTcWeights w, const __grid_constant__ CUtensorMap tm_h,
-                   const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_wop,
-                   const __grid_constant__ CUtensorMap tm_dpb, int n_btiles, int n_tiles_cap,
+                   const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_dpb, int n_btiles, int n_tiles_cap,
                    float* __restrict__ wpartial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1236,7 +1233,6 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   m.Ubk = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
   m.biasp = reinterpret_cast<float*>(take(4 * H * 4));
   m.WoTp = reinterpret_cast<__nv_bfloat16*>(take(TC_OPAD * H * 2));
-  m.Wop = reinterpret_cast<__nv_bfloat16*>(take(H * 32 * 2));
   m.WoSp = reinterpret_cast<__nv_bfloat16*>(take(H * 32 * 2));
   m.bop = reinterpret_cast<float*>(take(TC_OPAD * 4));
   m.head_ctas = 148 * 2;
@@ -1283,7 +1279,6 @@ int tc_init(TcState& st, const lfmq_config& c) {
   if ((rc = make_map_2d(&m.tm_x, m.xh, xh_row, B, xh_row * 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&m.tm_h128, m.xh, xh_row, B, xh_row * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map_2d(&m.tm_wot, m.WoTp, TC_H, TC_OPAD, TC_H * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&m.tm_wop, m.Wop, 32, TC_H, 64, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_map_2d(&m.tm_wos, m.WoSp, 32, TC_H, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if (m.dpb &&
       (rc = make_map_2d(&m.tm_dpb, m.dpb, 32, (uint64_t)m.T * ((m.maxB + 127) / 128) * 128, 64, 32, 128,
@@ -1338,7 +1333,7 @@ static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   a.W = params + m.oW; a.U = params + m.oU; a.bias = params + m.ob;
   a.Wo = params + m.oWo; a.bo = params + m.obo; a.gamma = params + m.ogamma; a.beta = params + m.obeta;
   a.mean = params + m.omean; a.var = params + m.ovar;
-  a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.Wop = m.Wop; a.WoSp = m.WoSp; a.biasp = m.biasp; a.bop = m.bop;
+  a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.WoSp = m.WoSp; a.biasp = m.biasp; a.bop = m.bop;
   pack_all_kernel<<<a.nb_w + a.nb_h + a.nb_u, 256, 0, s>>>(a);
   LFMQ_LAUNCH_CHECK();
   st.weights_dirty = 0;
@@ -1442,12 +1437,12 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   if (grid > m.head_ctas) grid = m.head_ctas;
   h.partial = m.head_part;
   HeadTcWeights hw;
-  hw.WoTp = m.WoTp; hw.Wop = m.Wop; hw.bop = m.bop;
+  hw.WoTp = m.WoTp; hw.bop = m.bop;
   const bool use_tc = !h.use_dropout;       // the BN fold into the head weights needs y = a*h + b
   int n_wcta = m.head_wctas;
   if (train) {
     if (use_tc) {
-      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, m.tm_dpb, n_btiles,
+      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_dpb, n_btiles,
                                                              n_tiles_cap, m.head_wpart);
       LFMQ_LAUNCH_CHECK();
       n_wcta = grid;
@@ -1472,7 +1467,7 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
     }
   } else {
     if (use_tc)
-      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wop, m.tm_wop, n_btiles,
+      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wot, n_btiles,
                                                               n_tiles_cap, nullptr);
     else
       head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
