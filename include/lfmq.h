@@ -126,7 +126,10 @@ int32_t lfmq_mask_count(lfmq_handle h, const float* y, int32_t B, float* out_dev
 
 /* First half of Train._train_step_point (train.py:181-192): forward, loss, BPTT.  Fills the flat
  * gradient buffer (+ its 4-float tail).  denom_dev = device {B_global, mask_count_global} or NULL to use
- * this call's own batch.  With N ranks the host all-reduces grads[0 : n_trainable+2] (SUM) next. */
+ * this call's own batch.  With N ranks the host all-reduces grads[0 : n_trainable+2] (SUM) next.
+ * Stream semantics: everything is ordered on `stream`.  A LFMQ_PREC_BF16 handle additionally runs one prefetch-only
+ * helper kernel on a library-owned non-blocking stream, forked from and joined back into `stream` with events inside
+ * this call (it touches no caller-visible data; environment LFMQ_BWD_PREFETCH=0 disables it). */
 int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, int64_t row0, int64_t step,
                       const float* denom_dev, void* stream);
 
