@@ -423,7 +423,7 @@ def gru_backward(dh_out, cache, need_dx):
 
 
 def _trunk(params, x, *, num_layers, dropout, recurrent_dropout, training, seed, step, row0, bn_mean, bn_var,
-           rnn_cell):
+           rnn_cell, layer0=0):
     """The recurrent stack shared by RNNPointEstimate and RNNUqRangeEstimate: per layer LSTM|GRU ->
     BatchNormalization (inference-mode affine, SURVEY App. B #1) -> Dropout."""
     B, T, _ = x.shape
@@ -437,13 +437,13 @@ def _trunk(params, x, *, num_layers, dropout, recurrent_dropout, training, seed,
         var = np.ones(H, dtype=dt) if bn_var is None else bn_var[l].astype(dt)
         rmask = None
         if training and recurrent_dropout > 0.0:
-            rmask = dropout_mask(seed, step, 2 * l + 1, row0, B, H, recurrent_dropout, dtype=dt.type)
+            rmask = dropout_mask(seed, step, 2 * (layer0 + l) + 1, row0, B, H, recurrent_dropout, dtype=dt.type)
         hs, lc = (lstm_forward if rnn_cell == 'lstm' else gru_forward)(cur, W, U, b, rmask)
         inv = (1.0 / np.sqrt(var + dt.type(BN_EPS))).astype(dt)
         y = gamma * (hs - mean) * inv + beta
         dmask = None
         if training and dropout > 0.0:
-            dmask = dropout_mask(seed, step, 2 * l, row0, B, T * H, dropout, dtype=dt.type).reshape(B, T, H)
+            dmask = dropout_mask(seed, step, 2 * (layer0 + l), row0, B, T * H, dropout, dtype=dt.type).reshape(B, T, H)
             y = y * dmask
         caches.append((lc, hs, mean, inv, gamma, dmask))
         cur = y
@@ -594,6 +594,102 @@ def backward_uq(dpred, dvar, fcache, *, num_layers, rnn_cell='lstm'):
     grads[5 * num_layers + 3] = da.reshape(B * T, O).sum(axis=0)
     dy = dpred @ Wt.T + da @ Wv.T
     return _trunk_backward(dy, caches, grads, num_layers=num_layers, rnn_cell=rnn_cell)
+
+
+# --------------------------------------------------------------------------------------
+# forecast_steps > 1 (rnn_point_estimate.py:109-150, model_base_class.py:18-51).  Oracle only so far: the CUDA path
+# refuses forecast_steps != 1; this is the checker the next build step is written against.
+# --------------------------------------------------------------------------------------
+def forecast_param_names(num_layers, forecast_steps, rnn_cell='lstm'):
+    """trainable_variables order: the trunk and OUTPUT_1 as for forecast_steps = 1, then per extra step s one
+    recurrent layer (numbered on from the trunk, :129), its BatchNormalization and the Dense OUTPUT_{s+1} (:150)."""
+    names = param_names(num_layers, rnn_cell)
+    for s in range(1, forecast_steps):
+        l = num_layers + s
+        names += ['%s_%d/kernel' % (rnn_cell, l), '%s_%d/recurrent_kernel' % (rnn_cell, l), '%s_%d/bias' % (rnn_cell, l),
+                  'batch_normalization_%d/gamma' % (l - 1), 'batch_normalization_%d/beta' % (l - 1),
+                  'OUTPUT_%d/kernel' % (s + 1), 'OUTPUT_%d/bias' % (s + 1)]
+    return names
+
+
+def init_forecast_params(num_layers, n_inputs, n_outputs, num_hidden, forecast_steps, init_scale=1.0, seed=521,
+                         dtype=np.float32, rnn_cell='lstm'):
+    out = init_params(num_layers, n_inputs, n_outputs, num_hidden, init_scale, seed, dtype, rnn_cell)
+    for s in range(1, forecast_steps):
+        extra = init_params(1, n_inputs, n_outputs, num_hidden, init_scale, seed + 7 * s, dtype, rnn_cell)
+        out += extra                      # one recurrent layer on the raw feature width + its head
+    return out
+
+
+def forward_forecast(params, x, *, num_layers, forecast_steps, dropout=0.0, recurrent_dropout=0.0, training=False,
+                     seed=0, step=0, row0=0, rnn_cell='lstm'):
+    """model(inp) -> [pred_1, ..., pred_S].  Step s >= 2 runs ONE new recurrent layer over the input window shifted by
+    one: the first time step is dropped and [pred_{s-1}[:, -1, :], aux features of the LAST ORIGINAL time step]
+    (model_base_class.py:18-41: the last n_inputs - n_outputs columns) is appended (rnn_point_estimate.py:113-124)."""
+    B, T, F = x.shape
+    O = params[5 * num_layers].shape[1]
+    n0 = 5 * num_layers + 2
+    preds, caches = [], []
+    p0, fc0 = forward(params[:n0], x, num_layers=num_layers, dropout=dropout, recurrent_dropout=recurrent_dropout,
+                      training=training, seed=seed, step=step, row0=row0, rnn_cell=rnn_cell)
+    preds.append(p0)
+    caches.append(fc0)
+    aux = x[:, -1:, O:]
+    prev_input = x
+    for s in range(1, forecast_steps):
+        new_step = np.concatenate([preds[-1][:, -1:, :], aux], axis=2)
+        cur_input = np.concatenate([prev_input, new_step], axis=1)[:, 1:, :]
+        prev_input = cur_input
+        ps = params[n0 + 7 * (s - 1):n0 + 7 * s]
+        # the Philox stream index continues after the trunk's layers: layer num_layers + s - 1
+        cur, lc = _trunk(ps[:5], cur_input, num_layers=1, dropout=dropout, recurrent_dropout=recurrent_dropout,
+                         training=training, seed=seed, step=step, row0=row0, bn_mean=None, bn_var=None,
+                         rnn_cell=rnn_cell, layer0=num_layers + s - 1)
+        preds.append(cur @ ps[5] + ps[6])
+        caches.append((lc, cur, ps[5]))
+    return preds, (caches, num_layers, forecast_steps, O)
+
+
+def loss_forecast(y_trues, preds, weights, **kw):
+    """Losses.weight_adjusted_mse (losses.py:19-53): sum_s w_s * loss_s, sum_s w_s * mse_s."""
+    loss = mse = 0.0
+    dpreds = []
+    for y, p, w in zip(y_trues, preds, weights):
+        l, m, dp, _ = loss_point_estimate(y.astype(p.dtype), p, **kw)
+        loss += w * l
+        mse += w * m
+        dpreds.append(w * dp)
+    return loss, mse, dpreds
+
+
+def backward_forecast(dpreds, fcache, *, rnn_cell='lstm'):
+    """Gradients in forecast_param_names order.  The window of step s holds, at position T-1-j, the appended step of
+    forecast s-j (j = 0..s-1), whose first O columns are pred_{s-j}[:, -1, :]: the input gradient of the extra layer
+    flows back into those earlier predictions' last time step."""
+    caches, num_layers, S, O = fcache
+    dpreds = [d.copy() for d in dpreds]
+    B, T, _ = dpreds[0].shape
+    extra = []
+    for s in range(S - 1, 0, -1):
+        lc, y_last, Wo = caches[s]
+        dp = dpreds[s]
+        H = Wo.shape[0]
+        g = [None] * 7
+        g[5] = y_last.reshape(B * T, H).T @ dp.reshape(B * T, O)
+        g[6] = dp.reshape(B * T, O).sum(axis=0)
+        dy = dp @ Wo.T
+        (lcache, hs, mean, inv, gamma, dmask) = lc[0]
+        if dmask is not None:
+            dy = dy * dmask
+        g[3] = np.sum(dy * (hs - mean) * inv, axis=(0, 1))
+        g[4] = np.sum(dy, axis=(0, 1))
+        dW, dU, db, dx = (lstm_backward if rnn_cell == 'lstm' else gru_backward)(dy * gamma * inv, lcache, need_dx=True)
+        g[0], g[1], g[2] = dW, dU, db
+        for j in range(s):                       # appended steps inside this window
+            dpreds[s - 1 - j][:, -1, :] += dx[:, T - 1 - j, :O]
+        extra = g + extra
+    g0 = backward(dpreds[0], caches[0], num_layers=num_layers, rnn_cell=rnn_cell)
+    return g0 + extra
 
 
 # --------------------------------------------------------------------------------------

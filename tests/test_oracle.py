@@ -377,3 +377,60 @@ def test_uq_loss_is_nan_with_a_padded_step_like_the_reference_formula():
     loss, uq0, mse0, dp, dv = orc.loss_uq_estimate(y, p, v, target_idx=1, target_lambda=0.5, rnn_lambda=0.7)
     assert np.isnan(loss) and np.isfinite(uq0) and np.isfinite(mse0)
     assert np.isnan(dp[0, 0]).all() and np.isnan(dv[0, 0]).all()
+
+
+# ---- forecast_steps > 1 (second half): rnn_point_estimate.py:109-150 -- oracle only so far ----
+def test_forecast_chain_window_construction_and_names():
+    B, T, F, O, H, L, S = 3, 4, 6, 2, 5, 1, 3
+    rng = np.random.RandomState(1)
+    P = orc.init_forecast_params(L, F, O, H, S, seed=5, dtype=np.float64)
+    names = orc.forecast_param_names(L, S)
+    assert len(P) == len(names) == 5 * L + 2 + 7 * (S - 1)
+    assert names[5 * L:5 * L + 2] == ['OUTPUT_1/kernel', 'OUTPUT_1/bias']
+    assert names[-7:] == ['lstm_3/kernel', 'lstm_3/recurrent_kernel', 'lstm_3/bias', 'batch_normalization_2/gamma',
+                          'batch_normalization_2/beta', 'OUTPUT_3/kernel', 'OUTPUT_3/bias']
+    x = rng.normal(size=(B, T, F))
+    preds, fc = orc.forward_forecast(P, x, num_layers=L, forecast_steps=S)
+    assert len(preds) == S and all(p.shape == (B, T, O) for p in preds)
+    # the window of step 2: first step dropped, [pred_1[:, -1], aux of the last ORIGINAL step] appended
+    win2 = np.concatenate([x[:, 1:], np.concatenate([preds[0][:, -1:, :], x[:, -1:, O:]], axis=2)], axis=1)
+    ref2, _ = orc.forward(P[5 * L + 2:5 * L + 2 + 7], win2, num_layers=1)
+    assert np.abs(ref2 - preds[1]).max() < 1e-12
+    win3 = np.concatenate([win2[:, 1:], np.concatenate([preds[1][:, -1:, :], x[:, -1:, O:]], axis=2)], axis=1)
+    ref3, _ = orc.forward(P[5 * L + 2 + 7:], win3, num_layers=1)
+    assert np.abs(ref3 - preds[2]).max() < 1e-12
+    # forecast_steps = 1 degenerates to the plain model
+    p1, _ = orc.forward_forecast(P[:5 * L + 2], x, num_layers=L, forecast_steps=1)
+    assert np.abs(p1[0] - preds[0]).max() == 0.0
+
+
+@pytest.mark.parametrize('cell', ['lstm', 'gru'])
+def test_forecast_chain_backward_finite_differences(cell):
+    B, T, F, O, H, L, S = 4, 5, 7, 3, 8, 2, 3            # H % 4 == 0: one Philox call yields 4 mask elements
+    rng = np.random.RandomState(2)
+    P = orc.init_forecast_params(L, F, O, H, S, seed=5, dtype=np.float64, rnn_cell=cell)
+    x = rng.normal(size=(B, T, F))
+    ys = [rng.normal(size=(B, T, O)) for _ in range(S)]
+    ys[1][0, :2] = 0.0
+    w = [1.0, 0.6, 0.3]
+    kw = dict(target_idx=1, target_lambda=0.5, rnn_lambda=0.7)
+    fkw = dict(num_layers=L, forecast_steps=S, rnn_cell=cell, training=True, dropout=0.2, recurrent_dropout=0.1, seed=3,
+               step=4, row0=8)
+
+    def loss_of(Q):
+        pr, fc = orc.forward_forecast(Q, x, **fkw)
+        l, m, dp = orc.loss_forecast(ys, pr, w, **kw)
+        return l, dp, fc
+
+    l0, dp, fc = loss_of(P)
+    g = orc.backward_forecast(dp, fc, rnn_cell=cell)
+    assert len(g) == len(P)
+    for k in range(len(P)):
+        assert g[k].shape == P[k].shape
+        for _ in range(3):
+            idx = tuple(rng.randint(s) for s in P[k].shape)
+            Qp, Qm = [q.copy() for q in P], [q.copy() for q in P]
+            Qp[k][idx] += 1e-6
+            Qm[k][idx] -= 1e-6
+            fd = (loss_of(Qp)[0] - loss_of(Qm)[0]) / 2e-6
+            assert abs(fd - g[k][idx]) < 1e-6 * max(1.0, abs(fd)), (k, idx)
