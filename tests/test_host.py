@@ -158,3 +158,52 @@ def test_initializer_families(fresh_flags):
         c.initializer = name
         k = Initializer(c).initial_weights(specs)[0]
         assert np.isfinite(k).all() and 0 < k.std() < 1
+
+
+def test_gru_initial_weights_follow_keras_defaults(fresh_flags):
+    """Keras GRU (reset_after=True): kernel by the configured initializer, orthogonal recurrent kernel, zero [2,3H] bias."""
+    c = base_config.get_configs(['--init_scale', '0.25', '--rnn_cell', 'gru'])
+    specs = list(zip(orc.param_names(1, 'gru'), orc.param_shapes(1, 8, 3, 12, 'gru')))
+    w = Initializer(c).initial_weights(specs)
+    assert w[0].shape == (8, 36) and np.abs(w[0]).max() <= 0.25
+    np.testing.assert_allclose(w[1] @ w[1].T, np.eye(12), atol=1e-5)
+    assert w[2].shape == (2, 36) and (w[2] == 0).all()
+
+
+def test_model_factory_knows_both_recurrent_families_and_checks_the_uq_flag(fresh_flags):
+    """model_utils/model.py:25-33: nn_type is resolved by name; unknown names raise RuntimeError, families that are
+    not built NotImplementedError.  (Constructing a model needs a GPU; resolution and refusal do not.)"""
+    from lfm_quant_b200.scripts.model_utils import model as factory
+    assert {'RNNPointEstimate', 'RNNUqRangeEstimate'} <= set(vars(factory))
+    c = base_config.get_configs(['--nn_type', 'MLPPointEstimate'])
+    with pytest.raises(NotImplementedError):
+        factory.Model(c, None).get_model()
+    c.nn_type = 'NoSuchModel'
+    with pytest.raises(RuntimeError):
+        factory.Model(c, None).get_model()
+
+
+def test_uq_execution_routing(fresh_flags, monkeypatch):
+    """runtime/model_execution.py:149-150,201-206: UQ with training or one process is a single execution; the
+    multi-process MC ensemble at predict time is refused here."""
+    from lfm_quant_b200.scripts.runtime.model_execution import ModelExecution
+    calls = []
+    monkeypatch.setattr(ModelExecution, 'single_execution', staticmethod(lambda cfg: calls.append(cfg.train) or 'ran'))
+    c = base_config.get_configs(['--nn_type', 'RNNUqRangeEstimate', '--UQ=True', '--train=True', '--num_procs', '4'])
+    assert ModelExecution(c)() == 'ran'                  # training: num_procs does not matter
+    c.train = False
+    with pytest.raises(NotImplementedError):
+        ModelExecution(c)()                              # ensemble prediction
+    c.num_procs = 1
+    assert ModelExecution(c)() == 'ran' and calls == [True, False]
+
+
+def test_uq_loss_shim_asserts_like_the_reference(fresh_flags):
+    """losses.py:145-157: UQ must be on, arguments must be lists."""
+    from lfm_quant_b200.scripts.model_utils.losses import Losses
+    c = base_config.get_configs(['--nn_type', 'RNNUqRangeEstimate'])
+    with pytest.raises(AssertionError, match='UQ should be True'):
+        Losses(c, 0).weight_adjusted_uq_loss([0], [0], [0])
+    c.UQ = True
+    with pytest.raises(AssertionError, match='need to be a list'):
+        Losses(c, 0).weight_adjusted_uq_loss(np.zeros(3), [0], [0])
