@@ -134,6 +134,7 @@ def get_configs(argv=None, list_sep='-'):
             c.max_unrollings = (c.min_years + c.pls_years) * (12 // c.stride)
     # scripts/lfm_quant.py:125-127
     c.forecast_steps_weights = [float(v) for v in str(c.forecast_steps_weights).split(list_sep)]
-    c.piecewise_lr_boundaries = [float(v) for v in str(c.piecewise_lr_boundaries).split('-')]
-    c.piecewise_lr_values = [float(v) for v in str(c.piecewise_lr_values).split('-')]
+    if list_sep == '-':     # scripts/lfm_quant.py:126-127; scripts/base_config.py:115 leaves these two as strings
+        c.piecewise_lr_boundaries = [float(v) for v in str(c.piecewise_lr_boundaries).split('-')]
+        c.piecewise_lr_values = [float(v) for v in str(c.piecewise_lr_values).split('-')]
     return c

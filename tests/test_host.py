@@ -207,3 +207,24 @@ def test_uq_loss_shim_asserts_like_the_reference(fresh_flags):
     c.UQ = True
     with pytest.raises(AssertionError, match='need to be a list'):
         Losses(c, 0).weight_adjusted_uq_loss(np.zeros(3), [0], [0])
+
+
+@pytest.mark.parametrize('case', ['defaults', 'overrides', 'bool_forms', 'years'])
+def test_flag_parser_matches_the_reference_parser_golden(fresh_flags, case):
+    """tests/golden/reference_flags.json holds what the UNMODIFIED reference parser (scripts/configs.py +
+    scripts/base_config.py, run by tests/golden/make_reference_flags.py) returns for each argv; this package's mirror
+    must return the same value for every one of the reference's flags (it may define additional ones).  The reference's
+    CLI flavour (scripts/lfm_quant.py:108-129: dash-separated lists, piecewise flags parsed) cannot be run here -- that
+    module imports TensorFlow transitively -- and is covered by test_flag_defaults_match_reference_schema."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_flags.json')))[case]
+    assert 'values' in g, g
+    c = base_config.get_configs(list(g['argv']), list_sep=',')      # the base_config.py flavour, which is what ran
+    diffs = {}
+    for k, want in g['values'].items():
+        got = getattr(c, k, '<missing>')
+        if isinstance(got, tuple):
+            got = list(got)
+        if got != want:
+            diffs[k] = (got, want)
+    assert not diffs, diffs
