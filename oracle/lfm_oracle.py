@@ -4,16 +4,22 @@ This file is the *checker*, never the product: only ``tests/``, ``__graft_entry_
 and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product
 path (``lfm_quant_b200``) fails loudly when its CUDA extension is missing.
 
-PARITY UNPINNED: the reference (lakshaykc/lfm_quant @ ac6f47c) keeps all of its arithmetic
-inside TensorFlow 2.x / Keras, which is neither vendored under /root/reference nor pinned
-(no requirements.txt / lock file; API usage dates it to TF 2.0-2.3) and cannot be imported
-in the build container.  The reference ships no tests, golden vectors or fixtures for this
-path.  The oracle is therefore a NumPy restatement of the reference's own call sites plus the
-published Keras layer algorithms, pinned against
-  (1) the only fixture in the reference, the loss example in scripts/model_utils/losses.py:287-310
-      (expected values derived by hand, see tests/golden/make_golden.py),
-  (2) torch.nn.LSTM / torch autograd on CPU as an independent second opinion (same i,f,g,o order),
-  (3) fp64 finite differences of the full step.
+PINNING STATUS, by row of SURVEY section 8a.
+  * Batcher rows (a1 window index, a2 get_batch, scaler): PINNED to the reference itself.  Its data_processing.py uses
+    TensorFlow only to wrap arrays, so the unmodified file runs in the build container behind an import shim;
+    tests/golden/make_reference_batcher.py recorded what Dataset.generate_dataset / get_batch return on a synthetic
+    table (tests/golden/reference_batcher_*.npz) and tests/test_golden_batcher.py holds gather_batch, the window index,
+    the split and the scaler procedure to it.  The flag parser is pinned the same way (reference_flags.json).
+  * Model / loss / step rows (a3-a11): PARITY UNPINNED.  The reference (lakshaykc/lfm_quant @ ac6f47c) keeps that
+    arithmetic inside TensorFlow 2.x / Keras, which is neither vendored under /root/reference nor pinned (no
+    requirements.txt / lock file; API usage dates it to TF 2.0-2.3) and cannot be installed here, and it ships no tests or
+    golden vectors for it.  Those functions are a NumPy restatement of the reference's own call sites plus the published
+    Keras layer algorithms, checked against
+      (1) the only fixture in the reference, the loss example in scripts/model_utils/losses.py:287-310 (expected values
+          derived by hand in tests/test_oracle.py),
+      (2) torch.nn.LSTM / torch.nn.GRU / torch autograd / torch.optim on CPU as independent second opinions,
+      (3) fp64 finite differences of the full step,
+    and oracle/pin_with_tf.py is the (never yet executed) route to pin them where TensorFlow exists.
 
 Every function cites the reference file:line (relative to /root/reference/scripts) it follows.
 """
