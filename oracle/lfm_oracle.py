@@ -10,13 +10,18 @@ PINNING STATUS, by row of SURVEY section 8a.
     tests/golden/make_reference_batcher.py recorded what Dataset.generate_dataset / get_batch return on a synthetic
     table (tests/golden/reference_batcher_*.npz) and tests/test_golden_batcher.py holds gather_batch, the window index,
     the split and the scaler procedure to it.  The flag parser is pinned the same way (reference_flags.json).
-  * Model / loss / step rows (a3-a11): PARITY UNPINNED.  The reference (lakshaykc/lfm_quant @ ac6f47c) keeps that
+  * Loss rows (a7 weight_adjusted_mse, and weight_adjusted_uq_loss): LOGIC PINNED to the reference's own code.  losses.py
+    is tensor algebra over 14 TensorFlow primitives; with each mapped to its NumPy equivalent the unmodified file runs
+    (tests/golden/make_reference_losses.py -> reference_losses.npz) and tests/test_golden_losses.py holds
+    loss_point_estimate / loss_uq_estimate to its answers, incl. the NaN of the UQ loss on a zero-padded step.  What is
+    pinned is the masking / slicing / weighting / denominators; the primitives' arithmetic is NumPy float32, not TF's.
+  * Model / backward / optimizer rows (a3-a6, a8-a11): PARITY UNPINNED.  The reference (lakshaykc/lfm_quant @ ac6f47c) keeps that
     arithmetic inside TensorFlow 2.x / Keras, which is neither vendored under /root/reference nor pinned (no
     requirements.txt / lock file; API usage dates it to TF 2.0-2.3) and cannot be installed here, and it ships no tests or
     golden vectors for it.  Those functions are a NumPy restatement of the reference's own call sites plus the published
     Keras layer algorithms, checked against
       (1) the only fixture in the reference, the loss example in scripts/model_utils/losses.py:287-310 (expected values
-          derived by hand in tests/test_oracle.py),
+          derived by hand in tests/test_oracle.py, confirmed by the reference's own code in reference_losses.npz),
       (2) torch.nn.LSTM / torch.nn.GRU / torch autograd / torch.optim on CPU as independent second opinions,
       (3) fp64 finite differences of the full step,
     and oracle/pin_with_tf.py is the (never yet executed) route to pin them where TensorFlow exists.
