@@ -9,7 +9,9 @@ PINNING STATUS, by row of SURVEY section 8a.
     TensorFlow only to wrap arrays, so the unmodified file runs in the build container behind an import shim;
     tests/golden/make_reference_batcher.py recorded what Dataset.generate_dataset / get_batch return on a synthetic
     table (tests/golden/reference_batcher_*.npz) and tests/test_golden_batcher.py holds gather_batch, the window index,
-    the split and the scaler procedure to it.  The flag parser is pinned the same way (reference_flags.json).
+    the split and the scaler procedure to it.  The flag parser is pinned the same way (reference_flags.json), and so is
+    the prediction driver: reference_preds.dat is what the unmodified predict.py writes with a stub model, and
+    tests/test_gpu_cli.py holds the package's Predict + CUDA batcher to it (oracle not involved).
   * Loss rows (a7 weight_adjusted_mse, and weight_adjusted_uq_loss): LOGIC PINNED to the reference's own code.  losses.py
     is tensor algebra over 14 TensorFlow primitives; with each mapped to its NumPy equivalent the unmodified file runs
     (tests/golden/make_reference_losses.py -> reference_losses.npz) and tests/test_golden_losses.py holds

@@ -127,3 +127,66 @@ def test_cli_trains_and_predicts_the_uq_range_estimate_model(workdir):
     assert np.isfinite(out['norm_preds_1']).all() and (out['norm_variance_1'] >= 1e-6).all()
     assert np.isfinite(out['variance_1']).all()
     configs.reset()
+
+
+def test_predict_driver_and_preds_file_match_the_reference_golden(tmp_path, monkeypatch):
+    """tests/golden/reference_preds.dat was written by the UNMODIFIED reference scripts/predict.py (with its Dataset) run
+    in the build container with a stub model whose predict(inp) is the fixed function below (generator:
+    tests/golden/make_reference_preds.py).  This package's Predict, given the same stub and the reference's scaler
+    parameters, must produce the same file: batching through the CUDA batcher, extraction of the last step / target
+    field, un-scaling, reverse log-squash, seq-norm, the error columns and the column order (SURVEY 8b "Files")."""
+    import pickle
+    from lfm_quant_b200.scripts import base_config, predict as predict_mod
+    from lfm_quant_b200.scripts.data_processing import Dataset
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+    class _StubModel(object):
+        def predict(self, inp, batch_size=None):
+            x = (inp.detach().cpu().numpy() if hasattr(inp, 'detach') else np.asarray(inp)).astype(np.float64)
+            base = np.tanh(x.mean(axis=2, keepdims=True))
+            return (base + 0.1 * np.arange(16)[None, None, :] * x[:, :, :1]).astype(np.float32)
+
+        def load_weights(self, path):
+            return None
+
+        def summary(self):
+            return 'stub'
+
+    class _StubFactory(object):
+        def __init__(self, config, dataset):
+            pass
+
+        def get_model(self):
+            return _StubModel()
+
+    monkeypatch.setattr(predict_mod, 'Model', _StubFactory)
+    d = tmp_path / 'datasets'
+    write_open_dataset(str(d / 'open-dataset.dat'), n_keys=8, n_months=120, seed=11)
+    mdir = tmp_path / 'experiments' / 'm'
+    os.makedirs(str(mdir / 'chkpts'))
+    g = np.load(os.path.join(gold_dir, 'reference_batcher_train.npz'))
+    pickle.dump({'center': g['center'], 'scale': g['scale']}, open(str(mdir / 'scales.dat'), 'wb'))
+    configs.reset()
+    c = base_config.get_configs(['--datafile', 'open-dataset.dat', '--data_dir', str(d), '--experiments_dir',
+                                 str(tmp_path / 'experiments'), '--model_dir', 'm', '--financial_fields',
+                                 'saleq_ttm-ltq_mrq', '--aux_fields', 'rel_mom1m-rel_mom9m', '--target_field',
+                                 'oiadpq_ttm', '--scale_field', 'mrkcap', '--stride', '12', '--forecast_n', '12',
+                                 '--min_unrollings', '3', '--max_unrollings', '5', '--start_date', '197001', '--end_date',
+                                 '209912', '--validation_size', '0.3', '--seed', '521', '--batch_size', '64',
+                                 '--train=False'])
+    predict_mod.Predict(c, Dataset(c)).predict()
+    got = pd.read_csv(str(mdir / 'pred' / c.preds_fname), sep=' ', dtype={'gvkey': str})
+    ref = pd.read_csv(os.path.join(gold_dir, 'reference_preds.dat'), sep=' ', dtype={'gvkey': str})
+    assert list(got.columns) == list(ref.columns)
+    assert len(got) == len(ref) == 429
+    assert (got['date'].astype(str) == ref['date'].astype(str)).all() and (got['gvkey'] == ref['gvkey']).all()
+    for col in ref.columns[2:]:
+        a, b = got[col].to_numpy(dtype=np.float64), ref[col].to_numpy(dtype=np.float64)
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b), err_msg=col)
+        ok = ~np.isnan(b)
+        # un-scaled columns are multiplied by the row's seq_norm: an exact zero (padded step) comes back as fp32 rounding
+        # residue ~1e-6 * seq_norm on either side, so the absolute tolerance follows the row scale
+        atol = 1e-5 * np.maximum(1.0, ref['seq_norm'].to_numpy(dtype=np.float64))
+        bad = np.abs(a - b) > (atol + 5e-4 * np.abs(b))
+        assert not (bad & ok).any(), (col, int((bad & ok).sum()), float(np.abs(a - b)[bad & ok].max()))
+    configs.reset()
