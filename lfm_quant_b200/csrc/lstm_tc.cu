@@ -1576,7 +1576,7 @@ struct BwdParams {
   } while (0)
 
 constexpr int BWD_NC = 4;
-constexpr int BWD_THREADS = 320;   // producer + MMA + 2 sets of 4 pointwise warps
+constexpr int BWD_THREADS = 352;   // producer + MMA + 2 sets of 4 pointwise warps + dz store warp
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
 constexpr uint32_t SB_R = 163840;               // 3 foreign slices x [128 x 128 B]
@@ -1611,7 +1611,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     mbar_init(&bars->w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->a_full[i], 128);
-      mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->a_empty[i], 2);      // the MMAs that read the stage have completed + the dz store has read it
       mbar_init(&bars->acc_full[i], 1);
     }
     mbar_init(&bars->recv_full, 1);
@@ -1700,23 +1700,41 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             if (jb == 0) BWD_TRACE(1, T - 1 - t, 0);
             if (jb == 3) BWD_TRACE(1, T - 1 - t, 1);
             tcgen05_fence_after();
-            // dz_t of this chunk leaves for HBM straight from the staged A operand: one TMA store (128 rows x 128 B,
-            // rows >= B clipped) instead of four STG.256 per pointwise thread.  dz keeps the operand's column order
-            // [16-unit block][gate][16] (see tc_layout); wgrad_reduce_kernel puts the gate columns back in order.
-            tma_store_3d(&tm_dzst, smem + SB_A + st * 16384, (4 * (int)rank + jb) * 64, t,
-                         (it * p.n_clusters + cid) * 128);
-            bulk_commit_group();
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t da = make_smem_desc(smem_u32(smem + SB_A + st * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
               const uint64_t db = make_smem_desc(smem_u32(smem + SB_U + jb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
               umma_f16(acc, da, db, idesc, (jb | k16) != 0);
             }
-            bulk_wait_group_read0();             // the store has read the stage (well inside the MMAs' own time)
             umma_commit(&bars->a_empty[st]);
           }
           if (FUSED && t > 0) dy_mma(acc + rank * 64, true);      // head part of dLoss/dh_{t-1}, read as `rec` next step
           umma_commit(&bars->acc_full[gs & 1]);
+          BWD_TRACE(1, T - 1 - t, 2);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== dz store warp =====================
+    // dz_t of every staged chunk leaves for HBM straight from the A operand: one TMA store (128 rows x 128 B, rows >= B
+    // clipped) instead of four STG.256 per pointwise thread.  dz keeps the operand's column order [16-unit block][gate][16]
+    // (see tc_layout); wgrad_reduce_kernel puts the gate columns back in order.  A warp of its own: the wait for the
+    // store's shared-memory read (~1.5 K cycles per chunk, profiles/r01_btrace_v6) used to sit on the MMA thread, between
+    // the last chunk's MMAs and the commit the exchange waits for.
+    if (lane == 0) {
+      uint32_t gs = 0;
+      for (int it = 0; it < p.n_iters; ++it) {
+        for (int t = T - 1; t >= 0; --t, ++gs) {
+          for (int jb = 0; jb < 4; ++jb) {
+            const uint32_t st = jb & 1;
+            const uint32_t n_use = gs * 2 + (jb >> 1);
+            mbar_wait(&bars->a_full[st], n_use & 1);
+            tma_store_3d(&tm_dzst, smem + SB_A + st * 16384, (4 * (int)rank + jb) * 64, t,
+                         (it * p.n_clusters + cid) * 128);
+            bulk_commit_group();
+            bulk_wait_group_read0();
+            mbar_arrive(&bars->a_empty[st]);
+          }
         }
       }
       bulk_wait_group0();                        // all dz stores complete before the kernel ends

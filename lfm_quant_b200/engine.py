@@ -205,7 +205,7 @@ class ForecasterEngine(object):
         self.backward(x, y, step=step, row0=row0, denom=denom_global)
         allreduce_flat_gradient(self.grads, self.n_trainable, dist)
         self.apply(lr, step)
-        return self.grads[self.n_trainable:self.n_trainable + 2]
+        return self.grads[self.n_trainable:self.n_trainable + 2].clone()   # not a live view of the workspace tail
 
     REGIONS = ('fwd', 'head', 'bwd', 'wgrad', 'opt')
 
@@ -305,7 +305,7 @@ def gather_batch(table, inp_idx, tar_idx, *, seq_len, stride, inp_cols, fin_cols
     a.struct_size = C.sizeof(N.LfmqGatherArgs)
     a.n_rows, a.n_cols, a.B, a.T, a.F, a.O = table.shape[0], table.shape[1], B, seq_len, F, O
     a.stride = stride
-    a.seq_norm_col = -1 if not seq_norm_col else int(seq_norm_col)
+    a.seq_norm_col = -1 if (seq_norm_col is None or int(seq_norm_col) < 0) else int(seq_norm_col)
     a.log_squasher, a.aux_masking = int(bool(log_squasher)), int(bool(aux_masking))
     for name, t, dt in (('table', table, torch.float64), ('inp_idx', inp_idx, torch.int32),
                         ('tar_idx', tar_idx, torch.int32), ('inp_cols', inp_cols, torch.int32),

@@ -103,7 +103,6 @@ SCHEMA = [
     ('cdrs_inference_date', _STRING, None, "CDRS Inference date. Format: '%Y-%m-%d' "),
     # ---- B200 extensions (not in the reference) --------------------------------------------------------
     ('precision', _STRING, 'fp32', "'fp32' (parity mode) or 'bf16' (tcgen05 tensor-core gate GEMMs)"),
-    ('device_batcher', _BOOL, True, 'Build batches with the CUDA sliding-window batcher (table resident in HBM)'),
 ]
 
 _DEFINERS = {_STRING: configs.DEFINE_string, _INT: configs.DEFINE_integer, _FLOAT: configs.DEFINE_float,

@@ -261,7 +261,8 @@ class Dataset(object):
         inp_idx = torch.from_numpy(np.ascontiguousarray(inp_indices, dtype=np.int32)).cuda()
         tar_idx = torch.from_numpy(np.ascontiguousarray(tar_indices, dtype=np.int32)).cuda()
         x, y, sn = gather_batch(d['table'], inp_idx, tar_idx, seq_len=self.seq_len, stride=self.config.stride,
-                                inp_cols=d['inp_cols'], fin_cols=d['fin_cols'], seq_norm_col=self._seq_norm_idx,
+                                inp_cols=d['inp_cols'], fin_cols=d['fin_cols'],
+                                seq_norm_col=self._seq_norm_idx if self._seq_norm_idx else None,   # `if self._seq_norm_idx:` (:393,444)
                                 center=d['center'], scale=d['scale'], scale_flag=d['scale_flag'],
                                 aux_flag=d['aux_flag'], log_squasher=self.config.log_squasher,
                                 aux_masking=self.config.aux_masking)

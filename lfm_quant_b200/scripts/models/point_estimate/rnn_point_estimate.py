@@ -73,7 +73,11 @@ class NativeForecaster(object):
             self._calls += 1
             outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls, row0=s) for s in range(0, B, mb)]
             return [np.concatenate([o[k].cpu().numpy() for o in outs], axis=0) for k in (0, 1)]
-        outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls).cpu().numpy() for s in range(0, B, mb)]
+        # train-mode validation keeps dropout on (the literal training=config.train, rnn_point_estimate.py:87,89) and
+        # draws fresh masks per call; rows of later chunks are keyed by their own global row (row0 = s)
+        self._calls += 1
+        outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls, row0=s).cpu().numpy()
+                for s in range(0, B, mb)]
         return np.concatenate(outs, axis=0)
 
     def train_step(self, inp, targets, lr, iteration):
