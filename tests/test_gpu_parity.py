@@ -151,10 +151,13 @@ def _make_table(n_keys=6, n_months=40, n_fin=5, n_aux=3, seed=0):
     return np.concatenate(rows, axis=0)
 
 
+# (5, 3): scalar kernel; (8, 4) and (16, 16): the vectorised kernel (F % 4 == O % 4 == 0) with 16-byte aligned and
+# misaligned column groups (the first data column is table column 3)
+@pytest.mark.parametrize('n_fin,n_aux', [(5, 3), (8, 4), (16, 16)])
 @pytest.mark.parametrize('train', [True, False])
-def test_gather_batch_matches_oracle(train):
+def test_gather_batch_matches_oracle(train, n_fin, n_aux):
     from lfm_quant_b200.engine import gather_batch
-    n_fin, n_aux, T, stride, fn = 5, 3, 4, 3, 3
+    T, stride, fn = 4, 3, 3
     table = _make_table(n_fin=n_fin, n_aux=n_aux)
     n_rows, n_cols = table.shape
     inp_cols = list(range(3, 3 + n_fin + n_aux))
@@ -163,7 +166,7 @@ def test_gather_batch_matches_oracle(train):
     rng = np.random.RandomState(1)
     center = rng.normal(size=n_fin + n_aux)
     scale = np.abs(rng.normal(size=n_fin + n_aux)) + 0.5
-    scale_ids = [0, 1, 2, 3, 4, 6]                 # column 5 and 7 in dont_scale_fields
+    scale_ids = [i for i in range(n_fin + n_aux) if i not in (n_fin, n_fin + 2)]   # two aux columns in dont_scale_fields
     inp_idx, tar_idx, valid = [], [], []
     for i in range(12, n_rows - fn, 7):
         for pad in (0, 1, 2):
