@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -Xptxas -v -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --expt-relaxed-constexpr
 CSRC      := lfm_quant_b200/csrc
-SRCS      := $(CSRC)/lfmq_api.cu $(CSRC)/kernels_simt.cu $(CSRC)/lstm_tc.cu
+SRCS      := $(CSRC)/lfmq_api.cu $(CSRC)/kernels_simt.cu $(CSRC)/lstm_tc.cu $(CSRC)/rnn_tc.cu
 OBJS      := $(SRCS:.cu=.o)
 LIB       := lfm_quant_b200/_lfmq.so
 

@@ -24,13 +24,18 @@
 extern "C" {
 #endif
 
-#define LFMQ_ABI_VERSION 2
+#define LFMQ_ABI_VERSION 3   /* 3: LFMQ_PREC_BF16X3, general tensor-core path, lfmq_validate */
 
 enum { LFMQ_OK = 0, LFMQ_ERR_ARG = 1, LFMQ_ERR_CUDA = 2, LFMQ_ERR_UNSUPPORTED = 3, LFMQ_ERR_WORKSPACE = 4 };
 enum { LFMQ_OPT_ADADELTA = 0, LFMQ_OPT_ADAM = 1, LFMQ_OPT_RMSPROP = 2, LFMQ_OPT_SGD = 3 };
-/* LFMQ_PREC_FP32: fp32 SIMT arithmetic everywhere (the parity mode, <=1e-4 rel vs the oracle).
- * LFMQ_PREC_BF16: gate GEMMs on tcgen05 tensor cores with bf16 operands, fp32 accumulate, fp32 cell state. */
-enum { LFMQ_PREC_FP32 = 0, LFMQ_PREC_BF16 = 1 };
+/* LFMQ_PREC_FP32:   fp32 SIMT arithmetic everywhere (the parity mode, <=1e-4 rel vs the oracle; any cell / head).
+ * LFMQ_PREC_BF16:   gate GEMMs on tcgen05 tensor cores with bf16 operands, fp32 accumulate, fp32 cell state.  LSTM cell,
+ *                   point-estimate head, num_hidden a multiple of 64 (<= 1024), any num_layers, dropout and recurrent
+ *                   dropout; H = 256 / L = 1 without recurrent dropout runs the persistent cluster kernels.
+ * LFMQ_PREC_BF16X3: fp32-tolerance forward on tensor cores (forward_only handles: predict.py:129): every operand split
+ *                   into bf16 high + low halves, three tcgen05 products per GEMM (hi*hi + lo*hi + hi*lo), accurate
+ *                   expf / tanhf gate nonlinearities, fp32 head -- <=1e-4 rel vs the oracle. */
+enum { LFMQ_PREC_FP32 = 0, LFMQ_PREC_BF16 = 1, LFMQ_PREC_BF16X3 = 2 };
 
 /* config.rnn_cell (lfm_quant.py:39; rnn_point_estimate.py:80-102).  GRU is Keras' default reset_after=True cell:
  * 3 gate blocks z|r|h, bias [2][3H] (input row, recurrent row).  LFMQ_PREC_BF16 supports the LSTM cell only. */

@@ -10,9 +10,9 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lfmq.so')
 
 OPTIMIZERS = {'Adadelta': 0, 'Adam': 1, 'RMSprop': 2, 'SGD': 3}
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 CELLS = {'lstm': 0, 'gru': 1}           # LFMQ_CELL_*
-ABI_VERSION = 2                         # LFMQ_ABI_VERSION in include/lfmq.h (2: rnn_cell added to lfmq_config)
+ABI_VERSION = 3                         # LFMQ_ABI_VERSION in include/lfmq.h (3: LFMQ_PREC_BF16X3, general tensor-core path)
 
 
 class LfmqConfig(C.Structure):

@@ -2,6 +2,7 @@
 #include "../../include/lfmq.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -9,6 +10,7 @@
 
 #include "kernels.h"
 #include "lstm_tc.h"
+#include "rnn_tc.h"
 
 using namespace lfmq;
 
@@ -47,6 +49,8 @@ struct lfmq_handle_s {
   float *zh, *dz2;   // GRU only: recurrent projection of one step, gradient w.r.t. the recurrent projection
   size_t scratch_elems;
   lfmq::TcState tc;
+  lfmq::GenState gen;
+  int use_gen;               // 1: the general tensor-core path (rnn_tc.cu) runs this handle's bf16 / bf16x3 work
   lfmq::Profiler prof;
 };
 
@@ -97,7 +101,7 @@ int validate(const lfmq_config* c) {
                  c->uq);
     return LFMQ_ERR_ARG;
   }
-  if (c->precision != LFMQ_PREC_FP32 && c->precision != LFMQ_PREC_BF16) {
+  if (c->precision != LFMQ_PREC_FP32 && c->precision != LFMQ_PREC_BF16 && c->precision != LFMQ_PREC_BF16X3) {
     LFMQ_SET_ERR("lfmq_config: unknown precision %d", c->precision);
     return LFMQ_ERR_ARG;
   }
@@ -192,7 +196,28 @@ size_t layout(lfmq_handle_s* h, char* base) {
   }
   h->scratch_elems = scratch;
   h->scratch = cv.take<float>(scratch);
-  lfmq::tc_layout(h->tc, c, cv.base, cv.off);
+  // Tensor-core precisions: the persistent cluster kernels (lstm_tc.cu) take the shape family they are specialised for
+  // (LSTM, H = 256, one layer, no recurrent dropout; LFMQ_FORCE_GENERIC=1 sends it to the general path as well), every
+  // other supported configuration runs the general stepped path (rnn_tc.cu).
+  h->use_gen = 0;
+  if (c.precision != LFMQ_PREC_FP32) {
+    const char* fg = getenv("LFMQ_FORCE_GENERIC");
+    const bool force_gen = fg != nullptr && atoi(fg) != 0;
+    const bool fast = c.precision == LFMQ_PREC_BF16 && !force_gen && lfmq::tc_shape_supported(c);
+    if (!fast) {
+      h->use_gen = 1;
+      std::vector<lfmq::GenLayerOff> lo(L);
+      for (int l = 0; l < L; ++l) {
+        const LayerBuf& lb = h->layers[l];
+        lo[l] = lfmq::GenLayerOff{lb.oW, lb.oU, lb.ob, lb.ogamma, lb.obeta, lb.omean, lb.ovar, lb.I};
+      }
+      char why[160];
+      if (lfmq::gen_supported(c, why, sizeof(why)))      // lfmq_create reports unsupported configurations (gen_init)
+        lfmq::gen_layout(h->gen, c, lo.data(), h->oWo, h->obo, cv.base, cv.off);
+    } else {
+      lfmq::tc_layout(h->tc, c, cv.base, cv.off);
+    }
+  }
   return cv.off;
 }
 
@@ -361,6 +386,8 @@ int32_t lfmq_workspace_bytes(const lfmq_config* cfg, uint64_t* bytes) {
   lfmq_handle_s tmp;
   tmp.cfg = *cfg;
   *bytes = layout(&tmp, nullptr) + ALIGN;
+  lfmq::tc_destroy(tmp.tc);
+  lfmq::gen_destroy(tmp.gen);
   return LFMQ_OK;
 }
 
@@ -381,7 +408,19 @@ int32_t lfmq_create(const lfmq_config* cfg, void* workspace, uint64_t workspace_
   }
   layout(h, base);
   h->tc.prof = &h->prof;
-  int rc = lfmq::tc_init(h->tc, h->cfg);
+  h->gen.prof = &h->prof;
+  int rc = 0;
+  if (h->use_gen) {
+    char why[160];
+    if (!lfmq::gen_supported(h->cfg, why, sizeof(why))) {
+      LFMQ_SET_ERR("tensor-core precision unsupported for this configuration: %s; use LFMQ_PREC_FP32", why);
+      rc = LFMQ_ERR_UNSUPPORTED;
+    } else {
+      rc = lfmq::gen_init(h->gen, h->cfg);
+    }
+  } else {
+    rc = lfmq::tc_init(h->tc, h->cfg);
+  }
   if (rc != 0) {
     delete h;
     return rc;
@@ -416,6 +455,7 @@ int32_t lfmq_create(const lfmq_config* cfg, void* workspace, uint64_t workspace_
 int32_t lfmq_destroy(lfmq_handle h) {
   if (h) {
     lfmq::tc_destroy(h->tc);
+    lfmq::gen_destroy(h->gen);
     if (h->prof.created)
       for (int r = 0; r < Profiler::kRegions; ++r)
         for (int i = 0; i < Profiler::kCap; ++i) {
@@ -484,6 +524,7 @@ int32_t lfmq_set_params(lfmq_handle h, const float* host, int64_t n, void* strea
   LFMQ_CUDA_CHECK(cudaMemcpyAsync(h->params, host, sizeof(float) * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   LFMQ_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   h->tc.weights_dirty = 1;
+  h->gen.weights_dirty = 1;
   return LFMQ_OK;
 }
 
@@ -510,6 +551,7 @@ int32_t lfmq_forward(lfmq_handle h, const float* x, int32_t B, int64_t row0, int
     LFMQ_SET_ERR("lfmq_forward: uq handle, call lfmq_forward_uq");
     return LFMQ_ERR_ARG;
   }
+  if (h->use_gen) return lfmq::gen_forward(h->gen, h->cfg, h->params, x, B, row0, step, preds, s);
   if (h->cfg.precision == LFMQ_PREC_BF16)
     return lfmq::tc_forward(h->tc, h->cfg, h->params, x, B, row0, step, preds, /*save=*/false, s);
   return forward_fp32(h, x, B, row0, step, preds, nullptr, s);
@@ -601,6 +643,7 @@ int32_t lfmq_backward(lfmq_handle h, const float* x, const float* y, int32_t B, 
     denom = h->denom;
   }
   float* tail = h->grads + h->n_train;
+  if (h->use_gen) return lfmq::gen_backward(h->gen, c, h->params, h->grads, x, y, B, row0, step, denom, tail, s);
   if (c.precision == LFMQ_PREC_BF16)
     return lfmq::tc_backward(h->tc, c, h->params, h->grads, x, y, B, row0, step, denom, tail, s);
   RUN(forward_fp32(h, x, B, row0, step, h->preds, nullptr, s));
@@ -631,6 +674,7 @@ int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream) {
                      c.max_norm));
   h->prof.end(LFMQ_REGION_OPT, s);
   h->tc.weights_dirty = 1;
+  h->gen.weights_dirty = 1;
   return LFMQ_OK;
 }
 

@@ -1218,6 +1218,11 @@ static bool tc_supported(const lfmq_config& c, char* why, size_t n) {
   return true;
 }
 
+bool tc_shape_supported(const lfmq_config& c) {
+  char why[128];
+  return tc_supported(c, why, sizeof(why));
+}
+
 void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
   if (c.precision != LFMQ_PREC_BF16) return;
   char why[128];
@@ -1721,8 +1726,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     // (see tc_layout); wgrad_reduce_kernel puts the gate columns back in order.  A warp of its own: the wait for the
     // store's shared-memory read (~1.5 K cycles per chunk, profiles/r01_btrace_v6) used to sit on the MMA thread, between
     // the last chunk's MMAs and the commit the exchange waits for.
+    // Two stores in flight: the store of chunk i is issued before the wait for chunk i-1's shared-memory read, whose
+    // stage is the other one (a store takes ~1.5 K cycles from issue to read-complete; serialised, the four of a step
+    // held the second chunk of each pointwise warp-set back, profiles/r02_btrace_c1.txt).
     if (lane == 0) {
       uint32_t gs = 0;
+      bool pending = false;
+      uint32_t st_prev = 0;
       for (int it = 0; it < p.n_iters; ++it) {
         for (int t = T - 1; t >= 0; --t, ++gs) {
           for (int jb = 0; jb < 4; ++jb) {
@@ -1732,11 +1742,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             tma_store_3d(&tm_dzst, smem + SB_A + st * 16384, (4 * (int)rank + jb) * 64, t,
                          (it * p.n_clusters + cid) * 128);
             bulk_commit_group();
-            bulk_wait_group_read0();
-            mbar_arrive(&bars->a_empty[st]);
+            if (pending) {
+              bulk_wait_group_read1();
+              mbar_arrive(&bars->a_empty[st_prev]);
+            }
+            pending = true;
+            st_prev = st;
           }
         }
       }
+      bulk_wait_group_read0();
+      mbar_arrive(&bars->a_empty[st_prev]);
       bulk_wait_group0();                        // all dz stores complete before the kernel ends
     }
   } else {
@@ -1872,6 +1888,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           mbar_arrive(&bars->a_full[set]);
           if (tid == 64 && ci == 0) BWD_TRACE(2, T - 1 - t, 1);
           if (tid == 64 && ci == 1) BWD_TRACE(2, T - 1 - t, 2);
+          if (tid == 192 && ci == 0) BWD_TRACE(0, T - 1 - t, 1);     // warp-set 1 in the producer row's free slots
+          if (tid == 192 && ci == 1) BWD_TRACE(0, T - 1 - t, 2);
         }
         // inputs of both chunks of the next step: independent of the exchange below.  Placement matters because the
         // SM's memory pipe is a FIFO: issued here they delay the export slightly but land before the next step

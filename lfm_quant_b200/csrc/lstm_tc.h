@@ -17,6 +17,9 @@ struct TcState {
   TcImpl* impl = nullptr;
 };
 
+// The shape family of the persistent cluster kernels: LSTM, point estimate, H = 256, L = 1, F <= 32, O <= 16, no
+// recurrent dropout.
+bool tc_shape_supported(const lfmq_config& cfg);
 // Extends the workspace carve (base may be null when only sizing); `off` is advanced.
 void tc_layout(TcState& st, const lfmq_config& cfg, char* base, size_t& off);
 int tc_init(TcState& st, const lfmq_config& cfg);

@@ -44,7 +44,7 @@ class ForecasterEngine(object):
         cfg.max_batch, cfg.seq_len, cfg.n_inputs, cfg.n_outputs = max_batch, seq_len, n_inputs, n_outputs
         cfg.num_hidden, cfg.num_layers, cfg.target_idx = num_hidden, num_layers, target_idx
         cfg.train = 1 if train else 0
-        cfg.precision = {'fp32': N.PREC_FP32, 'bf16': N.PREC_BF16}[precision]
+        cfg.precision = {'fp32': N.PREC_FP32, 'bf16': N.PREC_BF16, 'bf16x3': N.PREC_BF16X3}[precision]
         cfg.optimizer = N.OPTIMIZERS[optimizer]
         cfg.forward_only = 1 if forward_only else 0
         if rnn_cell not in N.CELLS:

@@ -46,11 +46,13 @@ def test_bf16_forward_small_inputs_and_outputs():
 
 
 def test_bf16_unsupported_shapes_fail_loudly():
+    # H != 256 and L != 1 run the general tensor-core path since round 2 (tests/test_gpu_generic.py); what no tensor-core
+    # path covers still fails at lfmq_create, never silently on another path
     from lfm_quant_b200._native import LfmqError
     with pytest.raises(LfmqError):
-        make_engine(8, 4, 32, 16, 64, 1, precision='bf16')      # H != 256
+        make_engine(8, 4, 32, 16, 100, 1, precision='bf16')     # H not a multiple of 64
     with pytest.raises(LfmqError):
-        make_engine(8, 4, 32, 16, 256, 2, precision='bf16')     # L != 1
+        make_engine(8, 4, 32, 16, 576, 1, precision='bf16')     # H > 512
 
 
 def _oracle_grads(params, x, y, O, L=1, **kw):
