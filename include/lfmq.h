@@ -174,6 +174,13 @@ typedef struct lfmq_gather_args {
 } lfmq_gather_args;
 int32_t lfmq_gather_batch(const lfmq_gather_args* args, void* stream);
 
+/* Train._unscale_preds (train.py:420-432) on the device, for the validation pass (train.py:268-336) without a host
+ * round trip: out[r][k] = reverse_log_squasher(in[r][k] * scale[k] + center[k]) (data_processing.py:611-619), fp64
+ * arithmetic then cast to fp32 as the reference's NumPy expression does.  in/out [n_rows][O] fp32 (may alias),
+ * scale/center [>= O] fp64 device arrays (Dataset.scaling_params). */
+int32_t lfmq_unscale(const float* in, float* out, int64_t n_rows, int32_t O, const double* scale, const double* center,
+                     int32_t log_squasher, void* stream);
+
 /* Instrumentation: number of kernels this library has launched since load (bench.py "gpu_launches"). */
 int64_t lfmq_launch_count(void);
 

@@ -61,6 +61,7 @@ SYMBOLS = {
     'lfmq_apply': (C.c_int32, [_P, C.c_float, C.c_int64, _P]),
     'lfmq_train_step': (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P, _P]),
     'lfmq_gather_batch': (C.c_int32, [C.POINTER(LfmqGatherArgs), _P]),
+    'lfmq_unscale': (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P]),
     'lfmq_launch_count': (C.c_int64, []),
     'lfmq_profile_enable': (C.c_int32, [_P, C.c_int32]),
     'lfmq_profile_read': (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

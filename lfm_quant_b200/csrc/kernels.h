@@ -62,5 +62,7 @@ struct GatherArgs {
   double* seq_norm;
 };
 int gather_batch(cudaStream_t s, const GatherArgs& a);
+int unscale(cudaStream_t s, const float* in, float* out, long n_rows, int O, const double* scale, const double* center,
+            int log_squasher);
 
 }  // namespace lfmq

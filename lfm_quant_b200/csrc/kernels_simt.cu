@@ -972,4 +972,27 @@ int gather_batch(cudaStream_t s, const GatherArgs& a) {
   return 0;
 }
 
+// Train._unscale_preds (train.py:420-432): affine un-scaling + reverse log-squash, fp64 then cast.
+__global__ void unscale_kernel(long n, int O, const float* __restrict__ in, float* __restrict__ out,
+                               const double* __restrict__ scale, const double* __restrict__ center, int log_squasher) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = (int)(i % O);
+  double v = (double)in[i] * scale[k] + center[k];
+  if (log_squasher) {
+    const double sg = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : ((v == 0.0) ? 0.0 : v));
+    v = sg * expm1(fabs(v));
+  }
+  out[i] = (float)v;
+}
+
+int unscale(cudaStream_t s, const float* in, float* out, long n_rows, int O, const double* scale, const double* center,
+            int log_squasher) {
+  const long n = n_rows * O;
+  if (n <= 0) return 0;
+  unscale_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, O, in, out, scale, center, log_squasher);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace lfmq

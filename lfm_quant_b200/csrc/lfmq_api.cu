@@ -754,4 +754,13 @@ int32_t lfmq_gather_batch(const lfmq_gather_args* a, void* stream) {
   return gather_batch((cudaStream_t)stream, g);
 }
 
+int32_t lfmq_unscale(const float* in, float* out, int64_t n_rows, int32_t O, const double* scale, const double* center,
+                     int32_t log_squasher, void* stream) {
+  if (!in || !out || !scale || !center || n_rows < 0 || O <= 0) {
+    LFMQ_SET_ERR("lfmq_unscale: bad argument");
+    return LFMQ_ERR_ARG;
+  }
+  return unscale((cudaStream_t)stream, in, out, (long)n_rows, O, scale, center, log_squasher);
+}
+
 }  // extern "C"

@@ -175,6 +175,14 @@ class ForecasterEngine(object):
                                       preds.shape[0], _ptr(out), _stream()))
         return out
 
+    def unscale(self, arr, scale, center, log_squasher):
+        """Train._unscale_preds (train.py:420-432) on the device: arr [..., O] fp32, scale / center fp64 CUDA tensors."""
+        a = arr.contiguous()
+        out = torch.empty_like(a)
+        N.check(self.lib.lfmq_unscale(_ptr(a), _ptr(out), a.numel() // self.O, self.O, _ptr(scale), _ptr(center),
+                                      1 if log_squasher else 0, _stream()))
+        return out
+
     def mask_count(self, y):
         out = torch.empty(2, dtype=torch.float32, device=y.device)
         N.check(self.lib.lfmq_mask_count(self.handle, _ptr(y), y.shape[0], _ptr(out), _stream()))

@@ -80,6 +80,18 @@ class NativeForecaster(object):
                 for s in range(0, B, mb)]
         return np.concatenate(outs, axis=0)
 
+    def predict_device(self, inp):
+        """model.predict(inp) without the host copy: a device tensor [B,T,O] (the validation pass keeps everything in
+        HBM, train.py:284-336).  Same dropout semantics as predict()."""
+        import torch
+        assert not self.uq
+        x = self._to_device(inp)
+        B = x.shape[0]
+        mb = self.engine.cfg.max_batch
+        self._calls += 1
+        outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls, row0=s) for s in range(0, B, mb)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
     def train_step(self, inp, targets, lr, iteration):
         """Fused fwd + loss + BPTT + clip + optimizer + MaxNorm; returns a device tensor {loss, mse_0}."""
         return self.engine.train_step(self._to_device(inp), self._to_device(targets), iteration, lr)

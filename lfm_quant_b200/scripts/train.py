@@ -29,7 +29,18 @@ class Train(object):
         self.config = config
         self.dataset = dataset
         self.dataset.generate_dataset()
+        # Data parallelism over the company-batch axis: under torchrun every rank walks the same seeded
+        # batch sequence, gathers only its rows of each global batch and all-reduces the flat gradient once per step.
+        # The process group / device is chosen before the model (and its workspace) is created on that device.
+        from .. import dp as _dp
+        self.rank, self.world = _dp.init_from_env()
         self.model = Model(self.config, self.dataset).get_model()
+        if self.world > 1:                       # one set of initial weights: rank 0's
+            import torch
+            import torch.distributed as dist
+            flat = torch.from_numpy(self.model.engine.get_flat()).to(self.model.engine.device)
+            dist.broadcast(flat, 0)
+            self.model.engine.set_flat(flat.cpu().numpy())
         self.target_index = self.dataset.target_index
         self.optimizer = Optimizers(self.config).get_optimizer()
         self.optimizer.bind(self.model)
@@ -56,8 +67,24 @@ class Train(object):
         self._grad_norm = 1.0
 
         print("Creating batches ...")
-        self._batches = [self.dataset.get_batch(*items) for items in self.train_set]
+        self._batches = [self._build_train_batch(items) for items in self.train_set]
         self._valid_batches = [self.dataset.get_batch(*items) for items in self.valid_set]
+
+    def _build_train_batch(self, items):
+        """(inp, target, metadata[, row0, global denominators]) of one global batch; the shard of this rank under DP."""
+        if self.world == 1:
+            return self.dataset.get_batch(*items)
+        import torch.distributed as dist
+        from .. import dp as _dp
+        inp_idx, tar_idx, meta, row0 = _dp.shard_batch_indices(items[0], items[1], items[2], self.rank, self.world)
+        eng = self.model.engine
+        if len(inp_idx) == 0:                    # fewer windows than ranks: this rank only joins the collectives
+            import torch
+            denom = _dp.global_denominators(torch.zeros(2, dtype=torch.float32, device=eng.device), dist)
+            return (None, None, None, row0, denom)
+        x, y, md = self.dataset.get_batch(inp_idx, tar_idx, meta)
+        denom = _dp.global_denominators(eng.mask_count(y), dist)     # loss denominators are global (losses.py:87,90,131-135)
+        return (x, y, md, row0, denom)
 
     def train(self):
         if self.config.load_saved_weights:
@@ -67,16 +94,23 @@ class Train(object):
         checkpoint_prefix = os.path.join(self.chkpts_dir, "chkpt")
         train_logs_batch = defaultdict(list)
         train_logs_epoch = defaultdict(list)
-        self.model.save_weights(checkpoint_prefix)
+        if self.rank == 0:
+            self.model.save_weights(checkpoint_prefix)
         valid_mse = None
         start = time.time()
         for epoch in range(epochs):
             self.model.reset_states()
             mse_steps, uq_loss_steps = [], []
-            random.shuffle(self._batches)                       # train.py:115 (unseeded in the reference)
+            if self.world == 1:
+                random.shuffle(self._batches)                   # train.py:115 (unseeded in the reference)
+            else:                                               # every rank must walk the same batch order
+                random.Random(self.config.seed + epoch).shuffle(self._batches)
             for (batch_n, cur_batch) in enumerate(self._batches):
                 inp, target = cur_batch[0], cur_batch[1]
-                if self.config.UQ:
+                if self.world > 1:
+                    mse = self._train_step_point_dp(cur_batch)
+                    uq_loss = None
+                elif self.config.UQ:
                     uq_loss, mse = self._train_step_uq_range(inp, target)
                 else:
                     mse = self._train_step_point(inp, target)   # device scalar, no host sync here
@@ -105,7 +139,7 @@ class Train(object):
                 train_logs_epoch['valid_uq_loss'].append(valid_uq_loss)
                 train_logs_epoch['valid_mse_fcst'].append(valid_mse_fcst)
                 self._write_train_logs(train_logs_epoch, 'train-logs-epoch')
-                if self._save_criteria(train_logs_epoch):
+                if self._save_criteria(train_logs_epoch) and self.rank == 0:
                     self.model.save_weights(checkpoint_prefix)
                 if self._stop_criteria(train_logs_epoch):
                     break
@@ -124,6 +158,26 @@ class Train(object):
         self.optimizer.iterations += 1
         return out[1]
 
+    def _train_step_point_dp(self, cur_batch):
+        """train.py:178-199 under data parallelism: local BPTT with global denominators, ONE all-reduce of the flat
+        gradient (+ loss / mse tail), replicated clip + optimizer + MaxNorm.  Same trajectory as one GPU."""
+        assert not self.config.UQ, 'data parallelism is built for the point-estimate model'
+        import torch.distributed as dist
+        from ..dp import allreduce_flat_gradient
+        eng = self.model.engine
+        inp, targets, _, row0, denom = cur_batch
+        lr = self.optimizer.current_lr()
+        it = self.optimizer.iterations
+        if inp is None:
+            eng.grads[:eng.n_trainable + 2].zero_()
+            allreduce_flat_gradient(eng.grads, eng.n_trainable, dist)
+            eng.apply(lr, it)
+            out = eng.grads[eng.n_trainable:eng.n_trainable + 2].clone()
+        else:
+            out = eng.train_step_dp(inp, targets, it, lr, row0, denom)
+        self.optimizer.iterations += 1
+        return out[1]
+
     def _train_step_uq_range(self, inp, targets):
         """train.py:201-225 as one fused native step; returns device scalars (uq_loss_last_tar, mse_0)."""
         assert self.config.UQ
@@ -133,6 +187,8 @@ class Train(object):
         return out[0], out[1]
 
     def _write_train_logs(self, train_logs, name):
+        if self.rank != 0:
+            return
         df = pd.DataFrame.from_dict(train_logs)
         fname = os.path.join(self.train_log_dir, self.config.name + '-' + name + '.csv')
         df.to_csv(fname, sep=',', index=False)
@@ -152,19 +208,35 @@ class Train(object):
         return bool(valid_mse.shape[0] - np.argmin(valid_mse) + 1 >= self.config.early_stop)
 
     def _validation_metrics_point_estimate(self):
-        """train.py:268-336: predict every validation batch, loss over the stacked arrays, scaled and un-scaled."""
-        preds, targets = [], []
-        for cur_batch in self._valid_batches:
-            preds.append(self.model.predict(cur_batch[0]))
-            targets.append(cur_batch[1].cpu().numpy())
-        if not preds:
+        """train.py:268-336: predict every validation batch, loss over the stacked arrays, scaled and un-scaled -- all on
+        the device: the validation batches are resident (built once in __init__), predictions stay in HBM
+        (predict_device), un-scaling is lfmq_unscale, both losses are lfmq_loss; the only host traffic per epoch is the
+        two result scalars."""
+        import torch
+        if not self._valid_batches:
             return None, float('nan'), float('nan')
-        pred_all, target_all = np.vstack(preds), np.vstack(targets)
-        pred_unscaled = self._unscale_preds(copy.deepcopy(pred_all))
-        target_unscaled = self._unscale_preds(copy.deepcopy(target_all))
+        preds = [self.model.predict_device(cur_batch[0]) for cur_batch in self._valid_batches]
+        pred_all = torch.cat(preds, dim=0)
+        target_all = torch.cat([cur_batch[1] for cur_batch in self._valid_batches], dim=0)
+        scale, center = self._scaling_dev()
+        eng = self.model.engine
+        pred_unscaled = eng.unscale(pred_all, scale, center, self.config.log_squasher)
+        target_unscaled = eng.unscale(target_all, scale, center, self.config.log_squasher)
         _, valid_mse = self.losses.weight_adjusted_mse([target_all], [pred_all], True)
         _, valid_mse_fcst = self.losses.weight_adjusted_mse([target_unscaled], [pred_unscaled], True)
-        return None, valid_mse.numpy(), valid_mse_fcst.numpy()
+        both = torch.stack([valid_mse._t, valid_mse_fcst._t]).cpu().numpy()      # the epoch's single D2H
+        return None, float(both[0]), float(both[1])
+
+    def _scaling_dev(self):
+        import torch
+        if getattr(self, '_scale_dev', None) is None:
+            n = self.dataset.n_outputs
+            dev = self.model.engine.device
+            self._scale_dev = torch.from_numpy(np.ascontiguousarray(self.dataset.scaling_params['scale'][:n],
+                                                                    dtype=np.float64)).to(dev)
+            self._center_dev = torch.from_numpy(np.ascontiguousarray(self.dataset.scaling_params['center'][:n],
+                                                                     dtype=np.float64)).to(dev)
+        return self._scale_dev, self._center_dev
 
     def _validation_metrics_uq_range_estimate(self):
         """train.py:338-416: predict every validation batch (dropout stays on), uq loss over the stacked arrays, MSE of

@@ -85,3 +85,37 @@ def test_shard_rows_partition():
             assert spans[0][0] == 0 and sum(n for _, n in spans) == B
             for (a, n), (b, _) in zip(spans, spans[1:]):
                 assert a + n == b
+
+
+def _cli_worker(rank, world, port, out_dir):
+    """What scripts/train.py does under torchrun: dp.init_from_env() from the launcher's environment, then each rank
+    takes its rows of every global batch of window indices."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w = dp.init_from_env()
+    assert (r, w) == (rank, world) and dist.is_initialized()
+    rows = []
+    for n in (7, 2, 1):                                     # the last global batches of an epoch are ragged
+        inp = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+        tar = inp + 100
+        meta = np.array([[b'd%d' % i, b'k', b'k'] for i in range(n)], dtype=object)
+        a, b, m, row0 = dp.shard_batch_indices(inp, tar, meta, r, w)
+        assert len(a) == len(b) == len(m)
+        assert (b == a + 100).all()
+        rows.append((n, row0, a[:, 0].tolist()))
+    np.save(os.path.join(out_dir, 'cli%d.npy' % rank), np.array(rows, dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+def test_cli_sharding_covers_every_global_batch_exactly_once(tmp_path):
+    world = 2
+    mp.spawn(_cli_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    per_rank = [np.load(str(tmp_path / ('cli%d.npy' % r)), allow_pickle=True) for r in range(world)]
+    for bi, n in enumerate((7, 2, 1)):
+        got, expect_row0 = [], 0
+        for r in range(world):
+            nn, row0, firsts = per_rank[r][bi]
+            assert nn == n and row0 == expect_row0
+            expect_row0 += len(firsts)
+            got += firsts
+        assert got == [3 * i for i in range(n)]

@@ -84,6 +84,32 @@ def test_dataset_get_batch_matches_oracle(workdir):
     configs.reset()
 
 
+def test_device_validation_pass_matches_host_recomputation(workdir):
+    """Train._validation_metrics_point_estimate runs on the device (resident validation batches,
+    predict_device, lfmq_unscale, lfmq_loss; two scalars come back).  Recomputed here on the host the way the reference
+    does it (train.py:284-336): model.predict per batch -> vstack -> _unscale_preds (NumPy fp64) -> the weighted MSE of
+    the oracle."""
+    from lfm_quant_b200.scripts import base_config
+    from lfm_quant_b200.scripts.data_processing import Dataset
+    from lfm_quant_b200.scripts.train import Train
+    conf = str(workdir / 'config' / 'system-test.conf')
+    configs.reset()
+    c = base_config.get_configs(['--config=' + conf, '--train=True', '--model_dir', 'valid-dev'])
+    tr = Train(c, Dataset(c))
+    assert len(tr._valid_batches) > 1
+    _, v_mse, v_fcst = tr._validation_metrics_point_estimate()
+    preds = np.vstack([tr.model.predict(b[0]) for b in tr._valid_batches])
+    targets = np.vstack([b[1].cpu().numpy() for b in tr._valid_batches])
+    kw = dict(target_idx=tr.target_index, target_lambda=c.target_lambda, rnn_lambda=c.rnn_lambda)
+    _, mse_ref, _, _ = orc.loss_point_estimate(targets.astype(np.float64), preds.astype(np.float64), **kw)
+    pu, tu = tr._unscale_preds(preds.copy()), tr._unscale_preds(targets.copy())
+    _, fcst_ref, _, _ = orc.loss_point_estimate(tu.astype(np.float32).astype(np.float64),
+                                                pu.astype(np.float32).astype(np.float64), **kw)
+    assert v_mse == pytest.approx(mse_ref, rel=1e-4)
+    assert v_fcst == pytest.approx(fcst_ref, rel=1e-4)
+    configs.reset()
+
+
 def test_cli_trains_and_predicts_with_the_gru_cell(workdir):
     """config.rnn_cell = 'gru' (lfm_quant.py:39, rnn_point_estimate.py:89-98) through the same CLI flow."""
     conf = str(workdir / 'config' / 'system-test.conf')
