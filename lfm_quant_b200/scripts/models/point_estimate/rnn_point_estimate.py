@@ -117,22 +117,39 @@ class NativeForecaster(object):
         return prefix + '.lfmq.npz'
 
     def save_weights(self, prefix):
-        """model.save_weights(<model_dir>/chkpts/chkpt) (train.py:99,171): Keras-style names in one .npz."""
+        """model.save_weights(<model_dir>/chkpts/chkpt) (train.py:99,171).  Two containers are written side by side:
+        ``<prefix>.lfmq.npz`` (Keras-style names in one .npz, this package's native format) and the TF-format
+        checkpoint the reference itself writes and reads -- ``<prefix>.index`` + ``<prefix>.data-00000-of-00001`` with
+        Keras' object-graph variable keys (lfm_quant_b200/tf_checkpoint.py) -- so the reference's ``load_weights`` can
+        address a model trained here."""
+        from .... import tf_checkpoint
         flat = self.engine.get_flat()
         arrs = {name: flat[off:off + int(np.prod(shp))].reshape(shp) for name, shp, off, _ in self.engine.specs}
         os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
         with open(self._weights_path(prefix), 'wb') as fh:
             np.savez(fh, **arrs)
+        tf_checkpoint.write_keras_checkpoint(prefix, arrs)
 
     def load_weights(self, prefix):
-        """model.load_weights(prefix) (train.py:87, predict.py:93)."""
+        """model.load_weights(prefix) (train.py:87, predict.py:93): the native ``<prefix>.lfmq.npz`` when present, else a
+        TF-format checkpoint ``<prefix>.index`` (a model directory trained by the reference)."""
+        from .... import tf_checkpoint
         path = self._weights_path(prefix)
-        if not os.path.isfile(path):
-            raise FileNotFoundError('no native checkpoint at %s' % path)
-        data = np.load(path)
+        specs = self.engine.specs
+        if os.path.isfile(path):
+            data = np.load(path)
+            get = lambda name: data[name]
+        elif os.path.isfile(prefix + '.index'):
+            data = tf_checkpoint.read_keras_checkpoint(prefix, [n for n, _, _, _ in specs],
+                                                       {n: tuple(s_) for n, s_, _, _ in specs})
+            get = lambda name: data[name]
+        else:
+            raise FileNotFoundError('no checkpoint at %s: neither the native %s nor a TensorFlow-format %s.index '
+                                    '(Keras save_weights) exists' % (prefix, os.path.basename(path),
+                                                                     os.path.basename(prefix)))
         flat = self.engine.get_flat()
-        for name, shp, off, _ in self.engine.specs:
-            w = data[name]
+        for name, shp, off, _ in specs:
+            w = np.asarray(get(name), dtype=np.float32)
             assert tuple(w.shape) == tuple(shp), (name, w.shape, shp)
             flat[off:off + w.size] = w.ravel()
         self.engine.set_flat(flat)

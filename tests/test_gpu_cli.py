@@ -84,6 +84,33 @@ def test_dataset_get_batch_matches_oracle(workdir):
     configs.reset()
 
 
+def test_predict_serves_a_tf_format_checkpoint(workdir):
+    """train writes the TF-format checkpoint the reference uses (chkpt.index + chkpt.data-00000-of-00001,
+    Keras object-graph keys) beside the native .npz; with the .npz gone -- the situation of a model directory trained
+    by the reference -- predict.py:93's load_weights restores from the TF files and writes the same preds.dat."""
+    from lfm_quant_b200 import tf_checkpoint
+    conf = str(workdir / 'config' / 'system-test.conf')
+    extra = ['--model_dir', 'system-test-tfck']
+    configs.reset()
+    cli.main(['--config=' + conf, '--train=True'] + extra)
+    mdir = workdir / 'experiments' / 'system-test-tfck'
+    prefix = str(mdir / 'chkpts' / 'chkpt')
+    assert os.path.isfile(prefix + '.index') and os.path.isfile(prefix + '.data-00000-of-00001')
+    bundle = tf_checkpoint.read_bundle(prefix)
+    native = np.load(prefix + '.lfmq.npz')
+    assert bundle['layer_with_weights-0/cell/kernel/.ATTRIBUTES/VARIABLE_VALUE'].shape == (32, 256)
+    np.testing.assert_array_equal(bundle['layer_with_weights-2/kernel/.ATTRIBUTES/VARIABLE_VALUE'], native['OUTPUT_1/kernel'])
+    configs.reset()
+    cli.main(['--config=' + conf, '--train=False'] + extra)
+    a = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
+    os.rename(prefix + '.lfmq.npz', prefix + '.lfmq.npz.away')
+    configs.reset()
+    cli.main(['--config=' + conf, '--train=False'] + extra)
+    b = pd.read_csv(mdir / 'pred' / 'preds.dat', sep=' ', dtype={'gvkey': str})
+    np.testing.assert_array_equal(a['norm_preds_1'].values, b['norm_preds_1'].values)
+    configs.reset()
+
+
 def test_device_validation_pass_matches_host_recomputation(workdir):
     """Train._validation_metrics_point_estimate runs on the device (resident validation batches,
     predict_device, lfmq_unscale, lfmq_loss; two scalars come back).  Recomputed here on the host the way the reference
