@@ -166,8 +166,10 @@ __global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ 
   *reinterpret_cast<uint4*>(xh + (b * (T + 1) + t) * TC_XH_LD + TC_XOFF + c * 8) = o;
 }
 
-// Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 64r+j is row n = 64g+j of
-// slice r; the three sigmoid gates are pre-scaled by 0.5 (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
+// Weight slices in the order the forward kernel consumes them.  Gate g of hidden unit 64r + 16c + jj is row
+// n = 64c + 16g + jj of slice r (four 16-unit chunks of 64 gate columns each: the MMAs are issued and committed chunk by
+// chunk, so the epilogue of chunk c runs under the MMAs of chunk c+1); the three sigmoid gates are pre-scaled by 0.5
+// (sigmoid(z) = 0.5*tanh(z/2) + 0.5).
 __device__ __forceinline__ void pack_weights_body(int bid, int I, const float* __restrict__ W, const float* __restrict__ U,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ Up,
                                     __nv_bfloat16* __restrict__ Wp, float* __restrict__ biasp) {
@@ -177,7 +179,7 @@ __device__ __forceinline__ void pack_weights_body(int bid, int I, const float* _
     const int k = (int)(idx % H);
     const int n = (int)((idx / H) % TC_NSL);
     const int r = (int)(idx / ((long)H * TC_NSL));
-    const int g = n / TC_HS, j = n % TC_HS;
+    const int g = (n % 64) / 16, j = (n / 64) * 16 + n % 16;
     const float sc = (g == 2) ? 1.0f : 0.5f;
     Up[idx] = __float2bfloat16(sc * U[(long)k * 4 * H + g * H + r * TC_HS + j]);
   }
@@ -185,13 +187,13 @@ __device__ __forceinline__ void pack_weights_body(int bid, int I, const float* _
     const int k = (int)(idx % 32);
     const int n = (int)((idx / 32) % TC_NSL);
     const int r = (int)(idx / (32 * TC_NSL));
-    const int g = n / TC_HS, j = n % TC_HS;
+    const int g = (n % 64) / 16, j = (n / 64) * 16 + n % 16;
     const float sc = (g == 2) ? 1.0f : 0.5f;
     Wp[idx] = __float2bfloat16(k < I ? sc * W[(long)k * 4 * H + g * H + r * TC_HS + j] : 0.f);
   }
   if (idx < 4 * H) {                    // biasp: [4][256]
     const int n = (int)(idx % TC_NSL), r = (int)(idx / TC_NSL);
-    const int g = n / TC_HS, j = n % TC_HS;
+    const int g = (n % 64) / 16, j = (n / 64) * 16 + n % 16;
     biasp[idx] = ((g == 2) ? 1.0f : 0.5f) * bias[g * H + r * TC_HS + j];
   }
 }
@@ -225,7 +227,7 @@ constexpr uint32_t FWD_SMEM = SM_BARS + 256 + 1024;   // + alignment slack
 
 struct FwdBars {
   uint64_t w_full, x_full, x_empty, h_full, h_written;
-  uint64_t acc_full[2];
+  uint64_t acc_full[2][4];   // [accumulator buffer][16-unit chunk]
   uint64_t acc_free;      // deferred saved-state stores have drained the staging TMEM buffer
   uint64_t tma_issued;    // producer -> epilogue: the fetch of h for the next step has been issued
   uint32_t tmem_base;
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     mbar_init(&bars->x_empty, 1);
     mbar_init(&bars->h_full, 1);
     mbar_init(&bars->h_written, TC_NC);
-    mbar_init(&bars->acc_full[0], 1);
-    mbar_init(&bars->acc_full[1], 1);
+    for (int i = 0; i < 2; ++i)
+      for (int c = 0; c < 4; ++c) mbar_init(&bars->acc_full[i][c], 1);
     mbar_init(&bars->acc_free, 32 * FWD_EPI_WARPS);
     mbar_init(&bars->tma_issued, 1);
     fence_mbar_init();
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, TC_NSL, false, false);
+      const uint32_t idesc = make_idesc_bf16(128, 64, false, false);      // one 16-unit chunk = 64 gate columns
       mbar_wait(&bars->w_full, 0);
       uint32_t n_xf = 0, n_hf = 0;
       for (int it = 0; it < p.n_iters; ++it) {
@@ -312,27 +314,34 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           if (SAVE && g > 0) mbar_wait(&bars->acc_free, (g - 1) & 1);
           FWD_TRACE(1, t, 0);
           tcgen05_fence_after();
-          for (int k16 = 0; k16 < p.k16_x; ++k16) {
-            const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0) + k16 * 32, 0, 512, LAYOUT_SW64);
-            const uint64_t db = make_smem_desc(smem_u32(smem + SM_W) + k16 * 32, 0, 512, LAYOUT_SW64);
-            umma_f16(acc, da, db, idesc, k16 > 0);
-          }
+          // x part of all four chunks first (it does not wait for h), then the h part chunk by chunk, each chunk
+          // committed on its own barrier: the epilogue of chunk c overlaps the MMAs of chunks c+1..
+          for (int c = 0; c < 4; ++c)
+            for (int k16 = 0; k16 < p.k16_x; ++k16) {
+              const uint64_t da = make_smem_desc(smem_u32(smem + SM_X0) + k16 * 32, 0, 512, LAYOUT_SW64);
+              const uint64_t db = make_smem_desc(smem_u32(smem + SM_W + c * 4096) + k16 * 32, 0, 512, LAYOUT_SW64);
+              umma_f16(acc + c * 64, da, db, idesc, k16 > 0);
+            }
           umma_commit(&bars->x_empty);
           if (t == 0) {
-            umma_commit(&bars->acc_full[g & 1]);
+            for (int c = 0; c < 4; ++c) umma_commit(&bars->acc_full[g & 1][c]);
           } else {
             mbar_wait(&bars->h_full, (n_hf++) & 1);
             FWD_TRACE(1, t, 1);
             tcgen05_fence_after();
 #pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
+            for (int c = 0; c < 4; ++c) {
 #pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                const uint64_t da = make_smem_desc(smem_u32(smem + SM_H0 + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
-                const uint64_t db = make_smem_desc(smem_u32(smem + SM_U + kb * 32768) + k16 * 32, 0, 1024, LAYOUT_SW128);
-                umma_f16(acc, da, db, idesc, 1);
-              }
-            umma_commit(&bars->acc_full[g & 1]);
+              for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  const uint64_t da = make_smem_desc(smem_u32(smem + SM_H0 + kb * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+                  const uint64_t db = make_smem_desc(smem_u32(smem + SM_U + kb * 32768 + c * 8192) + k16 * 32, 0, 1024,
+                                                     LAYOUT_SW128);
+                  umma_f16(acc + c * 64, da, db, idesc, 1);
+                }
+              umma_commit(&bars->acc_full[g & 1][c]);
+            }
             FWD_TRACE(1, t, 2);
           }
         }
@@ -340,12 +349,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     }
   } else {
     // ===================== epilogue: gates, cell update, h exchange =====================
-    const int half = (warp - 2) / 4;        // which 32 of this CTA's 64 hidden units
+    const int half = (warp - 2) / 4;        // this warp takes the 16-unit chunks half and half + 2 of the CTA's 64 units
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int m = q * 32 + lane;            // row of the 128-row tile
     const bool leader = (warp == 2) && lane == 0;
     uint32_t n_ti = 0;                      // phases of tma_issued consumed (one per step that has a successor)
-    const int fr = 2 * (int)rank + half;    // 32-unit block index (saved-state layout, hidden offset 32*fr)
     float cstate[32];
     for (int it = 0; it < p.n_iters; ++it) {
       const int tile_c = it * p.n_clusters + cid;
@@ -355,28 +363,30 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
       for (int j = 0; j < 32; ++j) cstate[j] = 0.f;
       for (int t = 0; t < T; ++t) {
         const uint32_t g = (uint32_t)(it * T + t);
-        mbar_wait(&bars->acc_full[g & 1], (g >> 1) & 1);
-        if (leader) FWD_TRACE(2, t, 0);
-        tcgen05_fence_after();
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t taddr = tmem + lane_addr + (g & 1) * 256 + half * 32;
         const uint32_t taddr_other = tmem + lane_addr + ((g + 1) & 1) * 256 + half * 80;
-        __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + fr * 32;
-        // saved state, SoA at 32-byte granularity: [(t, tile, fr, quadrant)][piece][lane]
-        const long wblk = (((long)t * p.n_tiles_cap + tile_c) * 8 + fr) * 4 + q;
-        __nv_bfloat16* grow = SAVE ? p.gates + (wblk * 8 * 32 + lane) * 16 : nullptr;      // + piece * 512
-        __nv_bfloat16* crow = SAVE ? p.cst + (wblk * 2 * 32 + lane) * 16 : nullptr;        // + piece * 512
+        // saved state, SoA at 32-byte granularity: [(t, tile, 32-unit block fr, quadrant)][piece = gate*2 + h16][lane],
+        // unit = 32 fr + 16 h16 + e.  Chunk c = half + 2 jb of this CTA is fr = 2 rank + jb, h16 = half.
+        const long wblk0 = (((long)t * p.n_tiles_cap + tile_c) * 8 + 2 * (int)rank) * 4 + q;      // jb = 0; jb = 1: + 4
+        __nv_bfloat16* grow = SAVE ? p.gates + (wblk0 * 8 * 32 + lane) * 16 + half * 512 : nullptr;   // + gate*1024 (+ jb*4*8*512)
+        __nv_bfloat16* crow = SAVE ? p.cst + (wblk0 * 2 * 32 + lane) * 16 + half * 512 : nullptr;     // (+ jb*4*2*512)
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
+          const int c = half + 2 * jb;            // 16-unit chunk of this CTA's 64 hidden units
+          mbar_wait(&bars->acc_full[g & 1][c], (g >> 1) & 1);
+          if (leader && jb == 0) FWD_TRACE(2, t, 0);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem + lane_addr + (g & 1) * 256 + c * 64;
+          __nv_bfloat16* hrow = p.xh + (b * (T + 1) + (t + 1)) * TC_XH_LD + rank * TC_HS + c * 16;
           uint32_t vi[16], vf[16], vg[16], vo[16];
-          tmem_ld_32x32b_x16(taddr + 0 * TC_HS + jb * 16, vi);
-          tmem_ld_32x32b_x16(taddr + 1 * TC_HS + jb * 16, vf);
-          tmem_ld_32x32b_x16(taddr + 2 * TC_HS + jb * 16, vg);
-          tmem_ld_32x32b_x16(taddr + 3 * TC_HS + jb * 16, vo);
+          tmem_ld_32x32b_x16(taddr + 0, vi);
+          tmem_ld_32x32b_x16(taddr + 16, vf);
+          tmem_ld_32x32b_x16(taddr + 32, vg);
+          tmem_ld_32x32b_x16(taddr + 48, vo);
           tmem_ld_wait();
           uint32_t ph[8], pi[8], pf[8], pg[8], po[8];
           float cn[16];
-          const float* bs = bias_s + half * 32 + jb * 16;
+          const float* bs = bias_s + c * 64;
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) {
             float hv[2], iv[2], fv[2], gv[2], ov[2];
@@ -384,9 +394,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             for (int u = 0; u < 2; ++u) {
               const int j = jb * 16 + jj + u;
               const float gi = fmaf(0.5f, tanh_approx(__uint_as_float(vi[jj + u]) + bs[jj + u]), 0.5f);
-              const float gf = fmaf(0.5f, tanh_approx(__uint_as_float(vf[jj + u]) + bs[TC_HS + jj + u]), 0.5f);
-              const float gg = tanh_approx(__uint_as_float(vg[jj + u]) + bs[2 * TC_HS + jj + u]);
-              const float go = fmaf(0.5f, tanh_approx(__uint_as_float(vo[jj + u]) + bs[3 * TC_HS + jj + u]), 0.5f);
+              const float gf = fmaf(0.5f, tanh_approx(__uint_as_float(vf[jj + u]) + bs[16 + jj + u]), 0.5f);
+              const float gg = tanh_approx(__uint_as_float(vg[jj + u]) + bs[32 + jj + u]);
+              const float go = fmaf(0.5f, tanh_approx(__uint_as_float(vo[jj + u]) + bs[48 + jj + u]), 0.5f);
               const float cc = fmaf(gf, cstate[j], gi * gg);
               cstate[j] = cc;
               cn[jj + u] = cc;
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             pg[jj / 2] = pack_bf16x2(gv[0], gv[1]);
             po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
           }
-          if (valid) st_global_v8(hrow + jb * 16, ph);   // one full 32-byte sector per store (STG.256)
+          if (valid) st_global_v8(hrow, ph);   // one full 32-byte sector per store (STG.256)
           if (SAVE) {
             // Saved gates / cell states are not needed by the h exchange: park them in the idle accumulator
             // buffer (TMEM) and write them to HBM after the publish, off the per-step critical path.
@@ -436,11 +446,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           tmem_ld_32x32b_x32(taddr_other, sg);
           tmem_ld_32x32b_x8(taddr_other + 32, sc);
           tmem_ld_wait();
-          if (valid) {
-            st_global_v8(grow + (0 * 2 + 0) * 512, sg);
-            st_global_v8(grow + (1 * 2 + 0) * 512, sg + 8);
-            st_global_v8(grow + (2 * 2 + 0) * 512, sg + 16);
-            st_global_v8(grow + (3 * 2 + 0) * 512, sg + 24);
+          if (valid) {      // chunk jb = 0 (32-unit block fr = 2 rank)
+            st_global_v8(grow + 0 * 1024, sg);
+            st_global_v8(grow + 1 * 1024, sg + 8);
+            st_global_v8(grow + 2 * 1024, sg + 16);
+            st_global_v8(grow + 3 * 1024, sg + 24);
             st_global_v8(crow, sc);
           }
           tmem_ld_32x32b_x32(taddr_other + 40, sg);
@@ -449,12 +459,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
           tcgen05_fence_before();
           mbar_arrive(&bars->acc_free);
           if (t < T - 1) mbar_wait(&bars->tma_issued, (n_ti++) & 1);
-          if (valid) {
-            st_global_v8(grow + (0 * 2 + 1) * 512, sg);
-            st_global_v8(grow + (1 * 2 + 1) * 512, sg + 8);
-            st_global_v8(grow + (2 * 2 + 1) * 512, sg + 16);
-            st_global_v8(grow + (3 * 2 + 1) * 512, sg + 24);
-            st_global_v8(crow + 512, sc);
+          if (valid) {      // chunk jb = 1 (32-unit block fr = 2 rank + 1: 4 quadrant blocks further)
+            __nv_bfloat16* grow1 = grow + 4L * 8 * 512;
+            st_global_v8(grow1 + 0 * 1024, sg);
+            st_global_v8(grow1 + 1 * 1024, sg + 8);
+            st_global_v8(grow1 + 2 * 1024, sg + 16);
+            st_global_v8(grow1 + 3 * 1024, sg + 24);
+            st_global_v8(crow + 4L * 2 * 512, sc);
           }
         }
         if (leader) FWD_TRACE(2, t, 5);
@@ -1726,13 +1737,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     // (see tc_layout); wgrad_reduce_kernel puts the gate columns back in order.  A warp of its own: the wait for the
     // store's shared-memory read (~1.5 K cycles per chunk, profiles/r01_btrace_v6) used to sit on the MMA thread, between
     // the last chunk's MMAs and the commit the exchange waits for.
-    // Two stores in flight: the store of chunk i is issued before the wait for chunk i-1's shared-memory read, whose
-    // stage is the other one (a store takes ~1.5 K cycles from issue to read-complete; serialised, the four of a step
-    // held the second chunk of each pointwise warp-set back, profiles/r02_btrace_c1.txt).
+    // (Keeping two stores in flight -- issuing chunk i before waiting for chunk i-1's read -- was measured and lost:
+    // 0.397 ms against 0.384 ms with the prefetch helper, 0.451 against 0.43 without, profiles/r02_summary.md.)
     if (lane == 0) {
       uint32_t gs = 0;
-      bool pending = false;
-      uint32_t st_prev = 0;
       for (int it = 0; it < p.n_iters; ++it) {
         for (int t = T - 1; t >= 0; --t, ++gs) {
           for (int jb = 0; jb < 4; ++jb) {
@@ -1742,17 +1750,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             tma_store_3d(&tm_dzst, smem + SB_A + st * 16384, (4 * (int)rank + jb) * 64, t,
                          (it * p.n_clusters + cid) * 128);
             bulk_commit_group();
-            if (pending) {
-              bulk_wait_group_read1();
-              mbar_arrive(&bars->a_empty[st_prev]);
-            }
-            pending = true;
-            st_prev = st;
+            bulk_wait_group_read0();
+            mbar_arrive(&bars->a_empty[st]);
           }
         }
       }
-      bulk_wait_group_read0();
-      mbar_arrive(&bars->a_empty[st_prev]);
       bulk_wait_group0();                        // all dz stores complete before the kernel ends
     }
   } else {
