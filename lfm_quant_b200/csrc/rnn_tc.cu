@@ -77,7 +77,7 @@ inline long cdivl(long a, long b) { return (a + b - 1) / b; }
 // =============================================================================================
 // Tile GEMM skeleton
 // =============================================================================================
-constexpr int G_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (one TMEM lane quadrant each)
+// warp 0: TMA producer, warp 1: MMA issuer, then 4 epilogue warps (one TMEM lane quadrant each) per 128-row M tile
 constexpr int G_MAXSEG = 6;
 
 // One K segment: n_kb 64-wide k-blocks, A columns from a_col0 of map a_map, B columns from b_col0 of map b_map.
@@ -118,14 +118,22 @@ struct EpiParams {
   int ldc;
 };
 
-template <int BN>
+// MT = 128-row M tiles per CTA: 1 (two CTAs per SM overlap one tile's epilogue with the other's loads) or 2 (a 256-row
+// CTA tile: each B stage feeds two MMAs, which cuts the L2 -> SM operand traffic per FLOP by a third; the stepped GEMMs
+// are bound by exactly that traffic, profiles/r02_summary.md).  The ring takes whatever shared memory one / two resident
+// CTAs leave: the loads are latency-bound (~5 K cycles per stage under load), bytes in flight are what buys bandwidth.
+template <int BN, int MT, int EPI = 0>
 struct GSmem {
-  static constexpr uint32_t A_BYTES = 128 * 128;          // 128 rows x 64 bf16
+  static constexpr uint32_t A_BYTES = MT * 128 * 128;     // MT x (128 rows x 64 bf16)
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-  static constexpr int NS = (BN >= 256) ? 2 : 3;
+  // one launch = one wave for the recurrence steps (<= 148 tiles: one CTA per SM, deep ring); the multi-wave GEMMs keep
+  // two CTAs per SM
+  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2)) ? 2 : 1;
+  static constexpr int NS = (int)((CTAS_PER_SM == 2 ? 98304u : 196608u) / STAGE);
   static constexpr uint32_t BARS = NS * STAGE;
-  static constexpr uint32_t TOTAL = BARS + 128 + 1024;    // + alignment slack
+  static constexpr uint32_t TOTAL = BARS + 256 + 1024;    // + alignment slack
+  static constexpr int THREADS = 64 + 128 * MT;           // producer + MMA + 4 epilogue warps per M tile
 };
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -151,8 +159,7 @@ __device__ __forceinline__ void pack16(const float v[16], uint32_t w[8]) {
 // ---- EPI_FWD: gates, cell update, h_t (rnn_point_estimate.py:80-87) ----------------------------
 // Accumulator columns of a tile: [16-unit block][gate i|f|g|o][16] (the packed order of the B operand rows).
 template <int BN>
-__device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q, int lane) {
-  const int rt = blockIdx.x;
+__device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt) {
   const int m = q * 32 + lane;
   const long b = (long)rt * 128 + m;
   const bool valid = b < p.B;
@@ -243,8 +250,7 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
 // ---- EPI_BWD: BPTT pointwise algebra of step t ----------------------------------------------
 // Accumulator columns: hidden units unit0 .. unit0+BN-1 in order (rec = dz_{t+1} U^T, before the recurrent mask).
 template <int BN>
-__device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q, int lane) {
-  const int rt = blockIdx.x;
+__device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt) {
   const int m = q * 32 + lane;
   const long b = (long)rt * 128 + m;
   const bool valid = b < p.B;
@@ -349,13 +355,13 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, uint32_t tmem, int
   }
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(G_THREADS, 2)
+template <int BN, int EPI, int MT>
+__global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI>::CTAS_PER_SM)
     tile_gemm_kernel(GArgs g, EpiParams ep, const __grid_constant__ CUtensorMap tmA0,
                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB0,
                      const __grid_constant__ CUtensorMap tmB1) {
-  using S = GSmem<BN>;
+  using S = GSmem<BN, MT, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BARS);
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
   uint64_t* acc_full = empty + S::NS;
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TMEM_COLS = (BN * MT < 32) ? 32 : BN * MT;
 
   int total_kb = 0;
   for (int i = 0; i < g.n_seg; ++i) total_kb += g.seg[i].n_kb;
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_s, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
 
   if (warp == 0) {
     if (lane == 0) {
-      const int arow = g.a_row_base + 128 * (int)blockIdx.x;
+      const int arow = g.a_row_base + 128 * MT * (int)blockIdx.x;
       const int brow = g.b_row_base + BN * (int)blockIdx.y;
       int i = 0;
       for (int sg = 0; sg < g.n_seg; ++sg) {
@@ -395,7 +402,9 @@ __global__ void __launch_bounds__(G_THREADS, 2)
           if (i >= S::NS) mbar_wait(&empty[s], ((i / S::NS) - 1) & 1);
           mbar_arrive_expect_tx(&full[s], S::STAGE);
           uint8_t* st = smem + s * S::STAGE;
-          tma_load_2d(st, ma, &full[s], sgm.a_col0 + kb * 64, arow);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
           tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
         }
       }
@@ -410,9 +419,12 @@ __global__ void __launch_bounds__(G_THREADS, 2)
         uint8_t* st = smem + s * S::STAGE;
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
-          const uint64_t da = make_smem_desc(smem_u32(st) + k16 * 32, 0, 1024, LAYOUT_SW128);
           const uint64_t db = make_smem_desc(smem_u32(st + S::A_BYTES) + k16 * 32, 0, 1024, LAYOUT_SW128);
-          umma_f16(tmem, da, db, idesc, (i | k16) != 0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = make_smem_desc(smem_u32(st + mt * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+            umma_f16(tmem + mt * BN, da, db, idesc, (i | k16) != 0);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -420,18 +432,23 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     }
   } else {
     const int q = warp & 3;
+    const int mt = (warp - 2) >> 2;                  // which 128-row M tile of the CTA this warp's quadrant belongs to
+    const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
     if (total_kb > 0) {
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();
     }
-    if constexpr (EPI == EPI_FWD) epi_fwd<BN>(ep, tmem, q, lane);
-    if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tmem, q, lane);
-    if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tmem, q, lane, (long)g.a_row_base + 128L * blockIdx.x + q * 32 + lane);
+    const uint32_t tacc = tmem + mt * BN;
+    if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
+      if constexpr (EPI == EPI_FWD) epi_fwd<BN>(ep, tacc, q, lane, rt);
+      if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt);
+      if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
+    }
   }
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // =============================================================================================
@@ -1186,11 +1203,16 @@ int gen_init(GenState& st, const lfmq_config& c) {
     if ((rc = gmap_2d(&m.tm_dz, m.dz, 4 * H, T * Bp, 64, 128))) return rc;
     if ((rc = gmap_2d(&m.tm_dz_mn, m.dz, 4 * H, T * Bp, 64, 64))) return rc;
   }
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<256, EPI_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem<256>::TOTAL));
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<128, EPI_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem<128>::TOTAL));
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<64, EPI_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem<64>::TOTAL));
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<128, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem<128>::TOTAL));
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<64, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem<64>::TOTAL));
+#define LFMQ_GEMM_ATTR(BN_, EPI_, MT_)                                                                         \
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<BN_, EPI_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       GSmem<BN_, MT_, EPI_>::TOTAL))
+  LFMQ_GEMM_ATTR(256, EPI_FWD, 1);
+  LFMQ_GEMM_ATTR(256, EPI_FWD, 2);
+  LFMQ_GEMM_ATTR(128, EPI_BWD, 1);
+  LFMQ_GEMM_ATTR(64, EPI_BWD, 1);
+  LFMQ_GEMM_ATTR(128, EPI_STORE, 1);
+  LFMQ_GEMM_ATTR(64, EPI_STORE, 1);
+#undef LFMQ_GEMM_ATTR
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(gwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM));
   const int hsmem = (int)((H / 64) * 16384 + H * GH_O * 4 + 64 + 1024);
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(ghead_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
@@ -1246,6 +1268,8 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
   const int nrt = (B + 127) / 128;
   const bool rec = c.train && c.recurrent_dropout > 0.f;
   const bool drop = c.train && c.dropout > 0.f;
+  static const char* dual_env = getenv("LFMQ_GEN_DUAL");      // 0 / 1 force, unset: by tile count
+  const bool dual = dual_env ? atoi(dual_env) != 0 : ((long)((nrt + 1) / 2) * (4 * H / 256) >= 96);
   {
     const GenLayer& l0 = m.layers[0];
     const long n = (long)B * T * (l0.Ipad / 8);
@@ -1281,9 +1305,16 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
         g.seg[ns++] = GSeg{1, 1, nkb_x, 0, H};
       }
       g.n_seg = ns;
-      tile_gemm_kernel<256, EPI_FWD><<<dim3(nrt, 4 * H / 256), G_THREADS, GSmem<256>::TOTAL, s>>>(
-          g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th, m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf,
-          m.x3 ? ly.tm_wf_lo : ly.tm_wf);
+      // 256-row CTA tiles when there are enough of them to fill the machine (a third less operand traffic per FLOP),
+      // else 128-row tiles, two CTAs per SM
+      if (dual)
+        tile_gemm_kernel<256, EPI_FWD, 2><<<dim3((nrt + 1) / 2, 4 * H / 256), GSmem<256, 2>::THREADS, GSmem<256, 2>::TOTAL, s>>>(
+            g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th, m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf,
+            m.x3 ? ly.tm_wf_lo : ly.tm_wf);
+      else
+        tile_gemm_kernel<256, EPI_FWD, 1><<<dim3(nrt, 4 * H / 256), GSmem<256, 1>::THREADS, GSmem<256, 1>::TOTAL, s>>>(
+            g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th, m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf,
+            m.x3 ? ly.tm_wf_lo : ly.tm_wf);
       LFMQ_LAUNCH_CHECK();
     }
     const bool last = (l == m.L - 1);
@@ -1438,10 +1469,10 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       g.n_seg = ep.has_rec ? 1 : 0;
       g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
       if (m.BNU == 128)
-        tile_gemm_kernel<128, EPI_BWD><<<dim3(nrt, H / 128), G_THREADS, GSmem<128>::TOTAL, s>>>(
+        tile_gemm_kernel<128, EPI_BWD, 1><<<dim3(nrt, H / 128), GSmem<128, 1, EPI_BWD>::THREADS, GSmem<128, 1, EPI_BWD>::TOTAL, s>>>(
             g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_ub, ly.tm_ub);
       else
-        tile_gemm_kernel<64, EPI_BWD><<<dim3(nrt, H / 64), G_THREADS, GSmem<64>::TOTAL, s>>>(
+        tile_gemm_kernel<64, EPI_BWD, 1><<<dim3(nrt, H / 64), GSmem<64, 1, EPI_BWD>::THREADS, GSmem<64, 1, EPI_BWD>::TOTAL, s>>>(
             g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_ub, ly.tm_ub);
       LFMQ_LAUNCH_CHECK();
     }
@@ -1469,10 +1500,10 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
       const int row_tiles = T * Bp / 128;
       if (H % 128 == 0)
-        tile_gemm_kernel<128, EPI_STORE><<<dim3(row_tiles, H / 128), G_THREADS, GSmem<128>::TOTAL, s>>>(
+        tile_gemm_kernel<128, EPI_STORE, 1><<<dim3(row_tiles, H / 128), GSmem<128, 1, EPI_STORE>::THREADS, GSmem<128, 1, EPI_STORE>::TOTAL, s>>>(
             g, es, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_wb, ly.tm_wb);
       else
-        tile_gemm_kernel<64, EPI_STORE><<<dim3(row_tiles, H / 64), G_THREADS, GSmem<64>::TOTAL, s>>>(
+        tile_gemm_kernel<64, EPI_STORE, 1><<<dim3(row_tiles, H / 64), GSmem<64, 1, EPI_STORE>::THREADS, GSmem<64, 1, EPI_STORE>::TOTAL, s>>>(
             g, es, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_wb, ly.tm_wb);
       LFMQ_LAUNCH_CHECK();
     }
