@@ -91,7 +91,7 @@ struct GArgs {
   int b_row_base;      // B row coordinate = b_row_base + BN * blockIdx.y
 };
 
-enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2 };
+enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3 };   // _ACC: expf / tanhf nonlinearities (bf16x3)
 
 struct EpiParams {
   // common
@@ -116,6 +116,8 @@ struct EpiParams {
   // store
   __nv_bfloat16* out;           // [rows][ldc]
   int ldc;
+  long long* trace;             // debug (LFMQ_TRACE_GEN=1): clock64 stamps of CTA (0,0): start, first stage landed, last MMA
+                                // issued, accumulator complete, epilogue done
 };
 
 // MT = 128-row M tiles per CTA: 1 (two CTAs per SM overlap one tile's epilogue with the other's loads) or 2 (a 256-row
@@ -129,7 +131,7 @@ struct GSmem {
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   // one launch = one wave for the recurrence steps (<= 148 tiles: one CTA per SM, deep ring); the multi-wave GEMMs keep
   // two CTAs per SM
-  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2)) ? 2 : 1;
+  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2)) ? 2 : 1;      // (EPI 2 = EPI_STORE)
   static constexpr int NS = (int)((CTAS_PER_SM == 2 ? 98304u : 196608u) / STAGE);
   static constexpr uint32_t BARS = NS * STAGE;
   static constexpr uint32_t TOTAL = BARS + 256 + 1024;    // + alignment slack
@@ -158,8 +160,8 @@ __device__ __forceinline__ void pack16(const float v[16], uint32_t w[8]) {
 
 // ---- EPI_FWD: gates, cell update, h_t (rnn_point_estimate.py:80-87) ----------------------------
 // Accumulator columns of a tile: [16-unit block][gate i|f|g|o][16] (the packed order of the B operand rows).
-template <int BN>
-__device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt) {
+template <int BN, bool ACC>
+__device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt, const float* bias_s) {
   const int m = q * 32 + lane;
   const long b = (long)rt * 128 + m;
   const bool valid = b < p.B;
@@ -186,15 +188,15 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
       for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
     }
     tmem_ld_wait();
-    const float* bs = p.bias + blockIdx.y * BN + blk * 64;
+    const float* bs = bias_s + blk * 64;          // this tile's packed bias, staged in shared memory (broadcast reads)
     float gi[16], gf[16], gg[16], go[16], cn[16], hv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float zi = __uint_as_float(vi[j]) + __ldg(bs + j);
-      const float zf = __uint_as_float(vf[j]) + __ldg(bs + 16 + j);
-      const float zg = __uint_as_float(vg[j]) + __ldg(bs + 32 + j);
-      const float zo = __uint_as_float(vo[j]) + __ldg(bs + 48 + j);
-      if (p.accurate) {
+      const float zi = __uint_as_float(vi[j]) + bs[j];
+      const float zf = __uint_as_float(vf[j]) + bs[16 + j];
+      const float zg = __uint_as_float(vg[j]) + bs[32 + j];
+      const float zo = __uint_as_float(vo[j]) + bs[48 + j];
+      if (ACC) {
         gi[j] = sigmoid_acc(zi); gf[j] = sigmoid_acc(zf); gg[j] = tanhf(zg); go[j] = sigmoid_acc(zo);
       } else {      // sigmoid(z) = 0.5 tanh(z/2) + 0.5; the 1/2 is folded into the packed weights and bias
         gi[j] = fmaf(0.5f, tanh_approx(zi), 0.5f);
@@ -203,7 +205,7 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
         go[j] = fmaf(0.5f, tanh_approx(zo), 0.5f);
       }
       cn[j] = fmaf(gf[j], cprev[j], gi[j] * gg[j]);
-      hv[j] = go[j] * (p.accurate ? tanhf(cn[j]) : tanh_approx(cn[j]));
+      hv[j] = go[j] * (ACC ? tanhf(cn[j]) : tanh_approx(cn[j]));
     }
     st_global_v8f(cs, cn);
     st_global_v8f(cs + 8, cn + 8);
@@ -370,6 +372,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t TMEM_COLS = (BN * MT < 32) ? 32 : BN * MT;
+  __shared__ float bias_s[(EPI == EPI_FWD || EPI == EPI_FWD_ACC) ? BN : 1];
+  if constexpr (EPI == EPI_FWD || EPI == EPI_FWD_ACC)
+    for (int i = tid; i < BN; i += S::THREADS) bias_s[i] = ep.bias[blockIdx.y * BN + i];    // weights: not the predecessor's
 
   int total_kb = 0;
   for (int i = 0; i < g.n_seg; ++i) total_kb += g.seg[i].n_kb;
@@ -387,11 +392,33 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_base_s;
+  const bool tr = ep.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (tr && tid == 0) ep.trace[0] = clock64();
 
+  // Programmatic dependent launch (the recurrence steps are launched with the stream-serialization attribute): this
+  // kernel's CTAs are dispatched while the previous step's grid drains.  Everything above (barriers, TMEM) and the B
+  // operand (weights: packed long before the previous step) of the first ring stages is independent of it; the A
+  // operand and every state the epilogue reads were written by the previous step, so all threads wait here first.
+  // launch_dependents comes AFTER the wait: when the next grid starts, this one has seen its predecessor complete, so
+  // by induction only the immediate predecessor can still be running.
   if (warp == 0) {
     if (lane == 0) {
       const int arow = g.a_row_base + 128 * MT * (int)blockIdx.x;
       const int brow = g.b_row_base + BN * (int)blockIdx.y;
+      {   // B operand of the first NS stages, before the dependency wait
+        int i = 0;
+        for (int sg = 0; sg < g.n_seg && i < S::NS; ++sg) {
+          const GSeg sgm = g.seg[sg];
+          const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
+          for (int kb = 0; kb < sgm.n_kb && i < S::NS; ++kb, ++i) {
+            mbar_arrive_expect_tx(&full[i], S::STAGE);
+            tma_load_2d(smem + i * S::STAGE + S::A_BYTES, mb, &full[i], sgm.b_col0 + kb * 64, brow);
+          }
+        }
+      }
+      griddep_wait();
+      griddep_launch_dependents();
+      if (tr) ep.trace[1] = clock64();
       int i = 0;
       for (int sg = 0; sg < g.n_seg; ++sg) {
         const GSeg sgm = g.seg[sg];
@@ -399,22 +426,30 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
         const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
         for (int kb = 0; kb < sgm.n_kb; ++kb, ++i) {
           const int s = i % S::NS;
-          if (i >= S::NS) mbar_wait(&empty[s], ((i / S::NS) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], S::STAGE);
           uint8_t* st = smem + s * S::STAGE;
+          if (i >= S::NS) {
+            mbar_wait(&empty[s], ((i / S::NS) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], S::STAGE);
+            tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
+          }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
             tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
-          tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
         }
       }
+    } else {
+      griddep_wait();
+      griddep_launch_dependents();
     }
   } else if (warp == 1) {
+    griddep_wait();
+    griddep_launch_dependents();
     if (lane == 0 && total_kb > 0) {
       const uint32_t idesc = make_idesc_bf16(128, BN, false, false);
       for (int i = 0; i < total_kb; ++i) {
         const int s = i % S::NS;
         mbar_wait(&full[s], (i / S::NS) & 1);
+        if (tr && i == 0) ep.trace[2] = clock64();
         tcgen05_fence_after();
         uint8_t* st = smem + s * S::STAGE;
 #pragma unroll
@@ -429,8 +464,11 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
         umma_commit(&empty[s]);
       }
       umma_commit(acc_full);
+      if (tr) ep.trace[3] = clock64();
     }
   } else {
+    griddep_wait();
+    griddep_launch_dependents();
     const int q = warp & 3;
     const int mt = (warp - 2) >> 2;                  // which 128-row M tile of the CTA this warp's quadrant belongs to
     const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
@@ -439,11 +477,14 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
       tcgen05_fence_after();
     }
     const uint32_t tacc = tmem + mt * BN;
+    if (tr && warp == 2 && lane == 0) ep.trace[4] = clock64();
     if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
-      if constexpr (EPI == EPI_FWD) epi_fwd<BN>(ep, tacc, q, lane, rt);
+      if constexpr (EPI == EPI_FWD) epi_fwd<BN, false>(ep, tacc, q, lane, rt, bias_s);
+      if constexpr (EPI == EPI_FWD_ACC) epi_fwd<BN, true>(ep, tacc, q, lane, rt, bias_s);
       if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt);
       if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
     }
+    if (tr && warp == 2 && lane == 0) ep.trace[5] = clock64();
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -460,33 +501,41 @@ struct GWgradParams {
   int n_kblocks, kb_per_split, Mpad, Ntot;
   float* partial;       // [S][Mpad][Ntot]
 };
-constexpr int GW_THREADS = 192;
-constexpr int GW_STAGES = 4;
-constexpr uint32_t GW_STAGE_BYTES = 16384 + 32768;
-constexpr uint32_t GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 1024 + 256;
+// MT = 128-row M tiles per CTA (2: a 256 x 256 CTA tile, each B stage feeds two MMAs -- a third less operand traffic
+// per FLOP, see GSmem)
+template <int MT>
+struct GWCfg {
+  static constexpr int THREADS = 64 + 128 * MT;
+  static constexpr uint32_t A_BYTES = MT * 16384;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + 32768;
+  static constexpr int STAGES = (int)(196608u / STAGE_BYTES);       // 4 (MT = 1) or 3 (MT = 2)
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
-__global__ void __launch_bounds__(GW_THREADS, 1)
+template <int MT>
+__global__ void __launch_bounds__(GWCfg<MT>::THREADS, 1)
     gwgrad_kernel(GWgradParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+  using C = GWCfg<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GW_STAGES * GW_STAGE_BYTES);
-  uint64_t* empty = full + GW_STAGES;
-  uint64_t* acc_full = empty + GW_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* acc_full = empty + C::STAGES;
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
+  const int m0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * 256;
   const int kb_beg = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.n_kblocks, kb_beg + p.kb_per_split);
   const int nkb = max(0, kb_end - kb_beg);
   if (tid == 0) {
-    for (int s = 0; s < GW_STAGES; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_s, 256);
+  if (warp == 1) tmem_alloc(tmem_base_s, 256 * MT);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -494,28 +543,31 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % GW_STAGES;
-        if (i >= GW_STAGES) mbar_wait(&empty[s], ((i / GW_STAGES) - 1) & 1);
-        mbar_arrive_expect_tx(&full[s], GW_STAGE_BYTES);
-        uint8_t* st = smem + s * GW_STAGE_BYTES;
+        const int s = i % C::STAGES;
+        if (i >= C::STAGES) mbar_wait(&empty[s], ((i / C::STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+        uint8_t* st = smem + s * C::STAGE_BYTES;
         const int krow = (kb_beg + i) * 64;
-        for (int mb = 0; mb < 2; ++mb) tma_load_2d(st + mb * 8192, &tm_a, &full[s], m0 + mb * 64, krow);
-        for (int nb = 0; nb < 4; ++nb) tma_load_2d(st + 16384 + nb * 8192, &tm_b, &full[s], n0 + nb * 64, krow);
+        for (int mb = 0; mb < 2 * MT; ++mb) tma_load_2d(st + mb * 8192, &tm_a, &full[s], m0 + mb * 64, krow);
+        for (int nb = 0; nb < 4; ++nb) tma_load_2d(st + C::A_BYTES + nb * 8192, &tm_b, &full[s], n0 + nb * 64, krow);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nkb > 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256, true, true);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % GW_STAGES;
-        mbar_wait(&full[s], (i / GW_STAGES) & 1);
+        const int s = i % C::STAGES;
+        mbar_wait(&full[s], (i / C::STAGES) & 1);
         tcgen05_fence_after();
-        uint8_t* st = smem + s * GW_STAGE_BYTES;
+        uint8_t* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
-          const uint64_t da = make_smem_desc(smem_u32(st) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
-          const uint64_t db = make_smem_desc(smem_u32(st + 16384) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
-          umma_f16(tmem, da, db, idesc, (i | k16) != 0);
+          const uint64_t db = make_smem_desc(smem_u32(st + C::A_BYTES) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = make_smem_desc(smem_u32(st + mt * 16384) + k16 * 2048, 8192, 1024, LAYOUT_SW128);
+            umma_f16(tmem + mt * 256, da, db, idesc, (i | k16) != 0);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -523,7 +575,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
     }
   } else {
     const int q = warp & 3;
-    const int m = q * 32 + lane;
+    const int mt = (warp - 2) >> 2;
+    const int m = mt * 128 + q * 32 + lane;
     float* out = p.partial + ((long)blockIdx.z * p.Mpad + m0 + m) * p.Ntot + n0;
     if (nkb > 0) {
       mbar_wait(acc_full, 0);
@@ -531,7 +584,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + mt * 256 + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -545,7 +598,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 256 * MT);
 }
 
 // dst[row][n] = sum_z partial[z][row][n] for row < Mvalid (dst row-major [Mvalid][Ntot])
@@ -1056,6 +1109,7 @@ struct GenLayer {
 
 struct GenImpl {
   bool enabled = false;
+  long long* trace = nullptr;      // LFMQ_TRACE_GEN=1: [phase 0 fwd / 1 bwd][layer][t][8] clock64 stamps of CTA (0,0)
   int maxB = 0, Bp = 0, NRT = 0, T = 0, F = 0, O = 0, H = 0, L = 0, NB16 = 0;
   bool x3 = false, train_ws = false;
   int64_t oWo = 0, obo = 0;
@@ -1149,9 +1203,9 @@ void gen_layout(GenState& st, const lfmq_config& c, const GenLayerOff* lo, int64
     m.cs_chunks = 64;
     m.cs_part = reinterpret_cast<float*>(take((size_t)4 * H * m.cs_chunks * 4));
     const size_t Mmax = (H > 64 ? H : 128);               // dU: H rows; dW: Ipad rows (<= max(H, 64..1024))
-    size_t mp = (Mmax + 127) / 128 * 128;
+    size_t mp = (Mmax + 255) / 256 * 256;
     for (int l = 0; l < m.L; ++l) {
-      const size_t ip = ((size_t)m.layers[l].Ipad + 127) / 128 * 128;
+      const size_t ip = ((size_t)m.layers[l].Ipad + 255) / 256 * 256;
       if (ip > mp) mp = ip;
     }
     m.wg_part_elems = (size_t)8 * mp * 4 * H;             // up to 8 K-splits
@@ -1208,12 +1262,15 @@ int gen_init(GenState& st, const lfmq_config& c) {
                                        GSmem<BN_, MT_, EPI_>::TOTAL))
   LFMQ_GEMM_ATTR(256, EPI_FWD, 1);
   LFMQ_GEMM_ATTR(256, EPI_FWD, 2);
+  LFMQ_GEMM_ATTR(256, EPI_FWD_ACC, 1);
+  LFMQ_GEMM_ATTR(256, EPI_FWD_ACC, 2);
   LFMQ_GEMM_ATTR(128, EPI_BWD, 1);
   LFMQ_GEMM_ATTR(64, EPI_BWD, 1);
   LFMQ_GEMM_ATTR(128, EPI_STORE, 1);
   LFMQ_GEMM_ATTR(64, EPI_STORE, 1);
 #undef LFMQ_GEMM_ATTR
-  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(gwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(gwgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GWCfg<1>::SMEM));
+  LFMQ_CUDA_CHECK(cudaFuncSetAttribute(gwgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GWCfg<2>::SMEM));
   const int hsmem = (int)((H / 64) * 16384 + H * GH_O * 4 + 64 + 1024);
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(ghead_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(ghead_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
@@ -1221,14 +1278,57 @@ int gen_init(GenState& st, const lfmq_config& c) {
     const int bsm = (256 / ((int)H / 8) > 0 ? 256 / ((int)H / 8) : 1) * 2 * (int)H * 4;
     LFMQ_CUDA_CHECK(cudaFuncSetAttribute(gbn_drop_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
   }
+  if (getenv("LFMQ_TRACE_GEN")) {
+    LFMQ_CUDA_CHECK(cudaMalloc(&m.trace, (size_t)2 * m.L * T * 8 * sizeof(long long)));
+    LFMQ_CUDA_CHECK(cudaMemset(m.trace, 0, (size_t)2 * m.L * T * 8 * sizeof(long long)));
+  }
   m.enabled = true;
   st.weights_dirty = 1;
   return 0;
 }
 
+static void gen_print_trace(GenImpl& m, cudaStream_t s) {
+  if (!m.trace) return;
+  const size_t n = (size_t)2 * m.L * m.T * 8;
+  std::vector<long long> h(n);
+  cudaStreamSynchronize(s);
+  cudaMemcpy(h.data(), m.trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  for (int ph = 0; ph < 2; ++ph)
+    for (int l = 0; l < m.L; ++l)
+      for (int t = 0; t < m.T; t += 8) {
+        const long long* r = h.data() + (((size_t)ph * m.L + l) * m.T + t) * 8;
+        if (!r[0]) continue;
+        fprintf(stderr, "[gtrace %s l=%d t=%2d] wait-passed %lld first-stage %lld mma-issued %lld acc-full %lld epi-done %lld\n",
+                ph ? "bwd" : "fwd", l, t, r[1] - r[0], r[2] - r[0], r[3] - r[0], r[4] - r[0], r[5] - r[0]);
+      }
+}
+
 void gen_destroy(GenState& st) {
+  if (st.impl && st.impl->trace) cudaFree(st.impl->trace);
   delete st.impl;
   st.impl = nullptr;
+}
+
+// Launch of one tile_gemm_kernel instantiation; `pdl`: with the programmatic-stream-serialization attribute (the
+// kernel waits for its predecessor itself, see the kernel).  LFMQ_GEN_PDL=0 turns the attribute off.
+template <int BN, int EPI, int MT>
+static int launch_tile_gemm(dim3 grid, cudaStream_t s, bool pdl, const GArgs& g, const EpiParams& ep, const CUtensorMap& a0,
+                            const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a3, const CUtensorMap& b0,
+                            const CUtensorMap& b1) {
+  static const bool pdl_on = !(getenv("LFMQ_GEN_PDL") && atoi(getenv("LFMQ_GEN_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GSmem<BN, MT, EPI>::THREADS);
+  cfg.dynamicSmemBytes = GSmem<BN, MT, EPI>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_on) ? 1 : 0;
+  LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<BN, EPI, MT>, g, ep, a0, a1, a2, a3, b0, b1));
+  g_launches++;
+  return 0;
 }
 
 static DropoutKey gkey(const lfmq_config& c, int stream, int64_t step, float rate) {
@@ -1290,6 +1390,7 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
     const CUtensorMap& th = rec ? ly.tm_hm : ly.tm_h;
     for (int t = 0; t < T; ++t) {
       ep.t = t;
+      ep.trace = m.trace ? m.trace + (((size_t)0 * m.L + l) * T + t) * 8 : nullptr;
       GArgs g = {};
       g.a_row_base = t * Bp;
       g.b_row_base = 0;
@@ -1306,16 +1407,21 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
       }
       g.n_seg = ns;
       // 256-row CTA tiles when there are enough of them to fill the machine (a third less operand traffic per FLOP),
-      // else 128-row tiles, two CTAs per SM
-      if (dual)
-        tile_gemm_kernel<256, EPI_FWD, 2><<<dim3((nrt + 1) / 2, 4 * H / 256), GSmem<256, 2>::THREADS, GSmem<256, 2>::TOTAL, s>>>(
-            g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th, m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf,
-            m.x3 ? ly.tm_wf_lo : ly.tm_wf);
-      else
-        tile_gemm_kernel<256, EPI_FWD, 1><<<dim3(nrt, 4 * H / 256), GSmem<256, 1>::THREADS, GSmem<256, 1>::TOTAL, s>>>(
-            g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th, m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf,
-            m.x3 ? ly.tm_wf_lo : ly.tm_wf);
-      LFMQ_LAUNCH_CHECK();
+      // else 128-row tiles, two CTAs per SM.  Steps after the first of a layer follow another step kernel: PDL.
+      int rc;
+#define LFMQ_FWD_LAUNCH(EPI_, MT_, GRID_)                                                                          \
+  rc = launch_tile_gemm<256, EPI_, MT_>(GRID_, s, t > 0, g, ep, th, ly.tm_in, m.x3 ? ly.tm_h_lo : th,               \
+                                        m.x3 ? ly.tm_in_lo : ly.tm_in, ly.tm_wf, m.x3 ? ly.tm_wf_lo : ly.tm_wf)
+      const dim3 grid2((nrt + 1) / 2, 4 * H / 256), grid1(nrt, 4 * H / 256);
+      if (m.x3) {
+        if (dual) LFMQ_FWD_LAUNCH(EPI_FWD_ACC, 2, grid2);
+        else LFMQ_FWD_LAUNCH(EPI_FWD_ACC, 1, grid1);
+      } else {
+        if (dual) LFMQ_FWD_LAUNCH(EPI_FWD, 2, grid2);
+        else LFMQ_FWD_LAUNCH(EPI_FWD, 1, grid1);
+      }
+#undef LFMQ_FWD_LAUNCH
+      if (rc) return rc;
     }
     const bool last = (l == m.L - 1);
     __nv_bfloat16* yo = last ? m.head_in : m.layers[l + 1].in;
@@ -1388,8 +1494,10 @@ int gen_forward(GenState& st, const lfmq_config& c, const float* params, const f
 
 static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst, cudaStream_t s) {
   const int Ntot = 4 * m.H;
-  const int mt = (Mvalid + 127) / 128;
-  const int Mpad = mt * 128;
+  const bool dual = Mvalid > 128;                    // 256 x 256 CTA tiles when there are at least two 128-row M tiles
+  const int mrows = dual ? 256 : 128;
+  const int mt = (Mvalid + mrows - 1) / mrows;
+  const int Mpad = mt * mrows;
   const long rows = (long)m.T * m.Bp;
   GWgradParams wp;
   wp.n_kblocks = (int)cdivl(rows, 64);
@@ -1406,7 +1514,10 @@ static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst
     LFMQ_SET_ERR("weight-gradient partial buffer too small");
     return LFMQ_ERR_WORKSPACE;
   }
-  gwgrad_kernel<<<dim3(mt, Ntot / 256, S), GW_THREADS, GW_SMEM, s>>>(wp, tm_a, m.tm_dz_mn);
+  if (dual)
+    gwgrad_kernel<2><<<dim3(mt, Ntot / 256, S), GWCfg<2>::THREADS, GWCfg<2>::SMEM, s>>>(wp, tm_a, m.tm_dz_mn);
+  else
+    gwgrad_kernel<1><<<dim3(mt, Ntot / 256, S), GWCfg<1>::THREADS, GWCfg<1>::SMEM, s>>>(wp, tm_a, m.tm_dz_mn);
   LFMQ_LAUNCH_CHECK();
   const long n4 = (long)Mvalid * Ntot / 4;
   gwgrad_reduce_kernel<<<(int)cdivl(n4, 256), 256, 0, s>>>(S, Mvalid, Mpad, Ntot, m.wg_part, dst);
@@ -1462,6 +1573,7 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
     ep.rkey = gkey(c, 2 * l + 1, step, c.recurrent_dropout);
     for (int t = T - 1; t >= 0; --t) {
       ep.t = t;
+      ep.trace = m.trace ? m.trace + (((size_t)1 * m.L + l) * T + t) * 8 : nullptr;
       ep.has_rec = (t < T - 1) ? 1 : 0;
       GArgs g = {};
       g.a_row_base = (t + 1) * Bp;      // dz_{t+1}
@@ -1469,12 +1581,12 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       g.n_seg = ep.has_rec ? 1 : 0;
       g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
       if (m.BNU == 128)
-        tile_gemm_kernel<128, EPI_BWD, 1><<<dim3(nrt, H / 128), GSmem<128, 1, EPI_BWD>::THREADS, GSmem<128, 1, EPI_BWD>::TOTAL, s>>>(
-            g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_ub, ly.tm_ub);
+        rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(nrt, H / 128), s, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz,
+                                               ly.tm_ub, ly.tm_ub);
       else
-        tile_gemm_kernel<64, EPI_BWD, 1><<<dim3(nrt, H / 64), GSmem<64, 1, EPI_BWD>::THREADS, GSmem<64, 1, EPI_BWD>::TOTAL, s>>>(
-            g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_ub, ly.tm_ub);
-      LFMQ_LAUNCH_CHECK();
+        rc = launch_tile_gemm<64, EPI_BWD, 1>(dim3(nrt, H / 64), s, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz,
+                                              ly.tm_ub, ly.tm_ub);
+      if (rc) return rc;
     }
     st.prof->end(LFMQ_REGION_BWD, s);
     st.prof->begin(LFMQ_REGION_WGRAD, s);
@@ -1500,16 +1612,17 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
       const int row_tiles = T * Bp / 128;
       if (H % 128 == 0)
-        tile_gemm_kernel<128, EPI_STORE, 1><<<dim3(row_tiles, H / 128), GSmem<128, 1, EPI_STORE>::THREADS, GSmem<128, 1, EPI_STORE>::TOTAL, s>>>(
-            g, es, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_wb, ly.tm_wb);
+        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles, H / 128), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
+                                                 m.tm_dz, ly.tm_wb, ly.tm_wb);
       else
-        tile_gemm_kernel<64, EPI_STORE, 1><<<dim3(row_tiles, H / 64), GSmem<64, 1, EPI_STORE>::THREADS, GSmem<64, 1, EPI_STORE>::TOTAL, s>>>(
-            g, es, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_wb, ly.tm_wb);
-      LFMQ_LAUNCH_CHECK();
+        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles, H / 64), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
+                                                m.tm_dz, ly.tm_wb, ly.tm_wb);
+      if (rc) return rc;
     }
     st.prof->end(LFMQ_REGION_WGRAD, s);
   }
   (void)x;
+  gen_print_trace(m, s);
   return 0;
 }
 

@@ -155,6 +155,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// wait: returns once the preceding kernel of the stream has completed and its writes are visible (a no-op when the
+// kernel was not launched with the programmatic-stream-serialization attribute); launch_dependents: the next kernel's
+// CTAs may be dispatched as soon as every CTA of this grid has executed it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMEM allocation ---------------------------------------------------------------------------
 // Whole-warp calls.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

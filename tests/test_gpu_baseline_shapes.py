@@ -10,8 +10,9 @@
 
 Tolerances (stated, asserted):
   fp32 path:  every tensor max-norm relative error <= 1e-4 (5e-4 on updated weights after 3 steps)
-  bf16 path:  loss / mse_0 relative 3e-2; every gradient tensor cosine >= 0.995 and max-norm relative error <= 0.12
-              at T=48 (48 recurrent steps of bf16 operand rounding; T<=6 cases in test_gpu_bf16.py hold 6e-2)
+  bf16 path:  loss / mse_0 relative 3e-2; every gradient tensor cosine >= 0.9995 and max-norm relative error <= 5e-2
+              at T=48 (measured on B200, profiles/r02_summary.md: worst tensor 1.6e-2 / cosine 0.99994 on the cluster
+              kernels, 6.8e-3 / 0.99998 on the general path at H=512, L=2 with both dropouts)
 """
 import numpy as np
 import pytest
@@ -23,7 +24,7 @@ from util import make_engine, make_problem, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL32 = 1e-4
-BF16_LOSS, BF16_COS, BF16_REL = 3e-2, 0.995, 0.12
+BF16_LOSS, BF16_COS, BF16_REL = 3e-2, 0.9995, 5e-2
 
 
 def _cuda(a):
@@ -102,13 +103,13 @@ def test_cfg3_family_gradients_match_oracle(prec):
     eng.close()
 
 
-TRAJ_STEPS, TRAJ_BOUND = 50, 2e-2
+TRAJ_STEPS, TRAJ_BOUND = 50, 2e-3      # measured: 2.2e-4 (profiles/r02_summary.md)
 
 
 def test_bf16_loss_trajectory_tracks_fp32_on_bench_batches():
     """50 train steps on the bench's synthetic batches (B=4096, T=48, 4 rotating batches, Adadelta lr 0.6): the bf16
     tensor-core path's {loss, mse_0} stays within TRAJ_BOUND (relative) of the fp32 path at every step.  bench.py holds
-    its own final_loss_mse to the same bound (`loss_check`)."""
+    its own final_loss_mse to the same bound (`loss_check`, 2e-3)."""
     import bench
     rng = np.random.default_rng(bench.SEED)
     host = [bench.synthetic(4096, rng) for _ in range(4)]
