@@ -91,7 +91,7 @@ struct GArgs {
   int b_row_base;      // B row coordinate = b_row_base + BN * blockIdx.y
 };
 
-enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3 };   // _ACC: expf / tanhf nonlinearities (bf16x3)
+enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3, EPI_HEAD = 4 };   // _ACC: expf / tanhf (bf16x3)
 
 struct EpiParams {
   // common
@@ -116,6 +116,15 @@ struct EpiParams {
   // store
   __nv_bfloat16* out;           // [rows][ldc]
   int ldc;
+  // head (EPI_HEAD): pred = y Wo + bo, weighted MSE (losses.py:55-135), dLoss/dpred
+  const float* hy;              // targets [B][T][O] fp32 or null
+  const float* hdenom;          // {B_global, mask_count_global}
+  const float* hbo;             // [O]
+  float* hpreds;                // [B][T][O] fp32 or null
+  __nv_bfloat16* hdpb;          // [T*Bp][64] bf16, cols >= 16 stay zero: dLoss/dpred rows (operand of the dy and dWo GEMMs)
+  float* hpartial;              // [GH_PART][gridDim.x]
+  float hp1, hp2;
+  int hO, htarget, htrain;
   long long* trace;             // debug (LFMQ_TRACE_GEN=1): clock64 stamps of CTA (0,0): start, first stage landed, last MMA
                                 // issued, accumulator complete, epilogue done
 };
@@ -126,16 +135,17 @@ struct EpiParams {
 // CTAs leave: the loads are latency-bound (~5 K cycles per stage under load), bytes in flight are what buys bandwidth.
 template <int BN, int MT, int EPI = 0>
 struct GSmem {
+  static constexpr int EW = (EPI == 1) ? 2 : 1;          // warps per TMEM lane quadrant and M tile (2 for EPI_BWD)
   static constexpr uint32_t A_BYTES = MT * 128 * 128;     // MT x (128 rows x 64 bf16)
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   // one launch = one wave for the recurrence steps (<= 148 tiles: one CTA per SM, deep ring); the multi-wave GEMMs keep
   // two CTAs per SM
-  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2)) ? 2 : 1;      // (EPI 2 = EPI_STORE)
+  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2 || EPI == 4)) ? 2 : 1;      // (2 = EPI_STORE, 4 = EPI_HEAD)
   static constexpr int NS = (int)((CTAS_PER_SM == 2 ? 98304u : 196608u) / STAGE);
   static constexpr uint32_t BARS = NS * STAGE;
   static constexpr uint32_t TOTAL = BARS + 256 + 1024;    // + alignment slack
-  static constexpr int THREADS = 64 + 128 * MT;           // producer + MMA + 4 epilogue warps per M tile
+  static constexpr int THREADS = 64 + 128 * MT * EW;      // producer + MMA + 4 * EW epilogue warps per M tile
 };
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -168,6 +178,17 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   constexpr int U = BN / 4;                         // hidden units of this tile
   const int unit0 = blockIdx.y * U;
+  // c_{t-1} of the NEXT block is kept in flight while the current one is worked on (an L2 round trip per block otherwise)
+  float cnext[16];
+  const long cs_blk = 4L * 32 * 16;                 // cstate elements per 16-unit block
+  float* cs0 = p.cstate + ((((long)rt * p.NB16 + (unit0 >> 4)) * 4 + q) * 32 + lane) * 16;
+  if (p.t > 0) {
+    ld_global_v8f(cs0, cnext);
+    ld_global_v8f(cs0 + 8, cnext + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cnext[j] = 0.f;
+  }
 #pragma unroll 1
   for (int blk = 0; blk < U / 16; ++blk) {
     const int j0 = unit0 + blk * 16;
@@ -179,13 +200,12 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
     tmem_ld_32x32b_x16(ta + 32, vg);
     tmem_ld_32x32b_x16(ta + 48, vo);
     float cprev[16];
-    float* cs = p.cstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
-    if (p.t > 0) {
-      ld_global_v8f(cs, cprev);
-      ld_global_v8f(cs + 8, cprev + 8);
-    } else {
+    float* cs = cs0 + blk * cs_blk;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) cprev[j] = 0.f;
+    for (int j = 0; j < 16; ++j) cprev[j] = cnext[j];
+    if (p.t > 0 && blk + 1 < U / 16) {
+      ld_global_v8f(cs + cs_blk, cnext);
+      ld_global_v8f(cs + cs_blk + 8, cnext + 8);
     }
     tmem_ld_wait();
     const float* bs = bias_s + blk * 64;          // this tile's packed bias, staged in shared memory (broadcast reads)
@@ -251,91 +271,132 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
 
 // ---- EPI_BWD: BPTT pointwise algebra of step t ----------------------------------------------
 // Accumulator columns: hidden units unit0 .. unit0+BN-1 in order (rec = dz_{t+1} U^T, before the recurrent mask).
+// The saved gates / cell states come from HBM (~1.5 K cycles per dependent load): each warp keeps the operands of its
+// NEXT 16-unit block in flight while it works on the current one, and `ew` warps per lane quadrant split the blocks
+// (profiles/r02_summary.md: the serial version spent 22 K of a step's 40 K cycles here).
+struct BwdOps {
+  uint32_t wi[8], wf[8], wg[8], wo[8], wc[8], wcp[8], wd[8];
+};
+
+__device__ __forceinline__ void bwd_load_ops(const EpiParams& p, int rt, int q, int lane, long b, int j0, BwdOps& o) {
+  const int gblk = j0 >> 4;
+  const long gstride = 4L * 32 * 16;
+  const long tstride_c = (long)p.NRT * p.NB16 * 4 * 32 * 16;     // cst elements per time step
+  const long sb = (((long)p.t * p.NRT + rt) * p.NB16 + gblk);
+  const __nv_bfloat16* gp = p.gates + (((sb * 4 + 0) * 4 + q) * 32 + lane) * 16;
+  const __nv_bfloat16* cp_ = p.cst + ((sb * 4 + q) * 32 + lane) * 16;
+  ld_global_v8(gp, o.wi);
+  ld_global_v8(gp + gstride, o.wf);
+  ld_global_v8(gp + 2 * gstride, o.wg);
+  ld_global_v8(gp + 3 * gstride, o.wo);
+  ld_global_v8(cp_, o.wc);
+  if (p.t > 0) {
+    ld_global_v8(cp_ - tstride_c, o.wcp);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.wcp[e] = 0u;
+  }
+  ld_global_v8(p.dhout + ((long)p.t * p.Bp + b) * p.H + j0, o.wd);
+}
+
+__device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk, int rt, int q, int lane, long b, int j0,
+                                          const BwdOps& o) {
+  const int gblk = j0 >> 4;
+  float rec[16];
+  if (p.has_rec) {
+    uint32_t vr[16];
+    tmem_ld_32x32b_x16(tmem_blk, vr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rec[j] = __uint_as_float(vr[j]);
+    if (p.use_rec) {
+      float mk[16];
+      rec_mask16(p.rkey, p.row0 + b, p.H, j0, mk);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rec[j] *= mk[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rec[j] = 0.f;
+  }
+  float* dcs = p.dcstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
+  __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + j0;
+  float dcc[16];
+  if (p.t < p.T - 1) {
+    ld_global_v8f(dcs, dcc);
+    ld_global_v8f(dcs + 8, dcc + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dcc[j] = 0.f;
+  }
+  uint32_t zi[8], zf[8], zg[8], zo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {          // two units per packed word
+    float r2[4][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = 2 * e + u;
+      const float gi = u ? bf16_hi(o.wi[e]) : bf16_lo(o.wi[e]);
+      const float gf = u ? bf16_hi(o.wf[e]) : bf16_lo(o.wf[e]);
+      const float gg = u ? bf16_hi(o.wg[e]) : bf16_lo(o.wg[e]);
+      const float go = u ? bf16_hi(o.wo[e]) : bf16_lo(o.wo[e]);
+      const float ct = u ? bf16_hi(o.wc[e]) : bf16_lo(o.wc[e]);
+      const float cpv = u ? bf16_hi(o.wcp[e]) : bf16_lo(o.wcp[e]);
+      const float d = (u ? bf16_hi(o.wd[e]) : bf16_lo(o.wd[e])) + rec[j];
+      const float tc = tanh_approx(ct);
+      const float dcn = dcc[j] + d * go * (1.f - tc * tc);
+      dcc[j] = dcn * gf;
+      r2[0][u] = dcn * gg * gi * (1.f - gi);
+      r2[1][u] = dcn * cpv * gf * (1.f - gf);
+      r2[2][u] = dcn * gi * (1.f - gg * gg);
+      r2[3][u] = d * tc * go * (1.f - go);
+    }
+    zi[e] = pack_bf16x2(r2[0][0], r2[0][1]);
+    zf[e] = pack_bf16x2(r2[1][0], r2[1][1]);
+    zg[e] = pack_bf16x2(r2[2][0], r2[2][1]);
+    zo[e] = pack_bf16x2(r2[3][0], r2[3][1]);
+  }
+  st_global_v8f(dcs, dcc);
+  st_global_v8f(dcs + 8, dcc + 8);
+  st_global_v8(dzr, zi);
+  st_global_v8(dzr + (long)p.H, zf);
+  st_global_v8(dzr + 2L * p.H, zg);
+  st_global_v8(dzr + 3L * p.H, zo);
+}
+
+// `part` of `nparts` warps of this lane quadrant: blocks part, part + nparts, ...
 template <int BN>
-__device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt) {
+__device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt, int part, int nparts) {
   const int m = q * 32 + lane;
   const long b = (long)rt * 128 + m;
   const bool valid = b < p.B;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const int unit0 = blockIdx.y * BN;
-  const long gstride = 4L * 32 * 16;
-  const long tstride_c = (long)p.NRT * p.NB16 * 4 * 32 * 16;     // cst elements per time step
-#pragma unroll 1
-  for (int blk = 0; blk < BN / 16; ++blk) {
-    const int j0 = unit0 + blk * 16;
-    const int gblk = j0 >> 4;
-    float rec[16];
-    if (p.has_rec) {
-      uint32_t vr[16];
-      tmem_ld_32x32b_x16(tmem + lane_addr + blk * 16, vr);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) rec[j] = __uint_as_float(vr[j]);
-      if (p.use_rec) {
-        float mk[16];
-        rec_mask16(p.rkey, p.row0 + b, p.H, j0, mk);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rec[j] *= mk[j];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) rec[j] = 0.f;
-    }
-    float* dcs = p.dcstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
-    __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + j0;
+  constexpr int NB = BN / 16;
+  if (!valid) {        // rows beyond the batch: dz must be exactly zero (the weight-gradient GEMM sums over all rows)
     uint32_t w[8];
-    if (!valid) {        // rows beyond the batch: dz must be exactly zero (the weight-gradient GEMM sums over all rows)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) w[e] = 0u;
+    for (int e = 0; e < 8; ++e) w[e] = 0u;
+    for (int blk = part; blk < NB; blk += nparts) {
+      __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + unit0 + blk * 16;
 #pragma unroll
       for (int g = 0; g < 4; ++g) st_global_v8(dzr + (long)g * p.H, w);
-      continue;
     }
-    const long sb = (((long)p.t * p.NRT + rt) * p.NB16 + gblk);
-    const __nv_bfloat16* gp = p.gates + (((sb * 4 + 0) * 4 + q) * 32 + lane) * 16;
-    const __nv_bfloat16* cp_ = p.cst + ((sb * 4 + q) * 32 + lane) * 16;
-    uint32_t wi[8], wf[8], wg[8], wo[8], wc[8], wcp[8], wd[8];
-    ld_global_v8(gp, wi);
-    ld_global_v8(gp + gstride, wf);
-    ld_global_v8(gp + 2 * gstride, wg);
-    ld_global_v8(gp + 3 * gstride, wo);
-    ld_global_v8(cp_, wc);
-    if (p.t > 0) {
-      ld_global_v8(cp_ - tstride_c, wcp);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) wcp[e] = 0u;
+    return;
+  }
+  BwdOps A, B2;
+  int blk = part;
+  if (blk < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + blk * 16, A);
+#pragma unroll 1
+  for (; blk < NB; blk += 2 * nparts) {
+    const int nxt = blk + nparts;
+    if (nxt < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + nxt * 16, B2);
+    bwd_block(p, tmem + lane_addr + blk * 16, rt, q, lane, b, unit0 + blk * 16, A);
+    if (nxt < NB) {
+      const int nx2 = nxt + nparts;
+      if (nx2 < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + nx2 * 16, A);
+      bwd_block(p, tmem + lane_addr + nxt * 16, rt, q, lane, b, unit0 + nxt * 16, B2);
     }
-    ld_global_v8(p.dhout + ((long)p.t * p.Bp + b) * p.H + j0, wd);
-    float dcc[16];
-    if (p.t < p.T - 1) {
-      ld_global_v8f(dcs, dcc);
-      ld_global_v8f(dcs + 8, dcc + 8);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) dcc[j] = 0.f;
-    }
-    float gi[16], gf[16], gg[16], go[16], ct[16], cpv[16], dh[16];
-    unpack16(wi, gi); unpack16(wf, gf); unpack16(wg, gg); unpack16(wo, go);
-    unpack16(wc, ct); unpack16(wcp, cpv); unpack16(wd, dh);
-    float zi[16], zf[16], zg[16], zo[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float d = dh[j] + rec[j];
-      const float tc = tanh_approx(ct[j]);
-      const float dcn = dcc[j] + d * go[j] * (1.f - tc * tc);
-      dcc[j] = dcn * gf[j];
-      zi[j] = dcn * gg[j] * gi[j] * (1.f - gi[j]);
-      zf[j] = dcn * cpv[j] * gf[j] * (1.f - gf[j]);
-      zg[j] = dcn * gi[j] * (1.f - gg[j] * gg[j]);
-      zo[j] = d * tc * go[j] * (1.f - go[j]);
-    }
-    st_global_v8f(dcs, dcc);
-    st_global_v8f(dcs + 8, dcc + 8);
-    pack16(zi, w); st_global_v8(dzr, w);
-    pack16(zf, w); st_global_v8(dzr + (long)p.H, w);
-    pack16(zg, w); st_global_v8(dzr + 2L * p.H, w);
-    pack16(zo, w); st_global_v8(dzr + 3L * p.H, w);
   }
 }
 
@@ -357,6 +418,83 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, uint32_t tmem, int
   }
 }
 
+// ---- EPI_HEAD: Dense + weighted MSE + dLoss/dpred on the accumulator of pred = y Wo (N = 16) ---------------------------
+// One CTA = one 128-row tile (t, rt) of the time-major head input; thread = row.  (rnn_point_estimate.py:105;
+// model_utils/losses.py:55-135)
+constexpr int GH_O = 16;
+constexpr int GH_PART = GH_O + 4;      // dbo | s0 s1 s2
+__device__ __forceinline__ void epi_head(const EpiParams& p, uint32_t tmem, int q, int lane, float* red_s) {
+  const int tile = blockIdx.x;
+  const int t = tile / p.NRT, rt = tile % p.NRT;
+  const int m = q * 32 + lane;
+  const long b = (long)rt * 128 + m;
+  const bool valid = b < p.B;
+  if (m < GH_PART) red_s[m] = 0.f;
+  named_bar_sync(1, 128);
+  uint32_t v[16];
+  tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16), v);
+  const long r = b * p.T + t;          // row of the caller's [B][T][O] tensors
+  float yt[GH_O];
+#pragma unroll
+  for (int k = 0; k < GH_O; ++k) yt[k] = 0.f;
+  if (p.hy && valid)
+    for (int k = 0; k < p.hO; ++k) yt[k] = p.hy[r * p.hO + k];
+  tmem_ld_wait();
+  float pr[GH_O];
+#pragma unroll
+  for (int k = 0; k < GH_O; ++k) pr[k] = (k < p.hO) ? __uint_as_float(v[k]) + __ldg(p.hbo + k) : 0.f;
+  if (p.hpreds && valid)
+    for (int k = 0; k < p.hO; ++k) p.hpreds[r * p.hO + k] = pr[k];
+  if (!p.hy) return;
+  float c_all = 0.f, c_last = 0.f, c_tar = 0.f;
+  if (p.htrain) {
+    const float Bg = p.hdenom[0], Mg = p.hdenom[1];
+    c_all = (1.f - p.hp1) * (1.f - p.hp2) / ((float)p.hO * Mg);
+    c_last = (1.f - p.hp1) * p.hp2 / (Bg * (float)p.hO);
+    c_tar = p.hp1 / Bg;
+  }
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < GH_O; ++k) any |= (yt[k] != 0.0f);          // losses.py:72
+  const float mk = (any && valid) ? 1.f : 0.f;
+  const bool last = (t == p.T - 1);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  float dp[GH_O];
+#pragma unroll
+  for (int k = 0; k < GH_O; ++k) {
+    const float d = (k < p.hO && valid) ? (pr[k] * mk - yt[k]) : 0.f;  // losses.py:75
+    const float d2 = d * d;
+    s2 += d2;
+    float coef = c_all;
+    if (last) {
+      s1 += d2;
+      coef += c_last;
+      if (k == p.htarget) {
+        s0 += d2;
+        coef += c_tar;
+      }
+    }
+    dp[k] = p.htrain ? 2.f * d * coef * mk : 0.f;
+  }
+  if (p.htrain) {       // every row of the tile is written (zeros beyond the batch): the dy / dWo GEMMs run over all rows
+    uint32_t w[8];
+    pack16(dp, w);
+    st_global_v8(p.hdpb + ((long)t * p.Bp + b) * 64, w);
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+#pragma unroll
+  for (int k = 0; k < GH_O; ++k) dp[k] = warp_sum(dp[k]);
+  if (lane == 0) {
+    atomicAdd(&red_s[GH_O + 0], s0);
+    atomicAdd(&red_s[GH_O + 1], s1);
+    atomicAdd(&red_s[GH_O + 2], s2);
+    if (p.htrain)
+      for (int k = 0; k < GH_O; ++k) atomicAdd(&red_s[k], dp[k]);
+  }
+  named_bar_sync(1, 128);
+  if (m < GH_PART) p.hpartial[(long)m * gridDim.x + blockIdx.x] = red_s[m];
+}
+
 template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI>::CTAS_PER_SM)
     tile_gemm_kernel(GArgs g, EpiParams ep, const __grid_constant__ CUtensorMap tmA0,
@@ -372,6 +510,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t TMEM_COLS = (BN * MT < 32) ? 32 : BN * MT;
+  __shared__ float red_s[EPI == EPI_HEAD ? GH_PART : 1];
   __shared__ float bias_s[(EPI == EPI_FWD || EPI == EPI_FWD_ACC) ? BN : 1];
   if constexpr (EPI == EPI_FWD || EPI == EPI_FWD_ACC)
     for (int i = tid; i < BN; i += S::THREADS) bias_s[i] = ep.bias[blockIdx.y * BN + i];    // weights: not the predecessor's
@@ -470,7 +609,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     griddep_wait();
     griddep_launch_dependents();
     const int q = warp & 3;
-    const int mt = (warp - 2) >> 2;                  // which 128-row M tile of the CTA this warp's quadrant belongs to
+    const int grp = (warp - 2) >> 2;                 // group of four warps = one pass over the four TMEM lane quadrants
+    const int mt = grp / S::EW;                      // which 128-row M tile of the CTA this group works on
+    const int part = grp % S::EW;                    // ... and which share of its column blocks
     const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
     if (total_kb > 0) {
       mbar_wait(acc_full, 0);
@@ -478,12 +619,15 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     }
     const uint32_t tacc = tmem + mt * BN;
     if (tr && warp == 2 && lane == 0) ep.trace[4] = clock64();
-    if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
+    if constexpr (EPI == EPI_HEAD) {
+      epi_head(ep, tacc, q, lane, red_s);
+    } else if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
       if constexpr (EPI == EPI_FWD) epi_fwd<BN, false>(ep, tacc, q, lane, rt, bias_s);
       if constexpr (EPI == EPI_FWD_ACC) epi_fwd<BN, true>(ep, tacc, q, lane, rt, bias_s);
-      if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt);
+      if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt, part, S::EW);
       if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
     }
+    (void)part;
     if (tr && warp == 2 && lane == 0) ep.trace[5] = clock64();
   }
   __syncwarp();
@@ -655,10 +799,11 @@ __global__ void gcast_x_kernel(int B, int T, int F, int Bp, int Ipad, const floa
 //   biasp [4H]    bias in Wf's row order, same pre-scale
 struct GPackArgs {
   int H, I, Ipad, Kp;
-  float hs;
-  const float *W, *U, *bias;
+  float hs, eps;
+  const float *W, *U, *bias, *gamma, *beta, *mean, *var;
   __nv_bfloat16 *Wf, *Wf_lo, *Ub, *Wb;
   float* biasp;
+  float* bn;          // [4][H]: a = gamma * inv | b = beta - mean * a | mean | inv   (BN as the affine map it is here)
 };
 __global__ void gpack_kernel(GPackArgs a) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,15 +829,49 @@ __global__ void gpack_kernel(GPackArgs a) {
     const int tile = n / 256, blk = (n % 256) / 64, gate = (n % 64) / 16, jj = n % 16;
     a.biasp[n] = ((gate == 2) ? 1.0f : a.hs) * a.bias[gate * H + tile * 64 + blk * 16 + jj];
   }
+  if (idx < H) {
+    const int j = (int)idx;
+    const float inv = 1.0f / sqrtf(a.var[j] + a.eps);
+    const float ga = a.gamma[j] * inv;
+    a.bn[j] = ga;
+    a.bn[H + j] = a.beta[j] - a.mean[j] * ga;
+    a.bn[2 * H + j] = a.mean[j];
+    a.bn[3 * H + j] = inv;
+  }
+}
+
+// Head operands: WoT [16][H] (B operand of pred = y Wo: row = output k, K = hidden) and WoS [H][64] (B operand of
+// dy = dpred Wo^T: row = hidden unit, K = output k, zero beyond O).
+__global__ void gpack_head_kernel(int H, int O, const float* __restrict__ Wo, __nv_bfloat16* __restrict__ WoT,
+                                  __nv_bfloat16* __restrict__ WoS) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 16 * H) {
+    const int k = idx / H, j = idx % H;
+    WoT[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
+  }
+  if (idx < H * 64) {
+    const int j = idx / 64, k = idx % 64;
+    WoS[idx] = __float2bfloat16(k < O ? Wo[j * O + k] : 0.f);
+  }
+}
+
+// dWo[j][k] = sum_z partial[z][j][k] (k < O) from the weight-gradient GEMM of the head (N padded to 256)
+__global__ void ghead_wo_reduce_kernel(int S, int H, int O, int Mpad, const float* __restrict__ partial,
+                                       float* __restrict__ gWo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * O) return;
+  const int j = idx / O, k = idx % O;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[((long)z * Mpad + j) * 256 + k];
+  gWo[idx] = s;
 }
 
 // y = Dropout(BN(h)) (rnn_point_estimate.py:88-89; BN is the inference affine in both modes):
 // hseq slots 1..T -> in_next [T][Bp][H] (+ low halves for bf16x3).  8 columns per thread.
-__global__ void gbn_drop_fwd_kernel(int B, int T, int H, int Bp, const __nv_bfloat16* __restrict__ hseq,
-                                    const __nv_bfloat16* __restrict__ hseq_lo, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, const float* __restrict__ mean,
-                                    const float* __restrict__ var, float eps, int use_dropout, DropoutKey key,
-                                    int64_t row0, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo) {
+__global__ void __launch_bounds__(256)
+    gbn_drop_fwd_kernel(int B, int T, int H, int Bp, const __nv_bfloat16* __restrict__ hseq,
+                        const __nv_bfloat16* __restrict__ hseq_lo, const float* __restrict__ bn, int use_dropout,
+                        DropoutKey key, int64_t row0, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo) {
   const int c8 = H / 8;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)T * B * c8) return;
@@ -718,13 +897,13 @@ __global__ void gbn_drop_fwd_kernel(int B, int T, int H, int Bp, const __nv_bflo
 #pragma unroll
     for (int e = 0; e < 8; ++e) mk[e] = 1.f;
   }
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(bn + c * 8)), a1 = __ldg(reinterpret_cast<const float4*>(bn + c * 8 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bn + H + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bn + H + c * 8 + 4));
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float o[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int j = c * 8 + e;
-    const float inv = 1.0f / sqrtf(var[j] + eps);
-    o[e] = (gamma[j] * (hv[e] - mean[j]) * inv + beta[j]) * mk[e];
-  }
+  for (int e = 0; e < 8; ++e) o[e] = fmaf(av[e], hv[e], bv[e]) * mk[e];
   uint4 w;
   w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
   *reinterpret_cast<uint4*>(y + off) = w;
@@ -740,11 +919,10 @@ __global__ void gbn_drop_fwd_kernel(int B, int T, int H, int Bp, const __nv_bflo
 
 // Dropout / BN backward: dhout = dy * mask * gamma * inv; per-CTA partial sums of dgamma, dbeta.
 // Thread = 8 columns; a CTA of 256 threads holds 256 / (H/8) rows at a time and walks its row range.
-constexpr int GBN_ROWS = 512;
+constexpr int GBN_ROWS = 64;
 __global__ void __launch_bounds__(256)
     gbn_drop_bwd_kernel(int B, int T, int H, int Bp, const __nv_bfloat16* __restrict__ dy,
-                        const __nv_bfloat16* __restrict__ hseq, const float* __restrict__ gamma,
-                        const float* __restrict__ mean, const float* __restrict__ var, float eps, int use_dropout,
+                        const __nv_bfloat16* __restrict__ hseq, const float* __restrict__ bn, int use_dropout,
                         DropoutKey key, int64_t row0, __nv_bfloat16* __restrict__ dhout, float* __restrict__ partial) {
   extern __shared__ float red[];      // [RL][2H]
   const int c8 = H / 8;
@@ -754,9 +932,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int j = c * 8 + e;
-    g[e] = gamma[j];
-    mu[e] = mean[j];
-    inv[e] = 1.0f / sqrtf(var[j] + eps);
+    g[e] = bn[j];
+    mu[e] = bn[2 * H + j];
+    inv[e] = bn[3 * H + j];
     sg[e] = 0.f;
     sb[e] = 0.f;
   }
@@ -764,6 +942,7 @@ __global__ void __launch_bounds__(256)
   const long r0 = (long)blockIdx.x * GBN_ROWS;
   const long r1 = min(rows, r0 + GBN_ROWS);
   if (rl < RL) {
+#pragma unroll 2
     for (long r = r0 + rl; r < r1; r += RL) {
       const long b = r % B;
       const int t = (int)(r / B);
@@ -785,7 +964,7 @@ __global__ void __launch_bounds__(256)
       for (int e = 0; e < 8; ++e) {
         sg[e] += d[e] * (hv[e] - mu[e]) * inv[e];
         sb[e] += d[e];
-        o[e] = d[e] * g[e] * inv[e];
+        o[e] = d[e] * g[e];
       }
       uint4 w;
       w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
@@ -821,20 +1000,31 @@ __global__ void gpartial_reduce_kernel(int n_cta, int n0, int n1, const float* _
   }
 }
 
-// db = column sums of dz (bf16 [rows][N]) -> partial[chunk][N]; thread = 2 columns
+// db = column sums of dz (bf16 [rows][N]) -> partial[column][chunk]; thread = 8 columns (128-bit loads), 4 rows in flight
 __global__ void __launch_bounds__(128) gcolsum_kernel(long rows, int N, long rows_per_chunk,
                                                      const __nv_bfloat16* __restrict__ A, float* __restrict__ partial) {
-  const int col2 = blockIdx.x * 128 + threadIdx.x;       // pair index
-  if (col2 * 2 >= N) return;
+  const int c8 = blockIdx.x * 128 + threadIdx.x;       // group of 8 columns
+  if (c8 * 8 >= N) return;
   const long r0 = (long)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
-  float s0 = 0.f, s1 = 0.f;
-  for (long r = r0; r < r1; ++r) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(A + r * N + col2 * 2);
-    s0 += bf16_lo(w);
-    s1 += bf16_hi(w);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  long r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const uint4*>(A + (r + u) * N + c8 * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[0] += bf16_lo(w[u].x); s[1] += bf16_hi(w[u].x); s[2] += bf16_lo(w[u].y); s[3] += bf16_hi(w[u].y);
+      s[4] += bf16_lo(w[u].z); s[5] += bf16_hi(w[u].z); s[6] += bf16_lo(w[u].w); s[7] += bf16_hi(w[u].w);
+    }
   }
-  partial[(long)(col2 * 2) * gridDim.y + blockIdx.y] = s0;
-  partial[(long)(col2 * 2 + 1) * gridDim.y + blockIdx.y] = s1;
+  for (; r < r1; ++r) {
+    const uint4 w = *reinterpret_cast<const uint4*>(A + r * N + c8 * 8);
+    s[0] += bf16_lo(w.x); s[1] += bf16_hi(w.x); s[2] += bf16_lo(w.y); s[3] += bf16_hi(w.y);
+    s[4] += bf16_lo(w.z); s[5] += bf16_hi(w.z); s[6] += bf16_lo(w.w); s[7] += bf16_hi(w.w);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) partial[(long)(c8 * 8 + e) * gridDim.y + blockIdx.y] = s[e];
 }
 
 // =============================================================================================
@@ -842,7 +1032,6 @@ __global__ void __launch_bounds__(128) gcolsum_kernel(long rows, int N, long row
 // One thread per row of a 128-row tile (TMA-staged, SW128), Wo broadcast from shared memory.
 // (rnn_point_estimate.py:105; model_utils/losses.py:55-135)
 // =============================================================================================
-constexpr int GH_O = 16;
 struct GHeadParams {
   int B, T, O, H, Bp, NRT, target_idx, train;
   const float *Wo, *bo;
@@ -855,8 +1044,6 @@ struct GHeadParams {
   float* dpred;              // [T*Bp][16] fp32 (train)
   float* partial;            // [GH_PART][grid]
 };
-constexpr int GH_PART = GH_O + 4;      // dbo | s0 s1 s2
-
 template <bool TRAIN>
 __global__ void __launch_bounds__(128, 1) ghead_rows_kernel(GHeadParams p, const __grid_constant__ CUtensorMap tm_y) {
   extern __shared__ uint8_t smem_raw[];
@@ -1062,12 +1249,12 @@ __global__ void ghead_reduce_kernel(int n_cta, const float* __restrict__ partial
   const int lane = threadIdx.x & 31;
   const int nW = H * GH_O;
   if (i < nW) {
-    if (!train) return;
+    if (!train || !gWo) return;
     const int j = i / GH_O, k = i % GH_O;
     double s = 0.0;
     for (int c = lane; c < n_wcta; c += 32) s += wpartial[(long)i * n_wcta + c];
     s = warp_sum(s);
-    if (lane == 0 && k < O) gWo[j * O + k] = (float)s;
+    if (lane == 0 && k < O && gWo) gWo[j * O + k] = (float)s;
     return;
   }
   const int q = i - nW;
@@ -1102,7 +1289,7 @@ struct GenLayer {
   int I, Ipad, Kp;
   __nv_bfloat16 *hseq, *hseq_lo, *hmseq, *in, *in_lo, *gates, *cst;
   __nv_bfloat16 *Wf, *Wf_lo, *Ub, *Wb;
-  float* biasp;
+  float *biasp, *bn;
   CUtensorMap tm_h, tm_h_lo, tm_hm, tm_in, tm_in_lo, tm_wf, tm_wf_lo, tm_ub, tm_wb;    // K-major (recurrence, dx)
   CUtensorMap tm_hA_mn, tm_in_mn;                                                       // MN-major (weight gradients)
 };
@@ -1116,6 +1303,10 @@ struct GenImpl {
   std::vector<GenLayer> layers;
   __nv_bfloat16 *head_in = nullptr, *head_in_lo = nullptr;      // in[L]
   CUtensorMap tm_head_in;
+  // tensor-core head (bf16): packed Wo, bf16 dLoss/dpred rows, per-tile loss partials
+  __nv_bfloat16 *WoT = nullptr, *WoS = nullptr, *dpb = nullptr;
+  float* head_tc_part = nullptr;
+  CUtensorMap tm_wot, tm_wos, tm_dpb, tm_dpb_mn, tm_head_in_mn;
   float *cstate = nullptr, *dcstate = nullptr;
   __nv_bfloat16 *dz = nullptr, *dy = nullptr, *dhout = nullptr;
   CUtensorMap tm_dz, tm_dz_mn;
@@ -1176,6 +1367,7 @@ void gen_layout(GenState& st, const lfmq_config& c, const GenLayerOff* lo, int64
     ly.Wf = reinterpret_cast<__nv_bfloat16*>(take((size_t)4 * H * ly.Kp * 2));
     ly.Wf_lo = m.x3 ? reinterpret_cast<__nv_bfloat16*>(take((size_t)4 * H * ly.Kp * 2)) : nullptr;
     ly.biasp = reinterpret_cast<float*>(take(4 * H * 4));
+    ly.bn = reinterpret_cast<float*>(take(4 * H * 4));
     if (m.train_ws) {
       ly.gates = reinterpret_cast<__nv_bfloat16*>(take(T * Bp * 4 * H * 2));
       ly.cst = reinterpret_cast<__nv_bfloat16*>(take(T * Bp * H * 2));
@@ -1187,6 +1379,10 @@ void gen_layout(GenState& st, const lfmq_config& c, const GenLayerOff* lo, int64
   }
   m.head_in = reinterpret_cast<__nv_bfloat16*>(take(T * Bp * H * 2));
   m.head_in_lo = m.x3 ? reinterpret_cast<__nv_bfloat16*>(take(T * Bp * H * 2)) : nullptr;
+  m.WoT = reinterpret_cast<__nv_bfloat16*>(take(16 * H * 2));
+  m.WoS = reinterpret_cast<__nv_bfloat16*>(take(H * 64 * 2));
+  m.head_tc_part = reinterpret_cast<float*>(take((size_t)GH_PART * T * m.NRT * 4));
+  m.dpb = m.train_ws ? reinterpret_cast<__nv_bfloat16*>(take(T * Bp * 64 * 2)) : nullptr;
   m.cstate = reinterpret_cast<float*>(take(Bp * H * 4));
   m.head_ctas = 148;
   m.head_part = reinterpret_cast<float*>(take((size_t)GH_PART * m.head_ctas * 4));
@@ -1200,7 +1396,7 @@ void gen_layout(GenState& st, const lfmq_config& c, const GenLayerOff* lo, int64
     m.head_wpart = reinterpret_cast<float*>(take((size_t)H * GH_O * m.head_wctas * 4));
     m.bn_ctas_max = (int)cdivl((long)T * m.maxB, GBN_ROWS);
     m.bn_part = reinterpret_cast<float*>(take((size_t)2 * H * m.bn_ctas_max * 4));
-    m.cs_chunks = 64;
+    m.cs_chunks = 1024;
     m.cs_part = reinterpret_cast<float*>(take((size_t)4 * H * m.cs_chunks * 4));
     const size_t Mmax = (H > 64 ? H : 128);               // dU: H rows; dW: Ipad rows (<= max(H, 64..1024))
     size_t mp = (Mmax + 255) / 256 * 256;
@@ -1249,6 +1445,14 @@ int gen_init(GenState& st, const lfmq_config& c) {
   LFMQ_CUDA_CHECK(cudaMemset(m.head_in, 0, T * Bp * H * 2));
   if (m.head_in_lo) LFMQ_CUDA_CHECK(cudaMemset(m.head_in_lo, 0, T * Bp * H * 2));
   if ((rc = gmap_2d(&m.tm_head_in, m.head_in, H, T * Bp, 64, 128))) return rc;
+  if ((rc = gmap_2d(&m.tm_wot, m.WoT, H, 16, 64, 16))) return rc;
+  if (m.train_ws) {
+    LFMQ_CUDA_CHECK(cudaMemset(m.dpb, 0, T * Bp * 64 * 2));       // columns >= 16 stay zero for good
+    if ((rc = gmap_2d(&m.tm_wos, m.WoS, 64, H, 64, (H % 128 == 0) ? 128 : 64))) return rc;
+    if ((rc = gmap_2d(&m.tm_dpb, m.dpb, 64, T * Bp, 64, 128))) return rc;
+    if ((rc = gmap_2d(&m.tm_dpb_mn, m.dpb, 64, T * Bp, 64, 64))) return rc;
+    if ((rc = gmap_2d(&m.tm_head_in_mn, m.head_in, H, T * Bp, 64, 64))) return rc;
+  }
   if (m.train_ws) {
     LFMQ_CUDA_CHECK(cudaMemset(m.dz, 0, T * Bp * 4 * H * 2));
     LFMQ_CUDA_CHECK(cudaMemset(m.dy, 0, T * Bp * H * 2));
@@ -1266,6 +1470,7 @@ int gen_init(GenState& st, const lfmq_config& c) {
   LFMQ_GEMM_ATTR(256, EPI_FWD_ACC, 2);
   LFMQ_GEMM_ATTR(128, EPI_BWD, 1);
   LFMQ_GEMM_ATTR(64, EPI_BWD, 1);
+  LFMQ_GEMM_ATTR(16, EPI_HEAD, 1);
   LFMQ_GEMM_ATTR(128, EPI_STORE, 1);
   LFMQ_GEMM_ATTR(64, EPI_STORE, 1);
 #undef LFMQ_GEMM_ATTR
@@ -1342,7 +1547,7 @@ static DropoutKey gkey(const lfmq_config& c, int stream, int64_t step, float rat
   return k;
 }
 
-static int gen_pack(GenState& st, const float* params, cudaStream_t s) {
+static int gen_pack(GenState& st, const float* params, float eps, cudaStream_t s) {
   GenImpl& m = *st.impl;
   if (!st.weights_dirty) return 0;
   for (int l = 0; l < m.L; ++l) {
@@ -1350,12 +1555,16 @@ static int gen_pack(GenState& st, const float* params, cudaStream_t s) {
     GPackArgs a;
     a.H = m.H; a.I = ly.I; a.Ipad = ly.Ipad; a.Kp = ly.Kp;
     a.hs = m.x3 ? 1.0f : 0.5f;
+    a.eps = eps;
     a.W = params + ly.off.oW; a.U = params + ly.off.oU; a.bias = params + ly.off.ob;
-    a.Wf = ly.Wf; a.Wf_lo = ly.Wf_lo; a.Ub = ly.Ub; a.Wb = ly.Wb; a.biasp = ly.biasp;
+    a.gamma = params + ly.off.ogamma; a.beta = params + ly.off.obeta; a.mean = params + ly.off.omean; a.var = params + ly.off.ovar;
+    a.Wf = ly.Wf; a.Wf_lo = ly.Wf_lo; a.Ub = ly.Ub; a.Wb = ly.Wb; a.biasp = ly.biasp; a.bn = ly.bn;
     const long n = (long)4 * m.H * ly.Kp;
     gpack_kernel<<<(int)cdivl(n, 256), 256, 0, s>>>(a);
     LFMQ_LAUNCH_CHECK();
   }
+  gpack_head_kernel<<<(int)cdivl((long)m.H * 64, 256), 256, 0, s>>>(m.H, m.O, params + m.oWo, m.WoT, m.WoS);
+  LFMQ_LAUNCH_CHECK();
   st.weights_dirty = 0;
   return 0;
 }
@@ -1427,11 +1636,53 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
     __nv_bfloat16* yo = last ? m.head_in : m.layers[l + 1].in;
     __nv_bfloat16* yo_lo = last ? m.head_in_lo : m.layers[l + 1].in_lo;
     const long n = (long)T * B * (H / 8);
-    gbn_drop_fwd_kernel<<<(int)cdivl(n, 256), 256, 0, s>>>(
-        B, T, H, Bp, ly.hseq, ly.hseq_lo, params + ly.off.ogamma, params + ly.off.obeta, params + ly.off.omean,
-        params + ly.off.ovar, c.bn_epsilon, drop ? 1 : 0, gkey(c, 2 * l, step, c.dropout), row0, yo, yo_lo);
+    gbn_drop_fwd_kernel<<<(int)cdivl(n, 256), 256, 0, s>>>(B, T, H, Bp, ly.hseq, ly.hseq_lo, ly.bn, drop ? 1 : 0,
+                                                           gkey(c, 2 * l, step, c.dropout), row0, yo, yo_lo);
     LFMQ_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// D[Mvalid x Ntot] = A^T B over the T*Bp time-major rows (split-K partials in wg_part, [S][Mpad][Ntot]); the caller reduces
+static int gen_wgrad_gemm(GenImpl& m, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int Mvalid, int Ntot, int* S_out,
+                          int* Mpad_out, cudaStream_t s) {
+  const bool dual = Mvalid > 128;                    // 256 x 256 CTA tiles when there are at least two 128-row M tiles
+  const int mrows = dual ? 256 : 128;
+  const int mt = (Mvalid + mrows - 1) / mrows;
+  const int Mpad = mt * mrows;
+  const long rows = (long)m.T * m.Bp;
+  GWgradParams wp;
+  wp.n_kblocks = (int)cdivl(rows, 64);
+  int S = 148 / (mt * (Ntot / 256));
+  if (S < 1) S = 1;
+  if (S > 8) S = 8;
+  if (S > wp.n_kblocks) S = wp.n_kblocks;
+  wp.kb_per_split = (wp.n_kblocks + S - 1) / S;
+  S = (wp.n_kblocks + wp.kb_per_split - 1) / wp.kb_per_split;
+  wp.Mpad = Mpad;
+  wp.Ntot = Ntot;
+  wp.partial = m.wg_part;
+  if ((size_t)S * Mpad * Ntot > m.wg_part_elems) {
+    LFMQ_SET_ERR("weight-gradient partial buffer too small");
+    return LFMQ_ERR_WORKSPACE;
+  }
+  if (dual)
+    gwgrad_kernel<2><<<dim3(mt, Ntot / 256, S), GWCfg<2>::THREADS, GWCfg<2>::SMEM, s>>>(wp, tm_a, tm_b);
+  else
+    gwgrad_kernel<1><<<dim3(mt, Ntot / 256, S), GWCfg<1>::THREADS, GWCfg<1>::SMEM, s>>>(wp, tm_a, tm_b);
+  LFMQ_LAUNCH_CHECK();
+  *S_out = S;
+  *Mpad_out = Mpad;
+  return 0;
+}
+
+static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst, cudaStream_t s) {
+  const int Ntot = 4 * m.H;
+  int S = 0, Mpad = 0, rc;
+  if ((rc = gen_wgrad_gemm(m, tm_a, m.tm_dz_mn, Mvalid, Ntot, &S, &Mpad, s))) return rc;
+  const long n4 = (long)Mvalid * Ntot / 4;
+  gwgrad_reduce_kernel<<<(int)cdivl(n4, 256), 256, 0, s>>>(S, Mvalid, Mpad, Ntot, m.wg_part, dst);
+  LFMQ_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1448,6 +1699,53 @@ static int gen_run_head(GenState& st, const lfmq_config& c, const float* params,
   h.dy = train ? m.dy : nullptr;
   h.dpred = train ? m.dpred : nullptr;
   h.partial = m.head_part;
+  if (!m.x3) {
+    // Tensor-core head: pred = y Wo as a tcgen05 GEMM (N = 16) with the loss in its epilogue; training adds
+    // dy = dpred Wo^T (K = 16 padded to one k-block) and dWo = y^T dpred (the weight-gradient GEMM, N padded to 256).
+    // The fp32-accumulating SIMT head below stays for LFMQ_PREC_BF16X3 (1e-4 tolerance).
+    const int ntile = m.T * m.NRT;                  // every row tile of the time-major buffers (zeros beyond the batch)
+    EpiParams ep = {};
+    ep.T = m.T; ep.B = B; ep.Bp = m.Bp; ep.H = m.H; ep.NRT = m.NRT; ep.NB16 = m.NB16;
+    ep.hy = y; ep.hdenom = denom; ep.hbo = params + m.obo; ep.hpreds = preds; ep.hdpb = m.dpb;
+    ep.hpartial = m.head_tc_part; ep.hp1 = c.target_lambda; ep.hp2 = c.rnn_lambda; ep.hO = m.O;
+    ep.htarget = c.target_idx; ep.htrain = train ? 1 : 0;
+    GArgs g = {};
+    g.n_seg = 1;
+    g.seg[0] = GSeg{0, 0, m.H / 64, 0, 0};
+    int rc;
+    if ((rc = launch_tile_gemm<16, EPI_HEAD, 1>(dim3(ntile, 1), s, false, g, ep, m.tm_head_in, m.tm_head_in, m.tm_head_in,
+                                                m.tm_head_in, m.tm_wot, m.tm_wot)))
+      return rc;
+    if (train) {
+      EpiParams es = {};
+      es.out = m.dy;
+      es.ldc = m.H;
+      es.Bp = m.Bp;
+      GArgs gd = {};
+      gd.n_seg = 1;
+      gd.seg[0] = GSeg{0, 0, 1, 0, 0};
+      const int row_tiles = m.T * m.Bp / 128;
+      if (m.H % 128 == 0)
+        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles, m.H / 128), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
+                                                 m.tm_dpb, m.tm_wos, m.tm_wos);
+      else
+        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles, m.H / 64), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
+                                                m.tm_dpb, m.tm_wos, m.tm_wos);
+      if (rc) return rc;
+      int S = 0, Mpad = 0;
+      if ((rc = gen_wgrad_gemm(m, m.tm_head_in_mn, m.tm_dpb_mn, m.H, 256, &S, &Mpad, s))) return rc;
+      ghead_wo_reduce_kernel<<<(m.H * m.O + 255) / 256, 256, 0, s>>>(S, m.H, m.O, Mpad, m.wg_part, grads + m.oWo);
+      LFMQ_LAUNCH_CHECK();
+    }
+    if (y) {
+      const int n_out = m.H * GH_O + GH_PART;
+      ghead_reduce_kernel<<<(n_out * 32 + 255) / 256, 256, 0, s>>>(ntile, m.head_tc_part, 0, nullptr, m.H, m.O, denom,
+                                                                 c.target_lambda, c.rnn_lambda, train ? 1 : 0, nullptr,
+                                                                 grads ? grads + m.obo : nullptr, out2);
+      LFMQ_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   int grid = m.T * h.NRT;
   if (grid > m.head_ctas) grid = m.head_ctas;
   const int hsmem = (m.H / 64) * 16384 + m.H * GH_O * 4 + 64 + 1024;
@@ -1482,46 +1780,13 @@ int gen_forward(GenState& st, const lfmq_config& c, const float* params, const f
     return LFMQ_ERR_UNSUPPORTED;
   }
   int rc;
-  if ((rc = gen_pack(st, params, s))) return rc;
+  if ((rc = gen_pack(st, params, c.bn_epsilon, s))) return rc;
   st.prof->begin(LFMQ_REGION_FWD, s);
   if ((rc = gen_run_trunk(st, c, params, x, B, row0, step, false, s))) return rc;
   st.prof->end(LFMQ_REGION_FWD, s);
   st.prof->begin(LFMQ_REGION_HEAD, s);
   if ((rc = gen_run_head(st, c, params, nullptr, nullptr, B, nullptr, preds, nullptr, false, s))) return rc;
   st.prof->end(LFMQ_REGION_HEAD, s);
-  return 0;
-}
-
-static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst, cudaStream_t s) {
-  const int Ntot = 4 * m.H;
-  const bool dual = Mvalid > 128;                    // 256 x 256 CTA tiles when there are at least two 128-row M tiles
-  const int mrows = dual ? 256 : 128;
-  const int mt = (Mvalid + mrows - 1) / mrows;
-  const int Mpad = mt * mrows;
-  const long rows = (long)m.T * m.Bp;
-  GWgradParams wp;
-  wp.n_kblocks = (int)cdivl(rows, 64);
-  int S = 148 / (mt * (Ntot / 256));
-  if (S < 1) S = 1;
-  if (S > 8) S = 8;
-  if (S > wp.n_kblocks) S = wp.n_kblocks;
-  wp.kb_per_split = (wp.n_kblocks + S - 1) / S;
-  S = (wp.n_kblocks + wp.kb_per_split - 1) / wp.kb_per_split;
-  wp.Mpad = Mpad;
-  wp.Ntot = Ntot;
-  wp.partial = m.wg_part;
-  if ((size_t)S * Mpad * Ntot > m.wg_part_elems) {
-    LFMQ_SET_ERR("weight-gradient partial buffer too small");
-    return LFMQ_ERR_WORKSPACE;
-  }
-  if (dual)
-    gwgrad_kernel<2><<<dim3(mt, Ntot / 256, S), GWCfg<2>::THREADS, GWCfg<2>::SMEM, s>>>(wp, tm_a, m.tm_dz_mn);
-  else
-    gwgrad_kernel<1><<<dim3(mt, Ntot / 256, S), GWCfg<1>::THREADS, GWCfg<1>::SMEM, s>>>(wp, tm_a, m.tm_dz_mn);
-  LFMQ_LAUNCH_CHECK();
-  const long n4 = (long)Mvalid * Ntot / 4;
-  gwgrad_reduce_kernel<<<(int)cdivl(n4, 256), 256, 0, s>>>(S, Mvalid, Mpad, Ntot, m.wg_part, dst);
-  LFMQ_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1537,7 +1802,7 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
   const bool rec = c.train && c.recurrent_dropout > 0.f;
   const bool drop = c.train && c.dropout > 0.f;
   int rc;
-  if ((rc = gen_pack(st, params, s))) return rc;
+  if ((rc = gen_pack(st, params, c.bn_epsilon, s))) return rc;
   st.prof->begin(LFMQ_REGION_FWD, s);
   if ((rc = gen_run_trunk(st, c, params, x, B, row0, step, true, s))) return rc;
   st.prof->end(LFMQ_REGION_FWD, s);
@@ -1557,10 +1822,8 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
     {   // Dropout / BN backward of this layer's output: dy -> dhout, dgamma, dbeta
       const int ctas = (int)cdivl((long)T * B, GBN_ROWS);
       const int RL = 256 / (H / 8) > 0 ? 256 / (H / 8) : 1;
-      gbn_drop_bwd_kernel<<<ctas, 256, RL * 2 * H * 4, s>>>(B, T, H, Bp, m.dy, ly.hseq, params + ly.off.ogamma,
-                                                           params + ly.off.omean, params + ly.off.ovar, c.bn_epsilon,
-                                                           drop ? 1 : 0, gkey(c, 2 * l, step, c.dropout), row0, m.dhout,
-                                                           m.bn_part);
+      gbn_drop_bwd_kernel<<<ctas, 256, RL * 2 * H * 4, s>>>(B, T, H, Bp, m.dy, ly.hseq, ly.bn, drop ? 1 : 0,
+                                                           gkey(c, 2 * l, step, c.dropout), row0, m.dhout, m.bn_part);
       LFMQ_LAUNCH_CHECK();
       gpartial_reduce_kernel<<<(2 * H * 32 + 255) / 256, 256, 0, s>>>(ctas, H, H, m.bn_part, grads + ly.off.ogamma,
                                                                     grads + ly.off.obeta);
@@ -1595,7 +1858,7 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
     {   // db = column sums of dz over the T*Bp rows (rows beyond the batch are zero)
       const long rows = (long)T * Bp;
       const long rpc = cdivl(rows, m.cs_chunks);
-      gcolsum_kernel<<<dim3((4 * H / 2 + 127) / 128, m.cs_chunks), 128, 0, s>>>(rows, 4 * H, rpc, m.dz, m.cs_part);
+      gcolsum_kernel<<<dim3((4 * H / 8 + 127) / 128, m.cs_chunks), 128, 0, s>>>(rows, 4 * H, rpc, m.dz, m.cs_part);
       LFMQ_LAUNCH_CHECK();
       gpartial_reduce_kernel<<<(4 * H * 32 + 255) / 256, 256, 0, s>>>(m.cs_chunks, 4 * H, 0, m.cs_part,
                                                                     grads + ly.off.ob, nullptr);
