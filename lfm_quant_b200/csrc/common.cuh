@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace lfmq {
 
@@ -20,12 +21,73 @@ extern long long g_launches;
     }                                                                                      \
   } while (0)
 
+// Programmatic dependent launch.  Device side: every kernel launched through launch_pdl() calls pdl_sync() before it
+// touches anything its predecessors wrote -- wait for the previous kernel of the stream, THEN let the next one's CTAs be
+// dispatched (in that order: when a kernel starts, its predecessor has seen ITS predecessor complete, so only the
+// immediate predecessor can still be running).  A kernel launched without the attribute sees both as no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_release();
+}
+
 // Every kernel launch goes through this so bench.py can report gpu_launches.
+// LFMQ_DEBUG_SYNC=1: synchronise after every launch and say where (finds the kernel that hangs or faults).
+inline bool debug_sync_on() {
+  static const bool on = getenv("LFMQ_DEBUG_SYNC") && atoi(getenv("LFMQ_DEBUG_SYNC")) != 0;
+  return on;
+}
+#define LFMQ_DEBUG_SYNC()                                                                              \
+  do {                                                                                                 \
+    if (::lfmq::debug_sync_on()) {                                                                     \
+      fprintf(stderr, "[lfmq launch] %s:%d ...", __FILE__, __LINE__);                                  \
+      fflush(stderr);                                                                                  \
+      cudaError_t _e = cudaDeviceSynchronize();                                                        \
+      fprintf(stderr, " %s\n", cudaGetErrorString(_e));                                               \
+      fflush(stderr);                                                                                  \
+    }                                                                                                  \
+  } while (0)
+
 #define LFMQ_LAUNCH_CHECK()                                   \
   do {                                                        \
     ::lfmq::g_launches++;                                     \
     LFMQ_CUDA_CHECK(cudaGetLastError());                      \
+    LFMQ_DEBUG_SYNC();                                        \
   } while (0)
+
+// Host side: launch with the programmatic-stream-serialization attribute (LFMQ_PDL=0 turns it off).  `attrs_extra` lets
+// the cluster kernels add their cluster dimension.
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                      Args&&... args) {
+  static const bool on = !(getenv("LFMQ_PDL") && atoi(getenv("LFMQ_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (on) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches++;
+  LFMQ_DEBUG_SYNC();
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011) -- bit-identical to oracle/lfm_oracle.py:philox4x32_10.

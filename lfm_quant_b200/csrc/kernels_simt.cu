@@ -674,6 +674,7 @@ int uq_loss_grad(cudaStream_t s, int B, int T, int O, const float* pred, const f
 __global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, int B, const float* __restrict__ y,
                                                         unsigned int* __restrict__ tickets,
                                                         float* __restrict__ out2) {
+  pdl_sync();
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
   bool any = false;
   if (r < rows) {
@@ -704,8 +705,7 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(long rows, int O, int B,
 
 int mask_count(cudaStream_t s, int B, int T, int O, const float* y, float* out2, unsigned int* tickets) {
   const long rows = (long)B * T;
-  mask_rows_kernel<<<cdiv(rows, 256), 256, 0, s>>>(rows, O, B, y, tickets, out2);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(mask_rows_kernel, dim3(cdiv(rows, 256)), dim3(256), 0, s, 1, rows, O, B, y, tickets, out2)) return rc;
   return 0;
 }
 
@@ -729,6 +729,7 @@ __global__ void __launch_bounds__(256) sumsq_norm_kernel(long n, const float* __
                                                          double* __restrict__ partial, float clip,
                                                          float* __restrict__ scalars,
                                                          unsigned int* __restrict__ ticket) {
+  pdl_sync();
   double acc[4] = {0, 0, 0, 0};
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const double v = g[i];
@@ -758,14 +759,14 @@ int grad_norm_scale(cudaStream_t s, long n, const float* g, float clip, float* s
                     unsigned int* ticket) {
   double* partial = reinterpret_cast<double*>(scratch);
   const int nblk = (int)min((long)148, max((long)1, n / 2048));
-  sumsq_norm_kernel<<<nblk, 256, 0, s>>>(n, g, partial, clip, scalars, ticket);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(sumsq_norm_kernel, dim3(nblk), dim3(256), 0, s, 1, n, g, partial, clip, scalars, ticket)) return rc;
   return 0;
 }
 
 __global__ void opt_update_kernel(int opt, long n, float* __restrict__ p, const float* __restrict__ g,
                                   float* __restrict__ s0, float* __restrict__ s1,
                                   const float* __restrict__ scalars, float lr, float momentum) {
+  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gr = g[i] * scalars[1];
@@ -803,14 +804,14 @@ __global__ void opt_update_kernel(int opt, long n, float* __restrict__ p, const 
 
 int opt_update(cudaStream_t s, int opt, long n, float* p, const float* g, float* slot0, float* slot1,
                const float* scalars, float lr, float, float, float momentum) {
-  opt_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(opt, n, p, g, slot0, slot1, scalars, lr, momentum);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(opt_update_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, 1, opt, n, p, g, slot0, slot1, scalars, lr, momentum)) return rc;
   return 0;
 }
 
 // keras.constraints.MaxNorm(max_value, axis=0) on W[I,N]: one warp per column (lanes stride the rows; a thread per
 // column left 2048 threads walking 512 dependent rows each: 115 us at H=512, profiles/r02_summary.md).
 __global__ void maxnorm_cols_kernel(int I, int N, float* __restrict__ W, float max_norm) {
+  pdl_sync();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -826,8 +827,7 @@ __global__ void maxnorm_cols_kernel(int I, int N, float* __restrict__ W, float m
 }
 
 int maxnorm_cols(cudaStream_t s, int I, int N, float* W, float max_norm) {
-  maxnorm_cols_kernel<<<cdiv((long)N * 32, 256), 256, 0, s>>>(I, N, W, max_norm);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(maxnorm_cols_kernel, dim3(cdiv((long)N * 32, 256)), dim3(256), 0, s, 1, I, N, W, max_norm)) return rc;
   return 0;
 }
 

@@ -146,6 +146,7 @@ struct TcImpl {
 // =============================================================================================
 // x f32 [B,T,F] -> xh[b][t][256 .. 256+F), plus the constant-one column.  One 16-byte chunk per thread.
 __global__ void xh_fill_x_kernel(int B, int T, int F, const float* __restrict__ x, __nv_bfloat16* __restrict__ xh) {
+  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, chunk) with 5 chunks of 8 columns per row
   if (idx >= (long)B * T * 5) return;
   const long row = idx / 5;
@@ -267,6 +268,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
   tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const int T = p.T;
+  // Programmatic dependent launch: everything above and the weight slice (packed two kernels ago) do not depend on the
+  // preceding kernel (xh_fill_x); the 144 KB weight load overlaps its tail.
+  if (!(warp == 0 && lane == 0)) pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
       mbar_arrive_expect_tx(&bars->w_full, 131072 + 16384);
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SM_U + kb * 32768, &tm_u, &bars->w_full, kb * 64, rank * TC_NSL);
       tma_load_2d(smem + SM_W, &tm_w, &bars->w_full, 0, rank * TC_NSL);
+      pdl_sync();
       uint8_t* hbuf = smem + SM_H0;
       uint8_t* xbuf = smem + SM_X0;
       uint32_t n_hw = 0, n_xe = 0;
@@ -804,6 +809,7 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) pack_all_kernel(PackArgs a) {
+  pdl_sync();
   const int bid = blockIdx.x;
   if (bid < a.nb_w) {
     pack_weights_body(bid, a.I, a.W, a.U, a.bias, a.Up, a.Wp, a.biasp);
@@ -832,6 +838,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2)
     head_tc_kernel(HeadParams p, HeadTcWeights w, const __grid_constant__ CUtensorMap tm_h,
                    const __grid_constant__ CUtensorMap tm_wot, const __grid_constant__ CUtensorMap tm_dpb, int n_btiles, int n_tiles_cap,
                    float* __restrict__ wpartial) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   HtBars* bars = reinterpret_cast<HtBars*>(smem + HT_BARS);
@@ -1150,6 +1157,7 @@ __global__ void head_reduce_kernel(int n_cta, const float* __restrict__ partial,
                                    const float* __restrict__ wpartial, int O, int B, const float* denom, float p1,
                                    float p2, int train, float* __restrict__ gWo, float* __restrict__ gbo,
                                    float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ out2) {
+  pdl_sync();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per output value
   const int lane = threadIdx.x & 31;
   if (i < HWG_PART) {
@@ -1200,6 +1208,7 @@ __global__ void head_fold_kernel(int O, float* __restrict__ gWo, const float* __
                                  float* __restrict__ ggamma, float* __restrict__ gbeta, const float* __restrict__ Wo,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps) {
+  pdl_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= TC_H) return;
   const float iv = 1.0f / sqrtf(var[j] + eps);
@@ -1362,8 +1371,7 @@ static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
   a.Wo = params + m.oWo; a.bo = params + m.obo; a.gamma = params + m.ogamma; a.beta = params + m.obeta;
   a.mean = params + m.omean; a.var = params + m.ovar;
   a.Up = m.Up; a.Wp = m.Wp; a.Ubk = m.Ubk; a.WoTp = m.WoTp; a.WoSp = m.WoSp; a.biasp = m.biasp; a.bop = m.bop;
-  pack_all_kernel<<<a.nb_w + a.nb_h + a.nb_u, 256, 0, s>>>(a);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(pack_all_kernel, dim3(a.nb_w + a.nb_h + a.nb_u), dim3(256), 0, s, 1, a)) return rc;
   st.weights_dirty = 0;
   return 0;
 }
@@ -1371,8 +1379,7 @@ static int tc_pack_weights(TcState& st, const float* params, cudaStream_t s) {
 static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cudaStream_t s) {
   TcImpl& m = *st.impl;
   const long bt = (long)B * m.T * 5;
-  xh_fill_x_kernel<<<(int)((bt + 255) / 256), 256, 0, s>>>(B, m.T, m.I, x, m.xh);
-  LFMQ_LAUNCH_CHECK();
+  if (int rc = launch_pdl(xh_fill_x_kernel, dim3((int)((bt + 255) / 256)), dim3(256), 0, s, 1, B, m.T, m.I, x, m.xh)) return rc;
   const int n_tiles = (B + 127) / 128;
   FwdParams p;
   p.B = B; p.T = m.T;
@@ -1391,23 +1398,15 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   }
   if (want_trace) LFMQ_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, 3 * 16 * 8 * sizeof(long long), s));
   p.trace = want_trace ? trace_dev : nullptr;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(TC_NC * p.n_clusters);
-  cfg.blockDim = dim3(FWD_THREADS);
-  cfg.dynamicSmemBytes = FWD_SMEM;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = TC_NC;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (save)
-    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel<true>, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
-  else
-    LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel<false>, p, m.tm_h, m.tm_x, m.tm_u, m.tm_w));
-  g_launches++;
+  if (save) {
+    if (int rc = launch_pdl(lstm_fwd_tc_kernel<true>, dim3(TC_NC * p.n_clusters), dim3(FWD_THREADS), FWD_SMEM, s, TC_NC, p,
+                            m.tm_h, m.tm_x, m.tm_u, m.tm_w))
+      return rc;
+  } else {
+    if (int rc = launch_pdl(lstm_fwd_tc_kernel<false>, dim3(TC_NC * p.n_clusters), dim3(FWD_THREADS), FWD_SMEM, s, TC_NC, p,
+                            m.tm_h, m.tm_x, m.tm_u, m.tm_w))
+      return rc;
+  }
   if (want_trace) {
     long long h[3 * 16 * 8];
     LFMQ_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1470,9 +1469,9 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
   int n_wcta = m.head_wctas;
   if (train) {
     if (use_tc) {
-      head_tc_kernel<true><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_dpb, n_btiles,
-                                                             n_tiles_cap, m.head_wpart);
-      LFMQ_LAUNCH_CHECK();
+      if (int rc = launch_pdl(head_tc_kernel<true>, dim3(grid), dim3(HT_THREADS), HT_SMEM, s, 1, h, hw, m.tm_h128, m.tm_wot,
+                              m.tm_dpb, n_btiles, n_tiles_cap, m.head_wpart))
+        return rc;
       n_wcta = grid;
       if (want_htrace) {
         long long hh[2 * 8 * 8];
@@ -1494,26 +1493,28 @@ static int tc_run_head(TcState& st, const lfmq_config& c, const float* params, f
       LFMQ_LAUNCH_CHECK();
     }
   } else {
-    if (use_tc)
-      head_tc_kernel<false><<<grid, HT_THREADS, HT_SMEM, s>>>(h, hw, m.tm_h128, m.tm_wot, m.tm_wot, n_btiles,
-                                                              n_tiles_cap, nullptr);
-    else
+    if (use_tc) {
+      if (int rc = launch_pdl(head_tc_kernel<false>, dim3(grid), dim3(HT_THREADS), HT_SMEM, s, 1, h, hw, m.tm_h128,
+                              m.tm_wot, m.tm_wot, n_btiles, n_tiles_cap, (float*)nullptr))
+        return rc;
+    } else {
       head_rows_kernel<false><<<grid, 128, HROWS_SMEM, s>>>(h, m.tm_h128, n_btiles, n_tiles_cap);
-    LFMQ_LAUNCH_CHECK();
+      LFMQ_LAUNCH_CHECK();
+    }
   }
   if (y) {
     const int n_out = HWG_PART + HEAD_PART;
-    head_reduce_kernel<<<(n_out * 32 + 255) / 256, 256, 0, s>>>(
-        grid, m.head_part, n_wcta, m.head_wpart, m.O, B, denom, c.target_lambda, c.rnn_lambda, train ? 1 : 0,
-        grads ? grads + m.oWo : nullptr, grads ? grads + m.obo : nullptr, grads ? grads + m.ogamma : nullptr,
-        grads ? grads + m.obeta : nullptr, out2);
-    LFMQ_LAUNCH_CHECK();
+    if (int rc = launch_pdl(head_reduce_kernel, dim3((n_out * 32 + 255) / 256), dim3(256), 0, s, 1, grid,
+                            (const float*)m.head_part, n_wcta, (const float*)m.head_wpart, m.O, B, denom, c.target_lambda,
+                            c.rnn_lambda, train ? 1 : 0, grads ? grads + m.oWo : (float*)nullptr,
+                            grads ? grads + m.obo : (float*)nullptr, grads ? grads + m.ogamma : (float*)nullptr,
+                            grads ? grads + m.obeta : (float*)nullptr, out2))
+      return rc;
     if (train && use_tc) {
-      head_fold_kernel<<<(TC_H + 127) / 128, 128, 0, s>>>(m.O, grads + m.oWo, grads + m.obo, grads + m.ogamma,
-                                                        grads + m.obeta, params + m.oWo, params + m.ogamma,
-                                                        params + m.obeta, params + m.omean, params + m.ovar,
-                                                        c.bn_epsilon);
-      LFMQ_LAUNCH_CHECK();
+      if (int rc = launch_pdl(head_fold_kernel, dim3((TC_H + 127) / 128), dim3(128), 0, s, 1, m.O, grads + m.oWo,
+                              (const float*)(grads + m.obo), grads + m.ogamma, grads + m.obeta, params + m.oWo,
+                              params + m.ogamma, params + m.obeta, params + m.omean, params + m.ovar, c.bn_epsilon))
+        return rc;
     }
   }
   return 0;
@@ -1643,6 +1644,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  // programmatic dependent launch: the weight slices (packed at the start of the step) load under the predecessor's tail
+  if (!(warp == 0 && lane == 0)) pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
@@ -1651,6 +1654,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       mbar_arrive_expect_tx(&bars->w_full, 131072 + (FUSED ? 4096 : 0));
       for (int jb = 0; jb < 4; ++jb) tma_load_2d(smem + SB_U + jb * 32768, &tm_ubk, &bars->w_full, jb * 64, rank * 256);
       if (FUSED) tma_load_2d(smem + SB_WOS, &tm_wos, &bars->w_full, 0, rank * 64);
+      pdl_sync();
     }
     uint32_t n_er = 0, n_dp = 0;
     // dpred tile of time step td into the single staging buffer, once the MMA that read the previous one is done
@@ -1960,6 +1964,7 @@ constexpr uint32_t WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
     wgrad_tc_kernel(WgradParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -2047,6 +2052,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 // dz's order [16-unit block][gate][16]; the gradients want gate-major columns g*H + unit.
 __global__ void wgrad_reduce_kernel(int S, int I, const float* __restrict__ partial, float* __restrict__ gU,
                                     float* __restrict__ gW, float* __restrict__ gb) {
+  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)384 * 1024) return;
   const int row = (int)(idx / 1024), np = (int)(idx % 1024);
@@ -2162,18 +2168,6 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
       bp.base = m.epoch;
       m.epoch += (unsigned long long)T * bp.n_iters;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(BWD_NC * bp.n_clusters);
-    cfg.blockDim = dim3(BWD_THREADS);
-    cfg.dynamicSmemBytes = BWD_SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = BWD_NC;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     // dz as [b][t][1024] with columns ordered [16-unit block][gate][16]: one staged chunk = 128 rows x 64 columns
     CUtensorMap tm_dzst;
     {
@@ -2190,11 +2184,15 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
       g_launches++;
       LFMQ_CUDA_CHECK(cudaEventRecord(m.ev_join, m.side));
     }
-    if (fused)
-      LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel<true>, bp, m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos));
-    else
-      LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel<false>, bp, m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos));
-    g_launches++;
+    if (fused) {
+      if ((rc = launch_pdl(lstm_bwd_tc_kernel<true>, dim3(BWD_NC * bp.n_clusters), dim3(BWD_THREADS), BWD_SMEM, s, BWD_NC, bp,
+                           m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos)))
+        return rc;
+    } else {
+      if ((rc = launch_pdl(lstm_bwd_tc_kernel<false>, dim3(BWD_NC * bp.n_clusters), dim3(BWD_THREADS), BWD_SMEM, s, BWD_NC, bp,
+                           m.tm_ubk, m.tm_px, tm_dzst, m.tm_dpb, m.tm_wos)))
+        return rc;
+    }
     if (pf_lead > 0) LFMQ_CUDA_CHECK(cudaStreamWaitEvent(s, m.ev_join, 0));
     if (want_btrace) {
       long long h[3 * 16 * 8];
@@ -2230,11 +2228,10 @@ int tc_backward_impl(TcState& st, const lfmq_config& c, const float* params, flo
   wp.kb_per_split = (wp.n_kblocks + S - 1) / S;
   S = (wp.n_kblocks + wp.kb_per_split - 1) / wp.kb_per_split;
   wp.partial = m.wg_part;
-  wgrad_tc_kernel<<<dim3(3, 4, S), WG_THREADS, WG_SMEM, s>>>(wp, tm_a, tm_b);
-  LFMQ_LAUNCH_CHECK();
-  wgrad_reduce_kernel<<<(384 * 1024 + 255) / 256, 256, 0, s>>>(S, m.I, m.wg_part, grads + m.oU, grads + m.oW,
-                                                              grads + m.ob);
-  LFMQ_LAUNCH_CHECK();
+  if ((rc = launch_pdl(wgrad_tc_kernel, dim3(3, 4, S), dim3(WG_THREADS), WG_SMEM, s, 1, wp, tm_a, tm_b))) return rc;
+  if ((rc = launch_pdl(wgrad_reduce_kernel, dim3((384 * 1024 + 255) / 256), dim3(256), 0, s, 1, S, m.I,
+                       (const float*)m.wg_part, grads + m.oU, grads + m.oW, grads + m.ob)))
+    return rc;
   st.prof->end(LFMQ_REGION_WGRAD, s);
   (void)params;
   (void)c;

@@ -364,6 +364,31 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
   st_global_v8(dzr + 3L * p.H, zo);
 }
 
+// The saved gates / cell states / dLoss/dh of a step come from HBM and every CTA wants them at the same moment (all
+// tiles leave the mainloop together), while HBM idles during the mainloop: the epilogue warps, idle until the
+// accumulator is complete, pull their operands into L2 first (1 KB per (block, piece) in the blocked layout).
+template <int BN>
+__device__ __forceinline__ void bwd_prefetch(const EpiParams& p, int q, int lane, int rt, int part, int nparts) {
+  const long b = (long)rt * 128 + q * 32 + lane;
+  if (b >= p.B) return;
+  const int unit0 = blockIdx.y * BN;
+  constexpr int NB = BN / 16;
+  const long gstride = 4L * 32 * 16;
+  const long tstride_c = (long)p.NRT * p.NB16 * 4 * 32 * 16;
+  for (int blk = part; blk < NB; blk += nparts) {
+    const int gblk = (unit0 >> 4) + blk;
+    const long sb = (((long)p.t * p.NRT + rt) * p.NB16 + gblk);
+    if (lane < 4) {
+      prefetch_l2_bulk(p.gates + (((sb * 4 + 0) * 4 + q) * 32) * 16 + lane * gstride, 1024);
+    } else if (lane == 4) {
+      prefetch_l2_bulk(p.cst + ((sb * 4 + q) * 32) * 16, 1024);
+    } else if (lane == 5 && p.t > 0) {
+      prefetch_l2_bulk(p.cst + ((sb * 4 + q) * 32) * 16 - tstride_c, 1024);
+    }
+  }
+  if (part == 0) prefetch_l2_bulk(p.dhout + ((long)p.t * p.Bp + b) * p.H + unit0, BN * 2);
+}
+
 // `part` of `nparts` warps of this lane quadrant: blocks part, part + nparts, ...
 template <int BN>
 __device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q, int lane, int rt, int part, int nparts) {
@@ -613,6 +638,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     const int mt = grp / S::EW;                      // which 128-row M tile of the CTA this group works on
     const int part = grp % S::EW;                    // ... and which share of its column blocks
     const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
+    if constexpr (EPI == EPI_BWD) {
+      if ((long)rt * 128 < ep.Bp) bwd_prefetch<BN>(ep, q, lane, rt, part, S::EW);
+    }
     if (total_kb > 0) {
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();
@@ -1533,6 +1561,13 @@ static int launch_tile_gemm(dim3 grid, cudaStream_t s, bool pdl, const GArgs& g,
   cfg.numAttrs = (pdl && pdl_on) ? 1 : 0;
   LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<BN, EPI, MT>, g, ep, a0, a1, a2, a3, b0, b1));
   g_launches++;
+  if (debug_sync_on()) {
+    fprintf(stderr, "[lfmq launch] tile_gemm<%d,%d,%d> grid %u x %u t=%d ...", BN, EPI, MT, grid.x, grid.y, ep.t);
+    fflush(stderr);
+    cudaError_t e = cudaDeviceSynchronize();
+    fprintf(stderr, " %s\n", cudaGetErrorString(e));
+    fflush(stderr);
+  }
   return 0;
 }
 
