@@ -278,7 +278,13 @@ struct BwdOps {
   uint32_t wi[8], wf[8], wg[8], wo[8], wc[8], wcp[8], wd[8];
 };
 
-__device__ __forceinline__ void bwd_load_ops(const EpiParams& p, int rt, int q, int lane, long b, int j0, BwdOps& o) {
+__device__ __forceinline__ void bwd_load_ops(const EpiParams& p, int rt, int q, int lane, long b, bool valid, int j0,
+                                             BwdOps& o) {
+  if (!valid) {        // rows beyond the batch take part in the warp-collective TMEM loads but touch no memory
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.wi[e] = o.wf[e] = o.wg[e] = o.wo[e] = o.wc[e] = o.wcp[e] = o.wd[e] = 0u;
+    return;
+  }
   const int gblk = j0 >> 4;
   const long gstride = 4L * 32 * 16;
   const long tstride_c = (long)p.NRT * p.NB16 * 4 * 32 * 16;     // cst elements per time step
@@ -299,8 +305,8 @@ __device__ __forceinline__ void bwd_load_ops(const EpiParams& p, int rt, int q, 
   ld_global_v8(p.dhout + ((long)p.t * p.Bp + b) * p.H + j0, o.wd);
 }
 
-__device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk, int rt, int q, int lane, long b, int j0,
-                                          const BwdOps& o) {
+__device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk, int rt, int q, int lane, long b, bool valid,
+                                          int j0, const BwdOps& o) {
   const int gblk = j0 >> 4;
   float rec[16];
   if (p.has_rec) {
@@ -322,7 +328,7 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
   float* dcs = p.dcstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
   __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + j0;
   float dcc[16];
-  if (p.t < p.T - 1) {
+  if (p.t < p.T - 1 && valid) {
     ld_global_v8f(dcs, dcc);
     ld_global_v8f(dcs + 8, dcc + 8);
   } else {
@@ -356,8 +362,13 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
     zg[e] = pack_bf16x2(r2[2][0], r2[2][1]);
     zo[e] = pack_bf16x2(r2[3][0], r2[3][1]);
   }
-  st_global_v8f(dcs, dcc);
-  st_global_v8f(dcs + 8, dcc + 8);
+  if (valid) {
+    st_global_v8f(dcs, dcc);
+    st_global_v8f(dcs + 8, dcc + 8);
+  } else {             // rows beyond the batch: dz exactly zero (the weight-gradient GEMM sums over all rows)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) zi[e] = zf[e] = zg[e] = zo[e] = 0u;
+  }
   st_global_v8(dzr, zi);
   st_global_v8(dzr + (long)p.H, zf);
   st_global_v8(dzr + 2L * p.H, zg);
@@ -398,29 +409,21 @@ __device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const int unit0 = blockIdx.y * BN;
   constexpr int NB = BN / 16;
-  if (!valid) {        // rows beyond the batch: dz must be exactly zero (the weight-gradient GEMM sums over all rows)
-    uint32_t w[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) w[e] = 0u;
-    for (int blk = part; blk < NB; blk += nparts) {
-      __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + unit0 + blk * 16;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) st_global_v8(dzr + (long)g * p.H, w);
-    }
-    return;
-  }
+  // tcgen05.ld is warp-collective (.sync.aligned): every lane of the warp runs the block loop, also those whose row lies
+  // beyond the batch (a ragged last tile) -- they load nothing and store zeros.  (An early return of those lanes hung
+  // the kernel, profiles/r02_summary.md.)
   BwdOps A, B2;
   int blk = part;
-  if (blk < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + blk * 16, A);
+  if (blk < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + blk * 16, A);
 #pragma unroll 1
   for (; blk < NB; blk += 2 * nparts) {
     const int nxt = blk + nparts;
-    if (nxt < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + nxt * 16, B2);
-    bwd_block(p, tmem + lane_addr + blk * 16, rt, q, lane, b, unit0 + blk * 16, A);
+    if (nxt < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + nxt * 16, B2);
+    bwd_block(p, tmem + lane_addr + blk * 16, rt, q, lane, b, valid, unit0 + blk * 16, A);
     if (nxt < NB) {
       const int nx2 = nxt + nparts;
-      if (nx2 < NB) bwd_load_ops(p, rt, q, lane, b, unit0 + nx2 * 16, A);
-      bwd_block(p, tmem + lane_addr + nxt * 16, rt, q, lane, b, unit0 + nxt * 16, B2);
+      if (nx2 < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + nx2 * 16, A);
+      bwd_block(p, tmem + lane_addr + nxt * 16, rt, q, lane, b, valid, unit0 + nxt * 16, B2);
     }
   }
 }
@@ -1688,9 +1691,13 @@ static int gen_wgrad_gemm(GenImpl& m, const CUtensorMap& tm_a, const CUtensorMap
   const long rows = (long)m.T * m.Bp;
   GWgradParams wp;
   wp.n_kblocks = (int)cdivl(rows, 64);
+  // K splits: fill the machine, within what the partial buffer holds (the head's [H x 16] product has one N tile and
+  // wants many splits; the gate products have 8-16 output tiles and get 8)
   int S = 148 / (mt * (Ntot / 256));
+  const size_t smax = m.wg_part_elems / ((size_t)Mpad * Ntot);
+  if ((size_t)S > smax) S = (int)smax;
+  if (S > 64) S = 64;
   if (S < 1) S = 1;
-  if (S > 8) S = 8;
   if (S > wp.n_kblocks) S = wp.n_kblocks;
   wp.kb_per_split = (wp.n_kblocks + S - 1) / S;
   S = (wp.n_kblocks + wp.kb_per_split - 1) / wp.kb_per_split;
