@@ -335,32 +335,29 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
 #pragma unroll
     for (int j = 0; j < 16; ++j) dcc[j] = 0.f;
   }
+  // Gate-gradient algebra in packed bf16x2 (all operands arrive packed, dz leaves packed; a third of the instructions of
+  // the fp32 form, which made this epilogue issue-bound); only the carried dLoss/dc stays in fp32.  SURVEY App. A.4.
   uint32_t zi[8], zf[8], zg[8], zo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {          // two units per packed word
-    float r2[4][2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = 2 * e + u;
-      const float gi = u ? bf16_hi(o.wi[e]) : bf16_lo(o.wi[e]);
-      const float gf = u ? bf16_hi(o.wf[e]) : bf16_lo(o.wf[e]);
-      const float gg = u ? bf16_hi(o.wg[e]) : bf16_lo(o.wg[e]);
-      const float go = u ? bf16_hi(o.wo[e]) : bf16_lo(o.wo[e]);
-      const float ct = u ? bf16_hi(o.wc[e]) : bf16_lo(o.wc[e]);
-      const float cpv = u ? bf16_hi(o.wcp[e]) : bf16_lo(o.wcp[e]);
-      const float d = (u ? bf16_hi(o.wd[e]) : bf16_lo(o.wd[e])) + rec[j];
-      const float tc = tanh_approx(ct);
-      const float dcn = dcc[j] + d * go * (1.f - tc * tc);
-      dcc[j] = dcn * gf;
-      r2[0][u] = dcn * gg * gi * (1.f - gi);
-      r2[1][u] = dcn * cpv * gf * (1.f - gf);
-      r2[2][u] = dcn * gi * (1.f - gg * gg);
-      r2[3][u] = d * tc * go * (1.f - go);
-    }
-    zi[e] = pack_bf16x2(r2[0][0], r2[0][1]);
-    zf[e] = pack_bf16x2(r2[1][0], r2[1][1]);
-    zg[e] = pack_bf16x2(r2[2][0], r2[2][1]);
-    zo[e] = pack_bf16x2(r2[3][0], r2[3][1]);
+    const uint32_t i2 = o.wi[e], f2 = o.wf[e], g2 = o.wg[e], o2 = o.wo[e];
+    const uint32_t dh2 = add_bf16x2(o.wd[e], pack_bf16x2(rec[2 * e], rec[2 * e + 1]));
+    const uint32_t tc2 = tanh_bf16x2(o.wc[e]);
+    const uint32_t omtc2 = fma_bf16x2(neg_bf16x2(tc2), tc2, BF16X2_ONE);        // 1 - tanh(c)^2
+    const uint32_t t1 = mul_bf16x2(mul_bf16x2(dh2, o2), omtc2);                 // dh * o * (1 - tc^2)
+    const float dcn0 = dcc[2 * e] + bf16_lo(t1);
+    const float dcn1 = dcc[2 * e + 1] + bf16_hi(t1);
+    dcc[2 * e] = dcn0 * bf16_lo(f2);
+    dcc[2 * e + 1] = dcn1 * bf16_hi(f2);
+    const uint32_t dcn2 = pack_bf16x2(dcn0, dcn1);
+    const uint32_t omi = fma_bf16x2(neg_bf16x2(i2), i2, i2);                    // i (1 - i)
+    const uint32_t omf = fma_bf16x2(neg_bf16x2(f2), f2, f2);                    // f (1 - f)
+    const uint32_t omg = fma_bf16x2(neg_bf16x2(g2), g2, BF16X2_ONE);            // 1 - g^2
+    const uint32_t omo = fma_bf16x2(neg_bf16x2(o2), o2, o2);                    // o (1 - o)
+    zi[e] = mul_bf16x2(dcn2, mul_bf16x2(g2, omi));
+    zf[e] = mul_bf16x2(dcn2, mul_bf16x2(o.wcp[e], omf));
+    zg[e] = mul_bf16x2(dcn2, mul_bf16x2(i2, omg));
+    zo[e] = mul_bf16x2(mul_bf16x2(dh2, tc2), omo);
   }
   if (valid) {
     st_global_v8f(dcs, dcc);
@@ -373,31 +370,6 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
   st_global_v8(dzr + (long)p.H, zf);
   st_global_v8(dzr + 2L * p.H, zg);
   st_global_v8(dzr + 3L * p.H, zo);
-}
-
-// The saved gates / cell states / dLoss/dh of a step come from HBM and every CTA wants them at the same moment (all
-// tiles leave the mainloop together), while HBM idles during the mainloop: the epilogue warps, idle until the
-// accumulator is complete, pull their operands into L2 first (1 KB per (block, piece) in the blocked layout).
-template <int BN>
-__device__ __forceinline__ void bwd_prefetch(const EpiParams& p, int q, int lane, int rt, int part, int nparts) {
-  const long b = (long)rt * 128 + q * 32 + lane;
-  if (b >= p.B) return;
-  const int unit0 = blockIdx.y * BN;
-  constexpr int NB = BN / 16;
-  const long gstride = 4L * 32 * 16;
-  const long tstride_c = (long)p.NRT * p.NB16 * 4 * 32 * 16;
-  for (int blk = part; blk < NB; blk += nparts) {
-    const int gblk = (unit0 >> 4) + blk;
-    const long sb = (((long)p.t * p.NRT + rt) * p.NB16 + gblk);
-    if (lane < 4) {
-      prefetch_l2_bulk(p.gates + (((sb * 4 + 0) * 4 + q) * 32) * 16 + lane * gstride, 1024);
-    } else if (lane == 4) {
-      prefetch_l2_bulk(p.cst + ((sb * 4 + q) * 32) * 16, 1024);
-    } else if (lane == 5 && p.t > 0) {
-      prefetch_l2_bulk(p.cst + ((sb * 4 + q) * 32) * 16 - tstride_c, 1024);
-    }
-  }
-  if (part == 0) prefetch_l2_bulk(p.dhout + ((long)p.t * p.Bp + b) * p.H + unit0, BN * 2);
 }
 
 // `part` of `nparts` warps of this lane quadrant: blocks part, part + nparts, ...
@@ -641,9 +613,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     const int mt = grp / S::EW;                      // which 128-row M tile of the CTA this group works on
     const int part = grp % S::EW;                    // ... and which share of its column blocks
     const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
-    if constexpr (EPI == EPI_BWD) {
-      if ((long)rt * 128 < ep.Bp) bwd_prefetch<BN>(ep, q, lane, rt, part, S::EW);
-    }
+    // (An L2 prefetch of the epilogue's saved-state operands issued here, during the mainloop, was measured and lost:
+    //  it delays the operand ring -- first stage 1.5 K -> 3 K cycles -- and the epilogue, which is issue-bound, not
+    //  HBM-bound, got no shorter: 2.97 -> 3.25 ms for the backward steps of BASELINE configs[2].)
     if (total_kb > 0) {
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 240 python -m pytest tests/test_gpu_generic.py tests/test_gpu_baseline_shapes.py -m gpu -q -x -k "generic or cfg3" ) > gpurun_out/r02_c10_generic.log 2>&1; echo "generic rc=$?" > gpurun_out/r02_c10_rc.txt
+LFMQ_TRACE_GEN=1 timeout 120 python tools/run_once.py --workload cfg3 --steps 2 > /dev/null 2> gpurun_out/r02_c10_gtrace.txt
+timeout 300 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c10_cfg3.json 2> gpurun_out/r02_c10_cfg3.err
+cat gpurun_out/r02_c10_rc.txt; tail -n 2 gpurun_out/r02_c10_generic.log
+python - <<'PY'
+import json
+for f in ('r02_c10_cfg3',):
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
+        print(f, round(d['ms_per_step'],4), {k: round(v,3) for k,v in d['roofline']['regions_ms_per_step'].items()})
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
+grep -E "bwd l=1 t=(16)" gpurun_out/r02_c10_gtrace.txt | head -2
