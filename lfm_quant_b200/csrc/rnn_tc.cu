@@ -87,8 +87,9 @@ struct GSeg {
 struct GArgs {
   int n_seg;
   GSeg seg[G_MAXSEG];
-  int a_row_base;      // A row coordinate = a_row_base + 128 * blockIdx.x
+  int a_row_base;      // A row coordinate = a_row_base + 128 * (MT * blockIdx.x + rt_off)
   int b_row_base;      // B row coordinate = b_row_base + BN * blockIdx.y
+  int rt_off;          // first 128-row tile of this launch (the batch can be split over two concurrent launches)
 };
 
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3, EPI_HEAD = 4 };   // _ACC: expf / tanhf (bf16x3)
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   // by induction only the immediate predecessor can still be running.
   if (warp == 0) {
     if (lane == 0) {
-      const int arow = g.a_row_base + 128 * MT * (int)blockIdx.x;
+      const int arow = g.a_row_base + 128 * (MT * (int)blockIdx.x + g.rt_off);
       const int brow = g.b_row_base + BN * (int)blockIdx.y;
       {   // B operand of the first NS stages, before the dependency wait
         int i = 0;
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     const int grp = (warp - 2) >> 2;                 // group of four warps = one pass over the four TMEM lane quadrants
     const int mt = grp / S::EW;                      // which 128-row M tile of the CTA this group works on
     const int part = grp % S::EW;                    // ... and which share of its column blocks
-    const int rt = MT * (int)blockIdx.x + mt;        // 128-row tile index
+    const int rt = MT * (int)blockIdx.x + mt + g.rt_off;        // 128-row tile index
     // (An L2 prefetch of the epilogue's saved-state operands issued here, during the mainloop, was measured and lost:
     //  it delays the operand ring -- first stage 1.5 K -> 3 K cycles -- and the epilogue, which is issue-bound, not
     //  HBM-bound, got no shorter: 2.97 -> 3.25 ms for the backward steps of BASELINE configs[2].)
@@ -1299,6 +1300,8 @@ struct GenLayer {
 
 struct GenImpl {
   bool enabled = false;
+  cudaStream_t side = nullptr;          // second half of the batch in the backward recurrence (see gen_backward)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   long long* trace = nullptr;      // LFMQ_TRACE_GEN=1: [phase 0 fwd / 1 bwd][layer][t][8] clock64 stamps of CTA (0,0)
   int maxB = 0, Bp = 0, NRT = 0, T = 0, F = 0, O = 0, H = 0, L = 0, NB16 = 0;
   bool x3 = false, train_ws = false;
@@ -1512,6 +1515,12 @@ static void gen_print_trace(GenImpl& m, cudaStream_t s) {
 }
 
 void gen_destroy(GenState& st) {
+  if (st.impl && st.impl->side) {
+    cudaStreamSynchronize(st.impl->side);
+    cudaEventDestroy(st.impl->ev_fork);
+    cudaEventDestroy(st.impl->ev_join);
+    cudaStreamDestroy(st.impl->side);
+  }
   if (st.impl && st.impl->trace) cudaFree(st.impl->trace);
   delete st.impl;
   st.impl = nullptr;
@@ -1848,22 +1857,46 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
     ep.gates = ly.gates; ep.cst = ly.cst; ep.dhout = m.dhout; ep.dcstate = m.dcstate; ep.dz = m.dz;
     ep.use_rec = rec ? 1 : 0;
     ep.rkey = gkey(c, 2 * l + 1, step, c.recurrent_dropout);
+    // The step's epilogue is HBM-bound (saved gates / cell states in, dz out: ~46 MB per step at H = 512) and its
+    // mainloop L2-bound, and one launch puts every CTA into the same phase at the same time.  Two half-batches on two
+    // streams (each its own PDL chain) drift apart, so one half's epilogue runs beside the other's mainloop.
+    static const char* split_env = getenv("LFMQ_GEN_SPLIT");      // 0 / 1 force, unset: by tile count
+    const bool split = split_env ? (atoi(split_env) != 0 && nrt >= 2) : (nrt >= 16);
+    const int n_a = split ? (nrt + 1) / 2 : nrt, n_b = nrt - n_a;
+    if (split) {
+      if (!m.side) {
+        LFMQ_CUDA_CHECK(cudaStreamCreateWithFlags(&m.side, cudaStreamNonBlocking));
+        LFMQ_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
+        LFMQ_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming));
+      }
+      LFMQ_CUDA_CHECK(cudaEventRecord(m.ev_fork, s));
+      LFMQ_CUDA_CHECK(cudaStreamWaitEvent(m.side, m.ev_fork, 0));
+    }
     for (int t = T - 1; t >= 0; --t) {
-      ep.t = t;
-      ep.trace = m.trace ? m.trace + (((size_t)1 * m.L + l) * T + t) * 8 : nullptr;
-      ep.has_rec = (t < T - 1) ? 1 : 0;
-      GArgs g = {};
-      g.a_row_base = (t + 1) * Bp;      // dz_{t+1}
-      g.b_row_base = 0;
-      g.n_seg = ep.has_rec ? 1 : 0;
-      g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
-      if (m.BNU == 128)
-        rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(nrt, H / 128), s, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz,
-                                               ly.tm_ub, ly.tm_ub);
-      else
-        rc = launch_tile_gemm<64, EPI_BWD, 1>(dim3(nrt, H / 64), s, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz, m.tm_dz,
-                                              ly.tm_ub, ly.tm_ub);
-      if (rc) return rc;
+      for (int half = 0; half < (split ? 2 : 1); ++half) {       // launches interleaved: neither chain lags the other
+        cudaStream_t hs = half ? m.side : s;
+        const int rt_off = half ? n_a : 0, n_rt = half ? n_b : n_a;
+        ep.t = t;
+        ep.trace = (m.trace && half == 0) ? m.trace + (((size_t)1 * m.L + l) * T + t) * 8 : nullptr;
+        ep.has_rec = (t < T - 1) ? 1 : 0;
+        GArgs g = {};
+        g.a_row_base = (t + 1) * Bp;      // dz_{t+1}
+        g.b_row_base = 0;
+        g.rt_off = rt_off;
+        g.n_seg = ep.has_rec ? 1 : 0;
+        g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
+        if (m.BNU == 128)
+          rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(n_rt, H / 128), hs, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz,
+                                                 m.tm_dz, ly.tm_ub, ly.tm_ub);
+        else
+          rc = launch_tile_gemm<64, EPI_BWD, 1>(dim3(n_rt, H / 64), hs, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz,
+                                                m.tm_dz, ly.tm_ub, ly.tm_ub);
+        if (rc) return rc;
+      }
+    }
+    if (split) {
+      LFMQ_CUDA_CHECK(cudaEventRecord(m.ev_join, m.side));
+      LFMQ_CUDA_CHECK(cudaStreamWaitEvent(s, m.ev_join, 0));
     }
     st.prof->end(LFMQ_REGION_BWD, s);
     st.prof->begin(LFMQ_REGION_WGRAD, s);
