@@ -309,6 +309,15 @@ __device__ __forceinline__ void bwd_load_ops(const EpiParams& p, int rt, int q, 
 __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk, int rt, int q, int lane, long b, bool valid,
                                           int j0, const BwdOps& o) {
   const int gblk = j0 >> 4;
+  float* dcs = p.dcstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
+  float dcc[16];
+  if (p.t < p.T - 1 && valid) {
+    ld_global_v8f(dcs, dcc);
+    ld_global_v8f(dcs + 8, dcc + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dcc[j] = 0.f;
+  }
   float rec[16];
   if (p.has_rec) {
     uint32_t vr[16];
@@ -326,16 +335,7 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
 #pragma unroll
     for (int j = 0; j < 16; ++j) rec[j] = 0.f;
   }
-  float* dcs = p.dcstate + ((((long)rt * p.NB16 + gblk) * 4 + q) * 32 + lane) * 16;
   __nv_bfloat16* dzr = p.dz + ((long)p.t * p.Bp + b) * 4 * p.H + j0;
-  float dcc[16];
-  if (p.t < p.T - 1 && valid) {
-    ld_global_v8f(dcs, dcc);
-    ld_global_v8f(dcs + 8, dcc + 8);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) dcc[j] = 0.f;
-  }
   // Gate-gradient algebra in packed bf16x2 (all operands arrive packed, dz leaves packed; a third of the instructions of
   // the fp32 form, which made this epilogue issue-bound); only the carried dLoss/dc stays in fp32.  SURVEY App. A.4.
   uint32_t zi[8], zf[8], zg[8], zo[8];
@@ -385,19 +385,15 @@ __device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q
   // tcgen05.ld is warp-collective (.sync.aligned): every lane of the warp runs the block loop, also those whose row lies
   // beyond the batch (a ragged last tile) -- they load nothing and store zeros.  (An early return of those lanes hung
   // the kernel, profiles/r02_summary.md.)
-  BwdOps A, B2;
-  int blk = part;
-  if (blk < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + blk * 16, A);
+  // One block at a time, all of its nine loads issued together.  (Keeping the next block's operands in flight as well
+  // needs 2 x 56 registers: at the 168-register cap of a 320-thread CTA that spilled ~100 values per block, and with
+  // 198 KB of shared memory in use the L1 that would catch the spills is ~30 KB -- the epilogue took 25 K cycles whatever
+  // the arithmetic looked like, profiles/r02_summary.md.)
+  BwdOps A;
 #pragma unroll 1
-  for (; blk < NB; blk += 2 * nparts) {
-    const int nxt = blk + nparts;
-    if (nxt < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + nxt * 16, B2);
+  for (int blk = part; blk < NB; blk += nparts) {
+    bwd_load_ops(p, rt, q, lane, b, valid, unit0 + blk * 16, A);
     bwd_block(p, tmem + lane_addr + blk * 16, rt, q, lane, b, valid, unit0 + blk * 16, A);
-    if (nxt < NB) {
-      const int nx2 = nxt + nparts;
-      if (nx2 < NB) bwd_load_ops(p, rt, q, lane, b, valid, unit0 + nx2 * 16, A);
-      bwd_block(p, tmem + lane_addr + nxt * 16, rt, q, lane, b, valid, unit0 + nxt * 16, B2);
-    }
   }
 }
 

@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 240 python -m pytest tests/test_gpu_generic.py tests/test_gpu_baseline_shapes.py -m gpu -q -x -k "generic or cfg3" ) > gpurun_out/r02_c12_generic.log 2>&1; echo "generic rc=$?" > gpurun_out/r02_c12_rc.txt
+LFMQ_TRACE_GEN=1 LFMQ_GEN_SPLIT=0 timeout 120 python tools/run_once.py --workload cfg3 --steps 2 > /dev/null 2> gpurun_out/r02_c12_gtrace.txt
+LFMQ_GEN_SPLIT=0 timeout 300 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c12_cfg3_split0.json 2> gpurun_out/r02_c12_cfg3_split0.err
+timeout 300 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c12_cfg3_split1.json 2> gpurun_out/r02_c12_cfg3_split1.err
+cat gpurun_out/r02_c12_rc.txt; tail -n 2 gpurun_out/r02_c12_generic.log
+python - <<'PY'
+import json
+for f in ('r02_c12_cfg3_split0','r02_c12_cfg3_split1'):
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
+        print(f, round(d['ms_per_step'],4), {k: round(v,3) for k,v in d['roofline']['regions_ms_per_step'].items()})
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
+grep -E "bwd l=1 t=(16|24)" gpurun_out/r02_c12_gtrace.txt | head -3
