@@ -1593,6 +1593,10 @@ struct BwdParams {
   } while (0)
 
 constexpr int BWD_NC = 4;
+#ifndef LFMQ_BWD_LATE_C1
+#define LFMQ_BWD_LATE_C1 1
+#endif
+constexpr bool LATE_C1 = LFMQ_BWD_LATE_C1 != 0;
 constexpr int BWD_THREADS = 352;   // producer + MMA + 2 sets of 4 pointwise warps + dz store warp
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
@@ -1813,7 +1817,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 32; ++j) dc[j] = 0.f;
       load_chunk(0, tile, valid, T - 1);
-      load_chunk(1, tile, valid, T - 1);
+      if (!LATE_C1) load_chunk(1, tile, valid, T - 1);
       if (FUSED) {                             // the head's dLoss/dh_{T-1} for the own slice is in the accumulator
         const uint32_t pb = (gs + 1) & 1;
         mbar_wait(&bars->acc_full[pb], caf[pb] & 1);
@@ -1822,6 +1826,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       for (int t = T - 1; t >= 0; --t, ++gs) {
         const bool has_rec = t < T - 1;
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
+        // LATE_C1: the second chunk's operands are requested only now and land under the first chunk's arithmetic, so
+        // that only one chunk's operands (48 registers, not 96) are live across the export section below
+        if (LATE_C1) load_chunk(1, tile, valid, t);
         if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
         if (tid == 64) BWD_TRACE(2, T - 1 - t, 0);
 #pragma unroll
@@ -1903,7 +1910,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         // hold up the chunk's own dz / A-operand stores (+17 %).
         if (t > 0) {
           load_chunk(0, tile, valid, t - 1);
-          load_chunk(1, tile, valid, t - 1);
+          if (!LATE_C1) load_chunk(1, tile, valid, t - 1);
         }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
@@ -1916,14 +1923,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           for (uint32_t d = 1; d < BWD_NC; ++d) {
             const uint32_t dst = (rank + d) & 3;
             __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64 + set * 32;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(acc + dst * 64 + set * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
+            // 16 columns at a time: the next step's operands (112 registers) are live across this section, and the
+            // 32-column form pushed the kernel over its 168-register cap into local-memory spills
 #pragma unroll
-            for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-            st_global_v8(out, pk);
-            st_global_v8(out + 16, pk + 8);
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(acc + dst * 64 + set * 32 + hh * 16, v);
+              tmem_ld_wait();
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+              st_global_v8(out + hh * 16, pk);
+            }
           }
           tcgen05_fence_before();
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 4);

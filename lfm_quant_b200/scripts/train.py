@@ -101,7 +101,7 @@ class Train(object):
         for epoch in range(epochs):
             self.model.reset_states()
             mse_steps, uq_loss_steps = [], []
-            if self.world == 1:
+            if self.world == 1 and not os.environ.get('LFMQ_SEEDED_SHUFFLE'):
                 random.shuffle(self._batches)                   # train.py:115 (unseeded in the reference)
             else:                                               # every rank must walk the same batch order
                 random.Random(self.config.seed + epoch).shuffle(self._batches)

@@ -25,7 +25,11 @@ def main():
     write_open_dataset(os.path.join(d, 'datasets', 'open-dataset.dat'), n_keys=30, n_months=420, seed=9)
     conf = os.path.join(d, 'config', 'system-test.conf')
     write_system_test_conf(conf, os.path.join(d, 'datasets'), os.path.join(d, 'experiments'))
-    env = dict(os.environ, LFM_QUANT_ROOT=d, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    # the reference shuffles the batch ORDER of an epoch with an unseeded random.shuffle (train.py:115); data-parallel runs
+    # must seed it (all ranks walk the same order).  LFMQ_SEEDED_SHUFFLE=1 makes the 1-GPU run walk that order too, so the
+    # two trajectories are comparable step by step.
+    env = dict(os.environ, LFM_QUANT_ROOT=d, LFMQ_SEEDED_SHUFFLE='1',
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
     common = ['-m', 'lfm_quant_b200.scripts.lfm_quant', '--config=' + conf, '--train=True', '--precision', a.precision]
     subprocess.run([sys.executable] + common + ['--model_dir', 'one'], check=True, env=env, cwd=ROOT)
     subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
@@ -39,10 +43,9 @@ def main():
     worst = max(float(np.abs(w1[k] - w2[k]).max() / max(np.abs(w1[k]).max(), 1e-30)) for k in w1.files)
     rel = float(np.max(np.abs(e1['mse'].values - e2['mse'].values) / np.abs(e1['mse'].values)))
     print('max rel diff of epoch mse %.3e, of saved weights %.3e' % (rel, worst))
-    # NOTE: within an epoch the reference shuffles the batch ORDER with an unseeded random.shuffle (train.py:115); the
-    # 1-GPU run keeps that, the DP run must seed it (all ranks walk the same order), so trajectories agree only up to the
-    # batch order of epochs >= 0 -- compare loosely, the tight check is tests/test_dp_gloo.py + the denominators test.
+    tol = 1e-3 if a.precision == 'fp32' else 3e-2
     assert np.isfinite(e2['mse']).all() and e2['mse'].iloc[-1] < e2['mse'].iloc[0]
+    assert rel < tol and worst < 10 * tol, (rel, worst)
     print('OK')
 
 
