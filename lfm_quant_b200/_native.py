@@ -7,7 +7,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lfmq.so')
+# LFMQ_LIB_PATH: an alternative build of the same ABI (A/B measurements of kernel variants, tools/)
+_LIB_PATH = os.environ.get('LFMQ_LIB_PATH') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lfmq.so')
 
 OPTIMIZERS = {'Adadelta': 0, 'Adam': 1, 'RMSprop': 2, 'SGD': 3}
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2

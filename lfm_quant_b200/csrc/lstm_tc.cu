@@ -1597,6 +1597,10 @@ constexpr int BWD_NC = 4;
 #define LFMQ_BWD_LATE_C1 1
 #endif
 constexpr bool LATE_C1 = LFMQ_BWD_LATE_C1 != 0;
+#ifndef LFMQ_BWD_LATE_C0
+#define LFMQ_BWD_LATE_C0 0
+#endif
+constexpr bool LATE_C0 = LFMQ_BWD_LATE_C0 != 0;     // experiment: the first chunk's operands at the top of the step as well
 constexpr int BWD_THREADS = 352;   // producer + MMA + 2 sets of 4 pointwise warps + dz store warp
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
@@ -1796,7 +1800,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         if (!FUSED)
           ld_global_v8(p.dhout + ((((((long)t * p.n_tiles_cap + tile) * 4 + rank) * 4 + wq) * 4 + jb) * 32 + lane) * 16,
                        dhp[ci]);
-        ld_global_v8(crow, ct[ci]);
+        // c_t was this slot's c_{t-1} one step ago (the unroll runs backwards): only the first step of a tile loads it
+        if (t == T - 1) {
+          ld_global_v8(crow, ct[ci]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ct[ci][j] = cp[ci][j];
+        }
         if (t > 0) {
           ld_global_v8(crow - tstride, cp[ci]);
         } else {
@@ -1816,7 +1826,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       const bool valid = b < p.B;
 #pragma unroll
       for (int j = 0; j < 32; ++j) dc[j] = 0.f;
-      load_chunk(0, tile, valid, T - 1);
+      if (!LATE_C0) load_chunk(0, tile, valid, T - 1);
       if (!LATE_C1) load_chunk(1, tile, valid, T - 1);
       if (FUSED) {                             // the head's dLoss/dh_{T-1} for the own slice is in the accumulator
         const uint32_t pb = (gs + 1) & 1;
@@ -1828,6 +1838,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         const uint32_t acc_prev = tmem + ((gs + 1) & 1) * 256;     // partial of step t+1 (own slice still there)
         // LATE_C1: the second chunk's operands are requested only now and land under the first chunk's arithmetic, so
         // that only one chunk's operands (48 registers, not 96) are live across the export section below
+        if (LATE_C0) load_chunk(0, tile, valid, t);
         if (LATE_C1) load_chunk(1, tile, valid, t);
         if (has_rec) mbar_wait(&bars->recv_full, (n_rf++) & 1);
         if (tid == 64) BWD_TRACE(2, T - 1 - t, 0);
@@ -1909,7 +1920,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         // starts; issued after the export they arrive too late (+9 % kernel time), issued inside the chunk loop they
         // hold up the chunk's own dz / A-operand stores (+17 %).
         if (t > 0) {
-          load_chunk(0, tile, valid, t - 1);
+          if (!LATE_C0) load_chunk(0, tile, valid, t - 1);
           if (!LATE_C1) load_chunk(1, tile, valid, t - 1);
         }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----

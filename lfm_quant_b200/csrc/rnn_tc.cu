@@ -92,6 +92,9 @@ struct GArgs {
   int rt_off;          // first 128-row tile of this launch (the batch can be split over two concurrent launches)
 };
 
+#ifndef LFMQ_GEN_BWD_EW
+#define LFMQ_GEN_BWD_EW 3
+#endif
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3, EPI_HEAD = 4 };   // _ACC: expf / tanhf (bf16x3)
 
 struct EpiParams {
@@ -136,7 +139,7 @@ struct EpiParams {
 // CTAs leave: the loads are latency-bound (~5 K cycles per stage under load), bytes in flight are what buys bandwidth.
 template <int BN, int MT, int EPI = 0>
 struct GSmem {
-  static constexpr int EW = (EPI == 1) ? 2 : 1;          // warps per TMEM lane quadrant and M tile (2 for EPI_BWD)
+  static constexpr int EW = (EPI == 1) ? LFMQ_GEN_BWD_EW : 1;   // warps per TMEM lane quadrant and M tile (EPI_BWD)
   static constexpr uint32_t A_BYTES = MT * 128 * 128;     // MT x (128 rows x 64 bf16)
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
