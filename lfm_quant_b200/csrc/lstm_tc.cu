@@ -1601,7 +1601,12 @@ constexpr bool LATE_C1 = LFMQ_BWD_LATE_C1 != 0;
 #define LFMQ_BWD_LATE_C0 0
 #endif
 constexpr bool LATE_C0 = LFMQ_BWD_LATE_C0 != 0;     // experiment: the first chunk's operands at the top of the step as well
-constexpr int BWD_THREADS = 352;   // producer + MMA + 2 sets of 4 pointwise warps + dz store warp
+// Warp roles, by warpgroup (setmaxnreg moves registers between warpgroups): warps 0-3 pointwise set 0, warps 4-7 pointwise
+// set 1, warps 8-11 = producer, MMA issuer, dz store, idle.  The role warpgroup gives its registers up (72 each), the
+// pointwise warps take 216 (2 x 216 + 72 = the 504 of the 168 x 3 pool): the 168 of an even split left ~100 spilled values on the pointwise warps' path, with next to
+// no L1 to catch them (226 KB of shared memory in use).
+constexpr int BWD_THREADS = 384;
+constexpr int BWD_W_PROD = 8, BWD_W_MMA = 9, BWD_W_STORE = 10;
 constexpr uint32_t SB_U = 0;                    // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SB_A = 131072;               // 2 stages x [128 x 128 B]
 constexpr uint32_t SB_R = 163840;               // 3 foreign slices x [128 x 128 B]
@@ -1646,16 +1651,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     mbar_init(&bars->dpb_free, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == BWD_W_MMA) tmem_alloc(&bars->tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
   // programmatic dependent launch: the weight slices (packed at the start of the step) load under the predecessor's tail
-  if (!(warp == 0 && lane == 0)) pdl_sync();
+  if (!(warp == BWD_W_PROD && lane == 0)) pdl_sync();
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  // one setmaxnreg for the whole role warpgroup (it is warpgroup-collective), then the roles; not re-indented
+  setmaxnreg_dec<72>();
+  if (warp == BWD_W_PROD) {
     // ===================== TMA producer: weights once, then the foreign partial slices of every step =========
     // (an L2 prefetch of the saved activations two steps ahead was tried here and made the kernel 25 % slower)
     if (lane == 0) {
@@ -1693,7 +1701,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == BWD_W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256, false, false);
@@ -1742,7 +1750,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == BWD_W_STORE) {
     // ===================== dz store warp =====================
     // dz_t of every staged chunk leaves for HBM straight from the A operand: one TMA store (128 rows x 128 B, rows >= B
     // clipped) instead of four STG.256 per pointwise thread.  dz keeps the operand's column order [16-unit block][gate][16]
@@ -1769,12 +1777,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       }
       bulk_wait_group0();                        // all dz stores complete before the kernel ends
     }
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ===================== pointwise gate gradients, A-operand staging, partial exchange =====================
     // Two warp-sets (A: warps 2-5, B: warps 6-9) split the four 16-unit chunks of a step: set s handles chunks
     // s and s+2 and owns A-operand stage s, so two chunks' global loads are always in flight together, and each
     // set issues the loads of its first chunk of step t-1 before the exchange of step t (they do not depend on it).
-    const int set = (warp - 2) >> 2;         // 0 / 1
+    const int set = warp >> 2;               // 0 / 1
     const int wq = warp & 3;                 // TMEM lane quadrant
     const int m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
@@ -1951,8 +1961,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 4);
           named_bar_sync(1, 256);
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 5);
-          if (warp == 2 && lane == 0) mbar_arrive(&bars->recv_free);
-          if (warp == 2 && lane >= 1 && lane < BWD_NC) {
+          if (warp == 0 && lane == 0) mbar_arrive(&bars->recv_free);
+          if (warp == 0 && lane >= 1 && lane < BWD_NC) {
             mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
           }
         }
@@ -1965,7 +1975,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   __syncwarp();
   tcgen05_fence_before();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == BWD_W_MMA) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================

@@ -93,7 +93,7 @@ struct GArgs {
 };
 
 #ifndef LFMQ_GEN_BWD_EW
-#define LFMQ_GEN_BWD_EW 3
+#define LFMQ_GEN_BWD_EW 2
 #endif
 enum { EPI_FWD = 0, EPI_BWD = 1, EPI_STORE = 2, EPI_FWD_ACC = 3, EPI_HEAD = 4 };   // _ACC: expf / tanhf (bf16x3)
 

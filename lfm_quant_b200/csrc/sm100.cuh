@@ -162,6 +162,12 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- register re-allocation between warpgroups (4 aligned consecutive warps execute it together) ---------
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- TMEM allocation ---------------------------------------------------------------------------
 // Whole-warp calls.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
