@@ -1596,10 +1596,25 @@ constexpr int BWD_NC = 4;
 #ifndef LFMQ_BWD_LATE_C1
 #define LFMQ_BWD_LATE_C1 1
 #endif
-constexpr bool LATE_C1 = LFMQ_BWD_LATE_C1 != 0;
+constexpr bool LATE_C1 = LFMQ_BWD_LATE_C1 == 1;     // at the top of the step
+constexpr bool POST_C1 = LFMQ_BWD_LATE_C1 == 2;     // experiment: right after the export stores of the previous step
 #ifndef LFMQ_BWD_LATE_C0
 #define LFMQ_BWD_LATE_C0 0
 #endif
+#ifndef LFMQ_BWD_DSMEM
+#define LFMQ_BWD_DSMEM 0
+#endif
+// Partial exchange: 0 = through L2 (st.global, cluster arrive, TMA load by the peer's producer); 1 = every pointwise
+// thread pushes its piece of the foreign slices straight into the peers' shared memory (st.async completing tx-bytes on
+// the peer's recv_full).  Measured (profiles/r02_time_c19_dsmem_exchange.txt): the push makes the export itself shorter
+// (3.4 K -> 1.9 K cycles) but the 48 KB per CTA and step take ~4 K cycles to land (DSMEM moves ~12 B/clk/SM), against
+// 2.6 K for signal + TMA load from L2: bwd 0.304 -> 0.341 ms.  Kept as a build option, off.
+constexpr bool DSMEM_X = LFMQ_BWD_DSMEM != 0;
+#ifndef LFMQ_BWD_WARP_SIGNAL
+#define LFMQ_BWD_WARP_SIGNAL 0
+#endif
+// 1 = every pointwise warp signals the peers itself after its own export stores (no CTA-wide named barrier first)
+constexpr bool WARP_SIG = LFMQ_BWD_WARP_SIGNAL != 0 && !DSMEM_X;
 constexpr bool LATE_C0 = LFMQ_BWD_LATE_C0 != 0;     // experiment: the first chunk's operands at the top of the step as well
 // Warp roles, by warpgroup (setmaxnreg moves registers between warpgroups): warps 0-3 pointwise set 0, warps 4-7 pointwise
 // set 1, warps 8-11 = producer, MMA issuer, dz store, idle.  The role warpgroup gives its registers up (72 each), the
@@ -1645,8 +1660,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       mbar_init(&bars->acc_full[i], 1);
     }
     mbar_init(&bars->recv_full, 1);
-    mbar_init(&bars->recv_free, 1);
-    mbar_init(&bars->exp_ready, BWD_NC - 1);
+    mbar_init(&bars->recv_free, WARP_SIG ? 8 : 1);
+    mbar_init(&bars->exp_ready, (DSMEM_X || WARP_SIG) ? (BWD_NC - 1) * 8 : BWD_NC - 1);   // DSMEM_X: 'peers have read my last export'
     mbar_init(&bars->dpb_full, 1);
     mbar_init(&bars->dpb_free, 1);
     fence_mbar_init();
@@ -1685,7 +1700,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       if (FUSED && lane == 0) load_dpred(tile, T - 1);
       for (int t = T - 1; t >= 0; --t) {
         if (FUSED && lane == 0 && t > 0) load_dpred(tile, t - 1);      // for the MMA appended to this step
-        if (lane == 0 && t <= T - 2) {               // step t consumes the partials exported after step t+1
+        if (DSMEM_X && lane == 0 && t <= T - 2) {    // peers push the slices themselves: only arm the barrier, one phase
+          if (n_er > 0) mbar_wait(&bars->recv_full, (n_er - 1) & 1);    // at a time
+          ++n_er;
+          BWD_TRACE(0, T - 1 - t, 0);
+          mbar_arrive_expect_tx(&bars->recv_full, 3 * 16384);
+        }
+        if (!DSMEM_X && lane == 0 && t <= T - 2) {   // step t consumes the partials exported after step t+1
           mbar_wait_cluster(&bars->exp_ready, (n_er) & 1);
           mbar_wait(&bars->recv_free, (n_er++) & 1);    // own epilogue is done reading the previous slices
           BWD_TRACE(0, T - 1 - t, 0);
@@ -1791,6 +1812,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     const int sw = m & 7;
     float dc[32];
     uint32_t gs = 0, n_rf = 0;
+    uint32_t n_exp = 0;                      // exports done (DSMEM_X)
     uint32_t caf[2] = {0, 0};                // completed phases of acc_full[b] (mirrors the MMA warp's commit sequence)
     // inputs of this set's two chunks of one step (slot ci): loaded ahead of the exchange they do not depend on
     uint32_t gi[2][8], gf[2][8], gg[2][8], go[2][8], dhp[2][8], ct[2][8], cp[2][8];
@@ -1837,7 +1859,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < 32; ++j) dc[j] = 0.f;
       if (!LATE_C0) load_chunk(0, tile, valid, T - 1);
-      if (!LATE_C1) load_chunk(1, tile, valid, T - 1);
+      if (!LATE_C1) load_chunk(1, tile, valid, T - 1);     // (also POST_C1: nothing precedes the first step)
       if (FUSED) {                             // the head's dLoss/dh_{T-1} for the own slice is in the accumulator
         const uint32_t pb = (gs + 1) & 1;
         mbar_wait(&bars->acc_full[pb], caf[pb] & 1);
@@ -1925,13 +1947,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           if (tid == 192 && ci == 0) BWD_TRACE(0, T - 1 - t, 1);     // warp-set 1 in the producer row's free slots
           if (tid == 192 && ci == 1) BWD_TRACE(0, T - 1 - t, 2);
         }
+        if (DSMEM_X && has_rec) {                    // this warp is done with the received slices: tell the three senders
+          __syncwarp();
+          if (lane >= 1 && lane < BWD_NC)
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
+        }
         // inputs of both chunks of the next step: independent of the exchange below.  Placement matters because the
         // SM's memory pipe is a FIFO: issued here they delay the export slightly but land before the next step
         // starts; issued after the export they arrive too late (+9 % kernel time), issued inside the chunk loop they
         // hold up the chunk's own dz / A-operand stores (+17 %).
         if (t > 0) {
           if (!LATE_C0) load_chunk(0, tile, valid, t - 1);
-          if (!LATE_C1) load_chunk(1, tile, valid, t - 1);
+          if (!LATE_C1 && !POST_C1) load_chunk(1, tile, valid, t - 1);
         }
         // ---- export the foreign slices of partial_t (needed by the peers for step t-1) ----
         if (t > 0) {
@@ -1940,8 +1967,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           tcgen05_fence_after();
           const uint32_t acc = tmem + (gs & 1) * 256 + lane_addr;
           const int par = t & 1;
+          if (DSMEM_X) {
+            // all 24 reader warps of the three peers have released the slices of the previous export
+            if (n_exp > 0) mbar_wait_cluster(&bars->exp_ready, (n_exp - 1) & 1);
+            ++n_exp;
 #pragma unroll
-          for (uint32_t d = 1; d < BWD_NC; ++d) {
+            for (uint32_t d = 1; d < BWD_NC; ++d) {
+              const uint32_t dst = (rank + d) & 3;
+              // at the receiver, slot (d' - 1) holds the slice of source (dst + d') & 3: d' = 4 - d
+              const uint32_t rrow = mapa_u32(smem_u32(smem + SB_R + (3 - d) * 16384 + m * 128), dst);
+              const uint32_t rbar = mapa_u32(smem_u32(&bars->recv_full), dst);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(acc + dst * 64 + set * 32 + hh * 16, v);
+                tmem_ld_wait();
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                const int c0 = set * 4 + hh * 2;           // 16-byte chunk of the 64-column slice, 128B-swizzled by row
+                st_async_v4(rrow + (((c0) ^ sw) << 4), rbar, pk[0], pk[1], pk[2], pk[3]);
+                st_async_v4(rrow + (((c0 + 1) ^ sw) << 4), rbar, pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+          }
+#pragma unroll
+          for (uint32_t d = 1; d < BWD_NC && !DSMEM_X; ++d) {
             const uint32_t dst = (rank + d) & 3;
             __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64 + set * 32;
             // 16 columns at a time: the next step's operands (112 registers) are live across this section, and the
@@ -1958,11 +2009,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             }
           }
           tcgen05_fence_before();
+          if (POST_C1) load_chunk(1, tile, valid, t - 1);
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 4);
-          named_bar_sync(1, 256);
+          if (!DSMEM_X && !WARP_SIG) named_bar_sync(1, 256);
+          if (WARP_SIG) __syncwarp();
           if (tid == 64) BWD_TRACE(2, T - 1 - t, 5);
-          if (warp == 0 && lane == 0) mbar_arrive(&bars->recv_free);
-          if (warp == 0 && lane >= 1 && lane < BWD_NC) {
+          if (!DSMEM_X && (warp == 0 || WARP_SIG) && lane == 0) mbar_arrive(&bars->recv_free);
+          if (!DSMEM_X && (warp == 0 || WARP_SIG) && lane >= 1 && lane < BWD_NC) {
             mbar_arrive_cluster(mapa_u32(smem_u32(&bars->exp_ready), (rank + (uint32_t)lane) & 3));
           }
         }
