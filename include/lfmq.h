@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LFMQ_ABI_VERSION 3   /* 3: LFMQ_PREC_BF16X3, general tensor-core path, lfmq_validate */
+#define LFMQ_ABI_VERSION 4   /* 3: LFMQ_PREC_BF16X3, general tensor-core path; 4: lfmq_chain_* (forecast_steps > 1) */
 
 enum { LFMQ_OK = 0, LFMQ_ERR_ARG = 1, LFMQ_ERR_CUDA = 2, LFMQ_ERR_UNSUPPORTED = 3, LFMQ_ERR_WORKSPACE = 4 };
 enum { LFMQ_OPT_ADADELTA = 0, LFMQ_OPT_ADAM = 1, LFMQ_OPT_RMSPROP = 2, LFMQ_OPT_SGD = 3 };
@@ -147,6 +147,31 @@ int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream);
  * handle {uq_loss_last_tar, mse_0}, the pair Train._train_step_uq_range returns (train.py:225). */
 int32_t lfmq_train_step(lfmq_handle h, const float* x, const float* y, int32_t B, int64_t row0, int64_t step,
                         float lr, float* loss_out_dev, void* stream);
+
+/* ---- forecast_steps > 1 (models/point_estimate/rnn_point_estimate.py:109-150; models/model_base_class.py:18-51) ----
+ * The Keras graph of S forecast steps is S stages: stage 0 = the trunk handle (num_layers layers + OUTPUT_1); stage
+ * s >= 1 = one more handle with num_layers = 1 (lstm_{L+s} / gru_{L+s}, its BatchNormalization and Dropout, OUTPUT_{s+1})
+ * created with the same seq_len / n_inputs / n_outputs / max_batch.  Stage s reads the previous stage's input window
+ * shifted by one step with [pred_{s-1}[:, T-1, :], aux features of the last ORIGINAL step] appended (:113-124).
+ * `stages`, `preds`, `y` are host arrays of n_stages (<= 8) entries; `weights` = config.forecast_steps_weights (host).
+ * `work`: device floats, n_stages * B * seq_len * n_inputs (stage inputs + one input-gradient buffer).
+ * Dropout streams of stage s continue the trunk's layer numbering (layer num_layers + s - 1).
+ * Training-mode stages (cfg.train) run on the LFMQ_PREC_FP32 kernels; forward_only stages may use any precision. */
+/* model(inp) -> [pred_1 .. pred_S], each [B,T,O] (train.py:182, predict.py:129) */
+int32_t lfmq_chain_forward(const lfmq_handle* stages, int32_t n_stages, const float* x, int32_t B, int64_t row0,
+                           int64_t step, float* const* preds, float* work, void* stream);
+/* Losses.weight_adjusted_mse(y_true list, y_pred list) (losses.py:19-53): out_dev = {sum_s w_s loss_s, sum_s w_s mse_s} */
+int32_t lfmq_chain_loss(const lfmq_handle* stages, int32_t n_stages, const float* const* preds, const float* const* y,
+                        const float* weights, int32_t B, float* out_dev, void* stream);
+/* forward of all stages, the weighted loss, and BPTT through the whole graph: the input gradient of stage s flows into
+ * the last time step of the earlier predictions it was built from.  Fills every stage's gradient buffer;
+ * loss_out_dev (nullable) = {loss, mse} as lfmq_chain_loss. */
+int32_t lfmq_chain_backward(const lfmq_handle* stages, int32_t n_stages, const float* x, const float* const* y,
+                            const float* weights, int32_t B, int64_t row0, int64_t step, float* work,
+                            float* loss_out_dev, void* stream);
+/* tf.clip_by_global_norm over the variables of ALL stages (train.py:195-196, stage 0's max_grad_norm), then each
+ * stage's optimizer update and MaxNorm constraint. */
+int32_t lfmq_chain_apply(const lfmq_handle* stages, int32_t n_stages, float lr, int64_t iteration, void* stream);
 
 /* Dataset.get_batch (data_processing.py:307-368) with _get_train_seq/_get_pred_seq (:370-449) and
  * log_squasher (:600-609) over a device-resident float64 copy of Dataset.data_values' numeric columns.

@@ -13,7 +13,7 @@ _LIB_PATH = os.environ.get('LFMQ_LIB_PATH') or os.path.join(os.path.dirname(os.p
 OPTIMIZERS = {'Adadelta': 0, 'Adam': 1, 'RMSprop': 2, 'SGD': 3}
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 CELLS = {'lstm': 0, 'gru': 1}           # LFMQ_CELL_*
-ABI_VERSION = 3                         # LFMQ_ABI_VERSION in include/lfmq.h (3: LFMQ_PREC_BF16X3, general tensor-core path)
+ABI_VERSION = 4                         # LFMQ_ABI_VERSION in include/lfmq.h (4: lfmq_chain_*, forecast_steps > 1)
 
 
 class LfmqConfig(C.Structure):
@@ -61,6 +61,10 @@ SYMBOLS = {
     'lfmq_backward': (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     'lfmq_apply': (C.c_int32, [_P, C.c_float, C.c_int64, _P]),
     'lfmq_train_step': (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_float, _P, _P]),
+    'lfmq_chain_forward': (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),
+    'lfmq_chain_loss': (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P]),
+    'lfmq_chain_backward': (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),
+    'lfmq_chain_apply': (C.c_int32, [_P, C.c_int32, C.c_float, C.c_int64, _P]),
     'lfmq_gather_batch': (C.c_int32, [C.POINTER(LfmqGatherArgs), _P]),
     'lfmq_unscale': (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P]),
     'lfmq_launch_count': (C.c_int64, []),

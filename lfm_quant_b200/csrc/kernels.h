@@ -46,6 +46,17 @@ int opt_update(cudaStream_t s, int opt, long n, float* p, const float* g, float*
 int maxnorm_cols(cudaStream_t s, int I, int N, float* W, float max_norm);
 int fill(cudaStream_t s, float* p, long n, float v);
 
+// forecast_steps > 1 (rnn_point_estimate.py:109-150): glue between the stage handles
+constexpr int LFMQ_MAX_STAGES = 8;
+struct ChainPtrs { float* p[LFMQ_MAX_STAGES]; };
+struct ChainWeights { float w[LFMQ_MAX_STAGES]; };
+int chain_next_input(cudaStream_t s, int B, int T, int F, int O, const float* prev, const float* pred, const float* x0,
+                     float* next);
+int scale_inplace(cudaStream_t s, long n, float* p, float w);
+int chain_scatter_dx(cudaStream_t s, int B, int T, int F, int O, int stage, const float* dx, const ChainPtrs& dpred);
+int chain_combine(cudaStream_t s, int S, const ChainPtrs& scalars, float clip, const ChainPtrs& loss2,
+                  const ChainWeights& w, float* out2);
+
 struct GatherArgs {
   int n_rows, n_cols, B, T, F, O, stride, seq_norm_col, log_squasher, aux_masking;
   const double* table;

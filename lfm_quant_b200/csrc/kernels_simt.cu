@@ -463,6 +463,98 @@ int add_bias_rows(cudaStream_t s, long rows, int N, float* C, const float* bias)
   return 0;
 }
 
+// ---- forecast_steps > 1: glue between the stages (rnn_point_estimate.py:109-124; model_base_class.py:18-51) ----
+// next[b, t, :] = prev[b, t + 1, :] for t < T-1 (Cropping1D((1,0)) of the concatenation), and the appended step
+// next[b, T-1, :] = [pred[b, T-1, 0:O], x0[b, T-1, O:F]] (latest prediction + the last AVAILABLE aux features).
+__global__ void chain_next_input_kernel(long n, int T, int F, int O, const float* __restrict__ prev,
+                                        const float* __restrict__ pred, const float* __restrict__ x0,
+                                        float* __restrict__ next) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = (int)(i % F);
+  const long bt = i / F;
+  const int t = (int)(bt % T);
+  const long b = bt / T;
+  float v;
+  if (t < T - 1) v = prev[i + F];
+  else if (k < O) v = pred[(b * T + (T - 1)) * O + k];
+  else v = x0[i];
+  next[i] = v;
+}
+
+int chain_next_input(cudaStream_t s, int B, int T, int F, int O, const float* prev, const float* pred, const float* x0,
+                     float* next) {
+  const long n = (long)B * T * F;
+  chain_next_input_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, T, F, O, prev, pred, x0, next);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void scale_inplace_kernel(long n, float* __restrict__ p, float w) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] *= w;
+}
+
+int scale_inplace(cudaStream_t s, long n, float* p, float w) {
+  scale_inplace_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, p, w);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// The input window of stage `stage` holds, at time position T-1-j (j = 0..stage-1), the step appended for stage
+// stage-j, whose first O columns are pred_{stage-1-j}[:, T-1, :]: the input gradient flows back into those rows.
+__global__ void chain_scatter_dx_kernel(int B, int T, int F, int O, int stage, const float* __restrict__ dx,
+                                        ChainPtrs dpred) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n = (long)B * stage * O;
+  if (i >= n) return;
+  const int k = (int)(i % O);
+  const int j = (int)((i / O) % stage);
+  const long b = i / ((long)O * stage);
+  dpred.p[stage - 1 - j][(b * T + (T - 1)) * O + k] += dx[(b * T + (T - 1 - j)) * F + k];
+}
+
+int chain_scatter_dx(cudaStream_t s, int B, int T, int F, int O, int stage, const float* dx, const ChainPtrs& dpred) {
+  const long n = (long)B * stage * O;
+  chain_scatter_dx_kernel<<<cdiv(n, 256), 256, 0, s>>>(B, T, F, O, stage, dx, dpred);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// tf.clip_by_global_norm over ALL stages' variables (train.py:196): every stage's tail holds its own ||g||; this
+// writes the joint norm and the joint clip scale into each of them.  out2 (nullable) = sum_s w_s {loss_s, mse_s}
+// (Losses.weight_adjusted_mse, losses.py:47-51), read from the stages' {loss, mse_0} pairs.
+__global__ void chain_combine_kernel(int S, ChainPtrs scalars, float clip, ChainPtrs loss2, ChainWeights w,
+                                     float* __restrict__ out2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (scalars.p[0]) {
+    double ss = 0;
+    for (int s = 0; s < S; ++s) ss += (double)scalars.p[s][0] * (double)scalars.p[s][0];
+    const float gn = (float)sqrt(ss);
+    const float sc = (clip > 0.f) ? clip / fmaxf(gn, clip) : 1.0f;
+    for (int s = 0; s < S; ++s) {
+      scalars.p[s][0] = gn;
+      scalars.p[s][1] = sc;
+    }
+  }
+  if (out2) {
+    float l = 0.f, m = 0.f;
+    for (int s = 0; s < S; ++s) {
+      l += w.w[s] * loss2.p[s][0];
+      m += w.w[s] * loss2.p[s][1];
+    }
+    out2[0] = l;
+    out2[1] = m;
+  }
+}
+
+int chain_combine(cudaStream_t s, int S, const ChainPtrs& scalars, float clip, const ChainPtrs& loss2,
+                  const ChainWeights& w, float* out2) {
+  chain_combine_kernel<<<1, 32, 0, s>>>(S, scalars, clip, loss2, w, out2);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void fill_kernel(float* p, long n, float v) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -50,6 +50,7 @@ struct lfmq_handle_s {
   size_t scratch_elems;
   lfmq::TcState tc;
   lfmq::GenState gen;
+  int stream_base = 0;       // first Philox stream index of this handle's layers (stage s of a forecast chain: 2 (L0+s-1))
   int use_gen;               // 1: the general tensor-core path (rnn_tc.cu) runs this handle's bf16 / bf16x3 work
   lfmq::Profiler prof;
 };
@@ -265,7 +266,7 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
     const float* rmask = nullptr;
     const bool stochastic = c.train || c.uq;       // rnn_uq_range_estimate.py:86,88: training=True is a literal there
     if (stochastic && c.recurrent_dropout > 0.f) {
-      RUN(gen_row_mask(s, B, H, make_key(c, 2 * l + 1, step, c.recurrent_dropout), row0, lb.rmask));
+      RUN(gen_row_mask(s, B, H, make_key(c, h->stream_base + 2 * l + 1, step, c.recurrent_dropout), row0, lb.rmask));
       rmask = lb.rmask;
     }
     for (int t = 0; t < T && c.rnn_cell == LFMQ_CELL_GRU; ++t) {
@@ -289,7 +290,7 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
     }
     const bool drop = stochastic && c.dropout > 0.f;
     RUN(bn_dropout_fwd(s, B, T, H, lb.h, P + lb.ogamma, P + lb.obeta, P + lb.omean, P + lb.ovar, c.bn_epsilon, drop,
-                       make_key(c, 2 * l, step, c.dropout), row0, lb.y));
+                       make_key(c, h->stream_base + 2 * l, step, c.dropout), row0, lb.y));
   }
   h->prof.end(LFMQ_REGION_FWD, s);
   h->prof.begin(LFMQ_REGION_HEAD, s);
@@ -306,7 +307,8 @@ int forward_fp32(lfmq_handle h, const float* x, int B, int64_t row0, int64_t ste
   return 0;
 }
 
-int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
+// dx_out (nullable): dLoss/dx [B,T,F] of the lowest layer (the stages of a forecast chain feed predictions back in)
+int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s, float* dx_out = nullptr) {
   const lfmq_config& c = h->cfg;
   const int H = c.num_hidden, T = c.seq_len, O = c.n_outputs, L = c.num_layers;
   const long BT = (long)B * T;
@@ -331,7 +333,7 @@ int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
     const bool drop = (c.train || c.uq) && c.dropout > 0.f;
     h->prof.begin(LFMQ_REGION_BWD, s);
     RUN(bn_dropout_bwd(s, B, T, H, h->dy, lb.h, P + lb.ogamma, P + lb.omean, P + lb.ovar, c.bn_epsilon, drop,
-                       make_key(c, 2 * l, h->tc.last_step, c.dropout), h->tc.last_row0, h->dh_out, G + lb.ogamma,
+                       make_key(c, h->stream_base + 2 * l, h->tc.last_step, c.dropout), h->tc.last_row0, h->dh_out, G + lb.ogamma,
                        G + lb.obeta, h->scratch, h->scratch_elems));
     const bool gru = c.rnn_cell == LFMQ_CELL_GRU;
     const int NG = gru ? 3 : 4;
@@ -361,10 +363,29 @@ int backward_fp32(lfmq_handle h, const float* x, int B, cudaStream_t s) {
     RUN(sgemm(s, H, GH, (int)BT, h->hp, 1, H, dzr, GH, 1, G + lb.oU, GH, 0.f, h->scratch, h->scratch_elems));
     RUN(colsum(s, BT, GH, h->dz, G + lb.ob, h->scratch, h->scratch_elems));
     if (gru) RUN(colsum(s, BT, GH, h->dz2, G + lb.ob + GH, h->scratch, h->scratch_elems));
-    if (l > 0)
-      RUN(sgemm(s, (int)BT, I, GH, h->dz, GH, 1, P + lb.oW, 1, GH, h->dy, I, 0.f, nullptr, 0));
+    if (l > 0 || dx_out)
+      RUN(sgemm(s, (int)BT, I, GH, h->dz, GH, 1, P + lb.oW, 1, GH, l > 0 ? h->dy : dx_out, I, 0.f, nullptr, 0));
     h->prof.end(LFMQ_REGION_WGRAD, s);
   }
+  return 0;
+}
+
+// optimizer update with the clip scale already in the gradient tail (tail[3]) + the MaxNorm kernel constraint
+int apply_update(lfmq_handle h, float lr, int64_t iteration, cudaStream_t s) {
+  const lfmq_config& c = h->cfg;
+  float* tail = h->grads + h->n_train;
+  float lr_eff = lr;
+  if (c.optimizer == LFMQ_OPT_ADAM) {
+    const double t = (double)(iteration + 1);
+    lr_eff = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+  }
+  RUN(opt_update(s, c.optimizer, h->n_train, h->params, h->grads, h->slots,
+                 h->n_slots > 1 ? h->slots + h->n_train : nullptr, tail + 2, lr_eff, 0.f, 0.f, c.sgd_momentum));
+  for (int l = 0; l < c.num_layers; ++l)
+    RUN(maxnorm_cols(s, h->layers[l].I, (c.rnn_cell == LFMQ_CELL_GRU ? 3 : 4) * c.num_hidden, h->params + h->layers[l].oW,
+                     c.max_norm));
+  h->tc.weights_dirty = 1;
+  h->gen.weights_dirty = 1;
   return 0;
 }
 
@@ -662,19 +683,8 @@ int32_t lfmq_apply(lfmq_handle h, float lr, int64_t iteration, void* stream) {
   float* tail = h->grads + h->n_train;
   h->prof.begin(LFMQ_REGION_OPT, s);
   RUN(grad_norm_scale(s, h->n_train, h->grads, c.max_grad_norm, tail + 2, h->scratch, h->tickets + 2));
-  float lr_eff = lr;
-  if (c.optimizer == LFMQ_OPT_ADAM) {
-    const double t = (double)(iteration + 1);
-    lr_eff = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
-  }
-  RUN(opt_update(s, c.optimizer, h->n_train, h->params, h->grads, h->slots,
-                 h->n_slots > 1 ? h->slots + h->n_train : nullptr, tail + 2, lr_eff, 0.f, 0.f, c.sgd_momentum));
-  for (int l = 0; l < c.num_layers; ++l)
-    RUN(maxnorm_cols(s, h->layers[l].I, (c.rnn_cell == LFMQ_CELL_GRU ? 3 : 4) * c.num_hidden, h->params + h->layers[l].oW,
-                     c.max_norm));
+  RUN(apply_update(h, lr, iteration, s));
   h->prof.end(LFMQ_REGION_OPT, s);
-  h->tc.weights_dirty = 1;
-  h->gen.weights_dirty = 1;
   return LFMQ_OK;
 }
 
@@ -691,6 +701,162 @@ int32_t lfmq_train_step(lfmq_handle h, const float* x, const float* y, int32_t B
     LFMQ_CUDA_CHECK(cudaMemcpyAsync(loss_out_dev + 1, h->grads + h->n_train + 1, sizeof(float), cudaMemcpyDeviceToDevice,
                                     (cudaStream_t)stream));
   }
+  return LFMQ_OK;
+}
+
+// ---- forecast_steps > 1 (rnn_point_estimate.py:109-150) -------------------------------------------------------
+namespace {
+// Stage 0 is the trunk (num_layers layers + OUTPUT_1); stage s >= 1 one more recurrent layer + BatchNormalization +
+// Dropout + OUTPUT_{s+1} on the raw feature width.  All stages share T, F, O.
+int chain_check(const lfmq_handle* st, int32_t S, int32_t B, bool training) {
+  if (!st || S < 1 || S > lfmq::LFMQ_MAX_STAGES) {
+    LFMQ_SET_ERR("lfmq_chain: n_stages %d outside [1, %d]", S, lfmq::LFMQ_MAX_STAGES);
+    return LFMQ_ERR_ARG;
+  }
+  for (int i = 0; i < S; ++i) {
+    RUN(check_batch(st[i], B));
+    const lfmq_config& c = st[i]->cfg;
+    const lfmq_config& c0 = st[0]->cfg;
+    if (c.seq_len != c0.seq_len || c.n_inputs != c0.n_inputs || c.n_outputs != c0.n_outputs || c.uq ||
+        (i > 0 && c.num_layers != 1)) {
+      LFMQ_SET_ERR("lfmq_chain: stage %d does not continue stage 0 (same T/F/O, one layer, point estimate)", i);
+      return LFMQ_ERR_ARG;
+    }
+    if ((training || c.train) && c.precision != LFMQ_PREC_FP32) {
+      LFMQ_SET_ERR("lfmq_chain: training-mode stages run on the fp32 kernels (stage %d has precision %d)", i, c.precision);
+      return LFMQ_ERR_UNSUPPORTED;
+    }
+    if (training && c.forward_only) {
+      LFMQ_SET_ERR("lfmq_chain: stage %d was created forward_only", i);
+      return LFMQ_ERR_UNSUPPORTED;
+    }
+    // the Philox stream index continues after the trunk's layers: the extra layer of stage i is layer L0 + i - 1
+    st[i]->stream_base = (i == 0) ? 0 : 2 * (c0.num_layers + i - 1);
+  }
+  return 0;
+}
+}  // namespace
+
+int32_t lfmq_chain_forward(const lfmq_handle* stages, int32_t n_stages, const float* x, int32_t B, int64_t row0,
+                           int64_t step, float* const* preds, float* work, void* stream) {
+  RUN(chain_check(stages, n_stages, B, false));
+  if (!x || !preds || (n_stages > 1 && !work)) {
+    LFMQ_SET_ERR("lfmq_chain_forward: null pointer");
+    return LFMQ_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const lfmq_config& c = stages[0]->cfg;
+  const size_t slot = (size_t)B * c.seq_len * c.n_inputs;
+  const float* in = x;
+  for (int i = 0; i < n_stages; ++i) {
+    if (!preds[i]) {
+      LFMQ_SET_ERR("lfmq_chain_forward: preds[%d] == NULL", i);
+      return LFMQ_ERR_ARG;
+    }
+    if (i > 0) {
+      float* next = work + (size_t)(i - 1) * slot;
+      RUN(chain_next_input(s, B, c.seq_len, c.n_inputs, c.n_outputs, in, preds[i - 1], x, next));
+      in = next;
+    }
+    RUN(lfmq_forward(stages[i], in, B, row0, step, preds[i], stream));
+  }
+  return LFMQ_OK;
+}
+
+int32_t lfmq_chain_loss(const lfmq_handle* stages, int32_t n_stages, const float* const* preds, const float* const* y,
+                        const float* weights, int32_t B, float* out_dev, void* stream) {
+  if (!stages || n_stages < 1 || n_stages > lfmq::LFMQ_MAX_STAGES || !preds || !y || !weights || !out_dev || B <= 0) {
+    LFMQ_SET_ERR("lfmq_chain_loss: bad argument");
+    return LFMQ_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  lfmq::ChainPtrs none{}, l2{};
+  lfmq::ChainWeights w{};
+  for (int i = 0; i < n_stages; ++i) {
+    if (!stages[i]) {
+      LFMQ_SET_ERR("lfmq_chain_loss: null handle");
+      return LFMQ_ERR_ARG;
+    }
+    l2.p[i] = stages[i]->scalars + 10;      // two spare floats of the handle's scalar block
+    RUN(lfmq_loss(stages[i], preds[i], y[i], B, l2.p[i], stream));
+    w.w[i] = weights[i];
+  }
+  return chain_combine(s, n_stages, none, 0.f, l2, w, out_dev);
+}
+
+int32_t lfmq_chain_backward(const lfmq_handle* stages, int32_t n_stages, const float* x, const float* const* y,
+                            const float* weights, int32_t B, int64_t row0, int64_t step, float* work,
+                            float* loss_out_dev, void* stream) {
+  RUN(chain_check(stages, n_stages, B, true));
+  if (!x || !y || !weights || !work) {
+    LFMQ_SET_ERR("lfmq_chain_backward: null pointer");
+    return LFMQ_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = n_stages;
+  const lfmq_config& c0 = stages[0]->cfg;
+  const int T = c0.seq_len, F = c0.n_inputs, O = c0.n_outputs;
+  const size_t slot = (size_t)B * T * F;
+  float* dx = work + (size_t)(S - 1) * slot;
+  // forward of every stage (each keeps its own saved state), then each stage's loss and dLoss/dpred_s, weighted
+  lfmq::ChainPtrs dpred{}, l2{}, none{};
+  lfmq::ChainWeights w{};
+  const float* in = x;
+  for (int i = 0; i < S; ++i) {
+    lfmq_handle h = stages[i];
+    const lfmq_config& c = h->cfg;
+    if (!y[i]) {
+      LFMQ_SET_ERR("lfmq_chain_backward: y[%d] == NULL", i);
+      return LFMQ_ERR_ARG;
+    }
+    h->tc.last_step = step;
+    h->tc.last_row0 = row0;
+    if (i > 0) {
+      float* next = work + (size_t)(i - 1) * slot;
+      RUN(chain_next_input(s, B, T, F, O, in, stages[i - 1]->preds, x, next));
+      in = next;
+    }
+    RUN(forward_fp32(h, in, B, row0, step, h->preds, nullptr, s));
+    RUN(mask_count(s, B, T, O, y[i], h->denom, h->tickets));
+    float* tail = h->grads + h->n_train;
+    RUN(loss_grad(s, B, T, O, h->preds, y[i], h->denom, c.target_idx, c.target_lambda, c.rnn_lambda, h->dpred, tail,
+                  nullptr, h->scratch));
+    if (weights[i] != 1.0f) RUN(scale_inplace(s, (long)B * T * O, h->dpred, weights[i]));
+    dpred.p[i] = h->dpred;
+    l2.p[i] = tail;
+    w.w[i] = weights[i];
+  }
+  if (loss_out_dev) RUN(chain_combine(s, S, none, 0.f, l2, w, loss_out_dev));
+  // BPTT from the last stage down; the input gradient of stage i lands on the last time step of earlier predictions
+  for (int i = S - 1; i >= 1; --i) {
+    const float* in_i = work + (size_t)(i - 1) * slot;
+    RUN(backward_fp32(stages[i], in_i, B, s, dx));
+    RUN(chain_scatter_dx(s, B, T, F, O, i, dx, dpred));
+  }
+  return backward_fp32(stages[0], x, B, s);
+}
+
+int32_t lfmq_chain_apply(const lfmq_handle* stages, int32_t n_stages, float lr, int64_t iteration, void* stream) {
+  if (!stages || n_stages < 1 || n_stages > lfmq::LFMQ_MAX_STAGES) {
+    LFMQ_SET_ERR("lfmq_chain_apply: bad argument");
+    return LFMQ_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  lfmq::ChainPtrs sc{}, none{};
+  lfmq::ChainWeights w{};
+  for (int i = 0; i < n_stages; ++i) {
+    lfmq_handle h = stages[i];
+    if (!h || h->cfg.forward_only) {
+      LFMQ_SET_ERR("lfmq_chain_apply: bad handle");
+      return LFMQ_ERR_ARG;
+    }
+    float* tail = h->grads + h->n_train;
+    RUN(grad_norm_scale(s, h->n_train, h->grads, 0.f, tail + 2, h->scratch, h->tickets + 2));   // tail[2] = ||g_stage||
+    sc.p[i] = tail + 2;
+  }
+  // tf.clip_by_global_norm over all stages' variables (train.py:196)
+  RUN(chain_combine(s, n_stages, sc, stages[0]->cfg.max_grad_norm, none, w, nullptr));
+  for (int i = 0; i < n_stages; ++i) RUN(apply_update(stages[i], lr, iteration, s));
   return LFMQ_OK;
 }
 

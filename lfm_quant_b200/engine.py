@@ -234,6 +234,127 @@ class ForecasterEngine(object):
         return int(self.lib.lfmq_launch_count())
 
 
+class ForecastChainEngine(object):
+    """forecast_steps > 1 (scripts/models/point_estimate/rnn_point_estimate.py:109-150): stage 0 is the trunk, every
+    further stage one more recurrent layer + BatchNormalization + Dropout + Dense on the shifted input window.  One
+    ForecasterEngine (one C-ABI handle) per stage; the lfmq_chain_* entry points run the whole graph."""
+
+    def __init__(self, *, forecast_steps, weights, num_layers, **kw):
+        assert forecast_steps >= 1
+        self.S = int(forecast_steps)
+        self.stages = [ForecasterEngine(num_layers=num_layers if s == 0 else 1, **kw) for s in range(self.S)]
+        e0 = self.stages[0]
+        self.lib, self.device, self.cfg, self.precision = e0.lib, e0.device, e0.cfg, e0.precision
+        self.T, self.F, self.O, self.H, self.L = e0.T, e0.F, e0.O, e0.H, e0.L
+        self.weights = [float(w) for w in weights]
+        assert len(self.weights) == self.S, (self.weights, self.S)
+        self._handles = (C.c_void_p * self.S)(*[e.handle.value for e in self.stages])
+        self._w = (C.c_float * self.S)(*self.weights)
+        self._work = None
+        # Keras names: the extra layer of stage s is lstm_{L+s} / batch_normalization_{L+s-1} / OUTPUT_{s+1}
+        self.specs = []            # (stage, name, shape, offset in the stage's flat vector, trainable)
+        cell = kw.get('rnn_cell', 'lstm')
+        for s, e in enumerate(self.stages):
+            for name, shp, off, tr in e.specs:
+                if s > 0:
+                    name = name.replace('%s_1/' % cell, '%s_%d/' % (cell, self.L + s))
+                    name = name.replace('batch_normalization/', 'batch_normalization_%d/' % (self.L + s - 1))
+                    name = name.replace('OUTPUT_1/', 'OUTPUT_%d/' % (s + 1))
+                self.specs.append((s, name, shp, off, tr))
+        self.n_total = sum(e.n_total for e in self.stages)
+        self.n_trainable = sum(e.n_trainable for e in self.stages)
+
+    def _ptrs(self, tensors):
+        return (C.c_void_p * self.S)(*[t.data_ptr() for t in tensors])
+
+    def _workbuf(self, B):
+        n = self.S * B * self.T * self.F
+        if self._work is None or self._work.numel() < n:
+            self._work = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self._work
+
+    def forward(self, x, step=0, row0=0):
+        """model(inp) -> [pred_1 .. pred_S], device tensors [B,T,O]."""
+        B = self.stages[0]._check_x(x)
+        preds = [torch.empty(B, self.T, self.O, dtype=torch.float32, device=x.device) for _ in range(self.S)]
+        N.check(self.lib.lfmq_chain_forward(self._handles, self.S, _ptr(x), B, row0, step, self._ptrs(preds),
+                                            _ptr(self._workbuf(B)), _stream()))
+        return preds
+
+    def loss(self, preds, ys):
+        """Losses.weight_adjusted_mse(ys, preds): device tensor {loss, mse}."""
+        out = torch.empty(2, dtype=torch.float32, device=preds[0].device)
+        preds = [p.contiguous() for p in preds]
+        ys = [y.contiguous() for y in ys]
+        N.check(self.lib.lfmq_chain_loss(self._handles, self.S, self._ptrs(preds), self._ptrs(ys), self._w,
+                                         preds[0].shape[0], _ptr(out), _stream()))
+        return out
+
+    def backward(self, x, ys, step=0, row0=0, out=None):
+        B = self.stages[0]._check_x(x)
+        assert len(ys) == self.S
+        for y in ys:
+            assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == (B, self.T, self.O)
+        if out is None:
+            out = torch.empty(2, dtype=torch.float32, device=x.device)
+        N.check(self.lib.lfmq_chain_backward(self._handles, self.S, _ptr(x), self._ptrs(ys), self._w, B, row0, step,
+                                             _ptr(self._workbuf(B)), _ptr(out), _stream()))
+        return out
+
+    def apply(self, lr, iteration):
+        N.check(self.lib.lfmq_chain_apply(self._handles, self.S, float(lr), int(iteration), _stream()))
+
+    def train_step(self, x, ys, step, lr):
+        """One Train._train_step_point over the S-output model; device tensor {loss, mse}."""
+        out = self.backward(x, ys, step=step)
+        self.apply(lr, step)
+        return out
+
+    def unscale(self, arr, scale, center, log_squasher):
+        return self.stages[0].unscale(arr, scale, center, log_squasher)
+
+    @property
+    def launch_count(self):
+        return self.stages[0].launch_count
+
+    def grads_list(self):
+        return [g for e in self.stages for g in e.grads_list()]
+
+    def get_weights(self, trainable_only=True):
+        return [w for e in self.stages for w in e.get_weights(trainable_only)]
+
+    def set_weights(self, weights):
+        """weights in trainable_variables order: the trunk's, then 7 per extra stage."""
+        i = 0
+        for e in self.stages:
+            n = len(e.trainable_specs)
+            e.set_weights(weights[i:i + n])
+            i += n
+        assert i == len(weights)
+
+    def named_arrays(self):
+        out = {}
+        flats = [e.get_flat() for e in self.stages]
+        for s, name, shp, off, _ in self.specs:
+            out[name] = flats[s][off:off + int(np.prod(shp))].reshape(shp).copy()
+        return out
+
+    def load_named(self, get):
+        for s, e in enumerate(self.stages):
+            flat = e.get_flat()
+            for st, name, shp, off, _ in self.specs:
+                if st != s:
+                    continue
+                w = np.asarray(get(name), dtype=np.float32)
+                assert tuple(w.shape) == tuple(shp), (name, w.shape, shp)
+                flat[off:off + w.size] = w.ravel()
+            e.set_flat(flat)
+
+    def close(self):
+        for e in self.stages:
+            e.close()
+
+
 class HostBatchPipeline(object):
     """Feeds host-resident (pinned) batches to a ForecasterEngine with the H2D copy of step i+1 overlapped with the
     compute of step i (two device buffers, one copy stream) and an asynchronous D2H read of every step's

@@ -1,6 +1,7 @@
 """Losses(config, target_idx).weight_adjusted_mse (reference: scripts/model_utils/losses.py:19-135), evaluated by
-the native loss kernel (lfmq_loss), and Losses.weight_adjusted_uq_loss (:137-284) by lfmq_loss_uq.  Only the RNN
-branches with forecast_steps == 1 are built; the MLP / Huber branches belong to other model families."""
+the native loss kernel (lfmq_loss; lfmq_chain_loss for forecast_steps > 1), and Losses.weight_adjusted_uq_loss
+(:137-284) by lfmq_loss_uq (forecast_steps == 1).  Only the RNN branches are built; the MLP / Huber branches belong to
+other model families."""
 from __future__ import absolute_import, division, print_function
 
 import numpy as np
@@ -36,12 +37,23 @@ class Losses(object):
             'arguments to loss function need to be a list [y_true], [y_true1, y_true2, ..]'
         assert isinstance(y_pred, (list, tuple)), \
             'arguments to loss function need to be a list [y_pred], [y_pred1, y_pred2, ..]'
-        if self.config.forecast_steps != 1 or 'RNN' not in self.config.nn_type:
-            raise NotImplementedError('only RNN point estimates with forecast_steps=1 are built on this path')
-        if len(self.config.forecast_steps_weights) == 1:
-            self.config.forecast_steps_weights = [1.0]           # losses.py:44-45
-        loss, mse = self._get_loss_point_estimate(y_true[0], y_pred[0], is_validation)
-        return loss, mse
+        if 'RNN' not in self.config.nn_type:
+            raise NotImplementedError('only RNN point estimates are built on this path')
+        S = self.config.forecast_steps
+        if S == 1:
+            if len(self.config.forecast_steps_weights) == 1:
+                self.config.forecast_steps_weights = [1.0]       # losses.py:44-45
+            return self._get_loss_point_estimate(y_true[0], y_pred[0], is_validation)
+        # losses.py:36-51: per-step loss / mse, linearly weighted -- one native call over the S pairs
+        assert len(y_true) == S and len(y_pred) == S
+        assert len(self.config.forecast_steps_weights) == S
+        import torch
+        assert self.engine is not None, 'Losses is not bound to a native engine'
+        dev = self.engine.device
+        to = lambda a: (a if isinstance(a, torch.Tensor) else
+                        torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))).to(dev, torch.float32).contiguous()
+        out = self.engine.loss([to(p) for p in y_pred], [to(y) for y in y_true])
+        return _Scalar(out[0]), _Scalar(out[1])
 
     def _get_loss_point_estimate(self, y_true, y_pred, is_validation=False):
         import torch

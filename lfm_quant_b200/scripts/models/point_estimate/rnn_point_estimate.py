@@ -25,6 +25,100 @@ class _Variable(object):
         return self._model.engine.get_weights()[self._index]
 
 
+class NativeChainForecaster(object):
+    """The model object for forecast_steps > 1 (reference :109-150): ``model(inp)`` and ``model.predict(inp)`` return
+    the list [pred_1 .. pred_S]; ``train_step`` takes the list of S targets.  Every extra forecast step is one more
+    recurrent layer + BatchNormalization + Dropout + Dense over the input window shifted by one, with
+    [latest prediction's last time step, last available aux features] appended (models/model_base_class.py:18-51).
+    Training-mode graphs run on the fp32 kernels; a forward-only graph (predict.py) may use any precision."""
+
+    uq = False
+
+    def __init__(self, config, seq_len, n_inputs, n_outputs, target_idx):
+        from ....engine import ForecastChainEngine
+        self.config = config
+        if config.rnn_cell not in ('lstm', 'gru'):
+            raise NotImplementedError                    # rnn_point_estimate.py:148-149
+        precision = getattr(config, 'precision', 'fp32')
+        if config.train and precision != 'fp32':
+            raise NotImplementedError('forecast_steps > 1 trains on the fp32 kernels (precision=%s)' % precision)
+        w = list(config.forecast_steps_weights)
+        assert len(w) == config.forecast_steps, 'forecast_steps_weights needs one weight per forecast step'
+        self.engine = ForecastChainEngine(
+            forecast_steps=config.forecast_steps, weights=w,
+            max_batch=config.batch_size, seq_len=seq_len, n_inputs=n_inputs, n_outputs=n_outputs,
+            num_hidden=config.num_hidden, num_layers=config.num_layers, target_idx=target_idx,
+            train=bool(config.train), precision=precision, optimizer=config.optimizer,
+            dropout=config.dropout, recurrent_dropout=config.recurrent_dropout, target_lambda=config.target_lambda,
+            rnn_lambda=config.rnn_lambda, max_grad_norm=config.max_grad_norm, max_norm=float(config.max_norm),
+            sgd_momentum=config.sgd_momentum, seed=config.seed, forward_only=not config.train,
+            rnn_cell=config.rnn_cell)
+        specs = [(n, s) for (_, n, s, _, tr) in self.engine.specs if tr]
+        self.engine.set_weights(Initializer(config).initial_weights(specs))
+        self.trainable_variables = [_Variable(self, i, n, s) for i, (n, s) in enumerate(specs)]
+        self._calls = 0
+
+    def __call__(self, inp, training=None):
+        self._calls += 1
+        return self.engine.forward(self._to_device(inp), step=self._calls)
+
+    def predict_device(self, inp):
+        import torch
+        x = self._to_device(inp)
+        B, mb = x.shape[0], self.engine.cfg.max_batch
+        self._calls += 1
+        outs = [self.engine.forward(x[s:s + mb].contiguous(), step=self._calls, row0=s) for s in range(0, B, mb)]
+        S = self.engine.S
+        return [outs[0][k] if len(outs) == 1 else torch.cat([o[k] for o in outs], dim=0) for k in range(S)]
+
+    def predict(self, inp, batch_size=None):
+        """model.predict(inp) (train.py:289, predict.py:129): list of S ndarrays [B,T,O]."""
+        return [p.cpu().numpy() for p in self.predict_device(inp)]
+
+    def train_step(self, inp, targets, lr, iteration):
+        """Train._train_step_point (train.py:178-199) over the S-output graph; device tensor {loss, mse}."""
+        assert isinstance(targets, (list, tuple)), 'targets must be the list of forecast_steps targets (train.py:188)'
+        return self.engine.train_step(self._to_device(inp), [self._to_device(t) for t in targets], iteration, lr)
+
+    def reset_states(self):
+        return None
+
+    def count_params(self):
+        return self.engine.n_total
+
+    def summary(self):
+        lines = ['Model: "RNNPointEstimate" (native sm_100a, forecast_steps=%d, precision=%s)' % (self.engine.S,
+                                                                                                self.engine.precision),
+                 '%-44s %-16s %10s' % ('Variable', 'Shape', 'Param #'), '=' * 72]
+        for _, name, shape, _, tr in self.engine.specs:
+            lines.append('%-44s %-16s %10d%s' % (name, str(tuple(shape)), int(np.prod(shape)), '' if tr else '  (non-trainable)'))
+        lines += ['=' * 72, 'Total params: %d' % self.engine.n_total, 'Trainable params: %d' % self.engine.n_trainable]
+        return '\n'.join(lines)
+
+    def save_weights(self, prefix):
+        from .... import tf_checkpoint
+        arrs = self.engine.named_arrays()
+        os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+        with open(prefix + '.lfmq.npz', 'wb') as fh:
+            np.savez(fh, **arrs)
+        tf_checkpoint.write_keras_checkpoint(prefix, arrs, construction_order=True)
+
+    def load_weights(self, prefix):
+        from .... import tf_checkpoint
+        names = [n for _, n, _, _, _ in self.engine.specs]
+        if os.path.isfile(prefix + '.lfmq.npz'):
+            data = np.load(prefix + '.lfmq.npz')
+        elif os.path.isfile(prefix + '.index'):
+            data = tf_checkpoint.read_keras_checkpoint(prefix, names, {n: tuple(s_) for _, n, s_, _, _ in self.engine.specs},
+                                                       construction_order=True)
+        else:
+            raise FileNotFoundError('no checkpoint at %s (.lfmq.npz or TensorFlow-format .index)' % prefix)
+        self.engine.load_named(lambda name: data[name])
+
+    def get_weights(self):
+        return self.engine.get_weights(trainable_only=False)
+
+
 class NativeForecaster(object):
     """Keras-subset model object: __call__, predict, trainable_variables, save/load_weights,
     reset_states, summary -- plus ``train_step`` (the fused native Train._train_step_point)."""
@@ -36,7 +130,7 @@ class NativeForecaster(object):
         if config.rnn_cell not in ('lstm', 'gru'):
             raise NotImplementedError                    # rnn_point_estimate.py:101-102
         if config.forecast_steps != 1:
-            raise NotImplementedError('forecast_steps > 1 is a "next" row of the scope table')
+            raise NotImplementedError('forecast_steps > 1 is built by NativeChainForecaster (point estimates only)')
         self.engine = ForecasterEngine(
             max_batch=config.batch_size, seq_len=seq_len, n_inputs=n_inputs, n_outputs=n_outputs,
             num_hidden=config.num_hidden, num_layers=config.num_layers, target_idx=target_idx,
@@ -164,6 +258,9 @@ class NativeForecaster(object):
         self.engine.set_weights(weights[:n_tr], bn)
 
 
+NativeChainForecaster._to_device = NativeForecaster._to_device
+
+
 class RNNPointEstimate(BaseModelClass):
     """Builds the native recurrent forecaster with the architecture defined in the configs."""
 
@@ -182,4 +279,7 @@ class RNNPointEstimate(BaseModelClass):
         self.model = self._build_model()
 
     def _build_model(self):
+        if self.forecast_steps > 1:                      # reference :109-150
+            return NativeChainForecaster(self.config, self.seq_len, self.n_inputs, self.n_outputs,
+                                         self.dataset.target_index)
         return NativeForecaster(self.config, self.seq_len, self.n_inputs, self.n_outputs, self.dataset.target_index)

@@ -35,6 +35,8 @@ class Train(object):
         from .. import dp as _dp
         self.rank, self.world = _dp.init_from_env()
         self.model = Model(self.config, self.dataset).get_model()
+        if self.world > 1 and self.config.forecast_steps > 1:
+            raise NotImplementedError('data parallelism is built for forecast_steps = 1')
         if self.world > 1:                       # one set of initial weights: rank 0's
             import torch
             import torch.distributed as dist
@@ -216,14 +218,21 @@ class Train(object):
         if not self._valid_batches:
             return None, float('nan'), float('nan')
         preds = [self.model.predict_device(cur_batch[0]) for cur_batch in self._valid_batches]
-        pred_all = torch.cat(preds, dim=0)
-        target_all = torch.cat([cur_batch[1] for cur_batch in self._valid_batches], dim=0)
+        targets = [cur_batch[1] for cur_batch in self._valid_batches]
+        if self.config.forecast_steps == 1:              # preds, targets need to be lists (train.py:291-294)
+            preds = [[p] for p in preds]
+            targets = [[t] for t in targets]
+        assert all(isinstance(t, (list, tuple)) for t in targets), \
+            'forecast_steps > 1 needs a list of forecast_steps targets per batch (train.py:296-299)'
         scale, center = self._scaling_dev()
         eng = self.model.engine
-        pred_unscaled = eng.unscale(pred_all, scale, center, self.config.log_squasher)
-        target_unscaled = eng.unscale(target_all, scale, center, self.config.log_squasher)
-        _, valid_mse = self.losses.weight_adjusted_mse([target_all], [pred_all], True)
-        _, valid_mse_fcst = self.losses.weight_adjusted_mse([target_unscaled], [pred_unscaled], True)
+        S = self.config.forecast_steps
+        pred_all = [torch.cat([p[i] for p in preds], dim=0) for i in range(S)]            # train.py:316-320
+        target_all = [torch.cat([t[i] for t in targets], dim=0) for i in range(S)]
+        pred_unscaled = [eng.unscale(p, scale, center, self.config.log_squasher) for p in pred_all]
+        target_unscaled = [eng.unscale(t, scale, center, self.config.log_squasher) for t in target_all]
+        _, valid_mse = self.losses.weight_adjusted_mse(target_all, pred_all, True)
+        _, valid_mse_fcst = self.losses.weight_adjusted_mse(target_unscaled, pred_unscaled, True)
         both = torch.stack([valid_mse._t, valid_mse_fcst._t]).cpu().numpy()      # the epoch's single D2H
         return None, float(both[0]), float(both[1])
 

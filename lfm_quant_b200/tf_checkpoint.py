@@ -394,7 +394,7 @@ def write_bundle(prefix, tensors, string_tensors=None):
 
 
 # ---- Keras naming for the reference's layer stack -------------------------------------------------------------------------
-def keras_keys(spec_names):
+def keras_keys(spec_names, construction_order=False):
     """Maps this package's variable names (lfmq_param_spec: ``lstm_1/kernel``, ``batch_normalization/gamma``,
     ``OUTPUT_1/kernel`` ...) to the keys Keras' object-based save_weights uses.  Layers with weights are numbered in
     construction order (rnn_point_estimate.py:76-107): recurrent layer, its BatchNormalization, the next recurrent layer
@@ -412,7 +412,10 @@ def keras_keys(spec_names):
             k = 0 if layer == 'batch_normalization' else int(layer.split('_')[-1])
             return (0, 2 * k + 1)
         return (1, order.index(layer))
-    layers = sorted(order, key=rank)
+    # forecast_steps > 1 (rnn_point_estimate.py:109-150) interleaves heads and extra recurrent layers: the names then
+    # arrive in construction order already (trunk, OUTPUT_1, lstm_{L+1}, its BatchNormalization, OUTPUT_2, ...).
+    # NOTE: that numbering is not pinned against a TensorFlow-written multi-step checkpoint (none exists upstream).
+    layers = list(order) if construction_order else sorted(order, key=rank)
     out = {}
     for n in spec_names:
         layer, var = n.split('/')
@@ -452,9 +455,9 @@ def _object_graph(keys_by_name, keras_var_names):
     return msg
 
 
-def write_keras_checkpoint(prefix, arrays):
+def write_keras_checkpoint(prefix, arrays, construction_order=False):
     """arrays: {this package's variable name: ndarray} -> TF-format checkpoint the reference's load_weights addresses."""
-    keys = keras_keys(list(arrays))
+    keys = keras_keys(list(arrays), construction_order)
     full = {}
     for n in arrays:                                # Keras variable names: lstm_1/lstm_cell/kernel:0 etc.
         layer, var = n.split('/')
@@ -464,11 +467,11 @@ def write_keras_checkpoint(prefix, arrays):
                  {OBJECT_GRAPH_KEY: _object_graph(keys, full)})
 
 
-def read_keras_checkpoint(prefix, spec_names, shapes=None):
+def read_keras_checkpoint(prefix, spec_names, shapes=None, construction_order=False):
     """{this package's variable name: ndarray} from a TF-format checkpoint written by the reference (or by
     write_keras_checkpoint).  Raises KeyError naming the first variable the checkpoint does not hold."""
     bundle = read_bundle(prefix)
-    keys = keras_keys(list(spec_names))
+    keys = keras_keys(list(spec_names), construction_order)
     out = {}
     for n in spec_names:
         if keys[n] not in bundle:

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lfmq_abi_version() == N.ABI_VERSION == 3
+    assert lib.lfmq_abi_version() == N.ABI_VERSION == 4
 
 
 def test_struct_sizes_match_header_layout():
