@@ -1615,6 +1615,16 @@ constexpr bool DSMEM_X = LFMQ_BWD_DSMEM != 0;
 #endif
 // 1 = every pointwise warp signals the peers itself after its own export stores (no CTA-wide named barrier first)
 constexpr bool WARP_SIG = LFMQ_BWD_WARP_SIGNAL != 0 && !DSMEM_X;
+#ifndef LFMQ_BWD_EXPORT_BATCH
+#define LFMQ_BWD_EXPORT_BATCH 1
+#endif
+constexpr bool EXPORT_BATCH = LFMQ_BWD_EXPORT_BATCH != 0;
+#ifndef LFMQ_BWD_PX_BLOCKED
+#define LFMQ_BWD_PX_BLOCKED 1
+#endif
+// exchange scratch as [16-column block][row][16]: a warp's 256-bit export store is 1 KB contiguous (it was 32 separate
+// 32-byte pieces, one per 128-byte row), the receiver fetches its 16 KB slice with one 1-D bulk copy and reads it as is
+constexpr bool PX_BLOCKED = LFMQ_BWD_PX_BLOCKED != 0 && !DSMEM_X;
 constexpr bool LATE_C0 = LFMQ_BWD_LATE_C0 != 0;     // experiment: the first chunk's operands at the top of the step as well
 // Warp roles, by warpgroup (setmaxnreg moves registers between warpgroups): warps 0-3 pointwise set 0, warps 4-7 pointwise
 // set 1, warps 8-11 = producer, MMA issuer, dz store, idle.  The role warpgroup gives its registers up (72 each), the
@@ -1715,8 +1725,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           const int par = (t + 1) & 1;
           for (uint32_t d = 1; d < BWD_NC; ++d) {
             const uint32_t src = (rank + d) & 3;
-            tma_load_2d(smem + SB_R + (d - 1) * 16384, &tm_px, &bars->recv_full, 0,
-                        ((((tile * 2 + par) * 4 + (int)src) * 4 + (int)rank)) * 128);
+            if (PX_BLOCKED)
+              bulk_load_1d(smem + SB_R + (d - 1) * 16384,
+                           p.pexch + ((((long)(tile * 2 + par) * 4 + (int)src) * 4 + (int)rank)) * 128 * 64, 16384,
+                           &bars->recv_full);
+            else
+              tma_load_2d(smem + SB_R + (d - 1) * 16384, &tm_px, &bars->recv_full, 0,
+                          ((((tile * 2 + par) * 4 + (int)src) * 4 + (int)rank)) * 128);
           }
         }
         __syncwarp();
@@ -1887,10 +1902,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             for (int j = 0; j < 16; ++j) rec[j] = __uint_as_float(vr[j]);
 #pragma unroll
             for (int d = 0; d < 3 && has_rec; ++d) {
-              const uint8_t* rs = smem + SB_R + d * 16384 + m * 128;
+              const uint8_t* rs = smem + SB_R + d * 16384 + (PX_BLOCKED ? (jb * 128 + m) * 32 : m * 128);
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
-                const uint4 v = *reinterpret_cast<const uint4*>(rs + (((2 * jb + h2) ^ sw) << 4));
+                const uint4 v = *reinterpret_cast<const uint4*>(rs + (PX_BLOCKED ? h2 << 4 : ((2 * jb + h2) ^ sw) << 4));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1992,11 +2007,36 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             }
           }
 #pragma unroll
-          for (uint32_t d = 1; d < BWD_NC && !DSMEM_X; ++d) {
+          if (!DSMEM_X && EXPORT_BATCH) {
+            // all six 16-column pieces requested from TMEM before the first is waited for: one tcgen05.ld latency
+            // instead of six (the 216-register budget of the pointwise warpgroups has room for the 96 values)
+            uint32_t v[6][16];
+#pragma unroll
+            for (uint32_t d = 1; d < BWD_NC; ++d)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+                tmem_ld_32x32b_x16(acc + ((rank + d) & 3) * 64 + set * 32 + hh * 16, v[(d - 1) * 2 + hh]);
+            tmem_ld_wait();
+#pragma unroll
+            for (uint32_t d = 1; d < BWD_NC; ++d) {
+              const uint32_t dst = (rank + d) & 3;
+              __nv_bfloat16* slice = p.pexch + (((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 * 64;
+              __nv_bfloat16* out = PX_BLOCKED ? slice + ((long)(set * 2) * 128 + m) * 16 : slice + m * 64 + set * 32;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t* vv = v[(d - 1) * 2 + hh];
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(__uint_as_float(vv[2 * e]), __uint_as_float(vv[2 * e + 1]));
+                st_global_v8(out + hh * (PX_BLOCKED ? 128 * 16 : 16), pk);
+              }
+            }
+          }
+#pragma unroll
+          for (uint32_t d = 1; d < BWD_NC && !DSMEM_X && !EXPORT_BATCH; ++d) {
             const uint32_t dst = (rank + d) & 3;
-            __nv_bfloat16* out = p.pexch + ((((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 + m) * 64 + set * 32;
-            // 16 columns at a time: the next step's operands (112 registers) are live across this section, and the
-            // 32-column form pushed the kernel over its 168-register cap into local-memory spills
+            __nv_bfloat16* slice = p.pexch + (((long)(tile * 2 + par) * 4 + rank) * 4 + dst) * 128 * 64;
+            __nv_bfloat16* out = PX_BLOCKED ? slice + ((long)(set * 2) * 128 + m) * 16 : slice + m * 64 + set * 32;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t v[16];
@@ -2005,7 +2045,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
               uint32_t pk[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-              st_global_v8(out + hh * 16, pk);
+              st_global_v8(out + hh * (PX_BLOCKED ? 128 * 16 : 16), pk);
             }
           }
           tcgen05_fence_before();
