@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LFMQ_ABI_VERSION 4   /* 3: LFMQ_PREC_BF16X3, general tensor-core path; 4: lfmq_chain_* (forecast_steps > 1) */
+#define LFMQ_ABI_VERSION 4   /* 3: LFMQ_PREC_BF16X3, general tensor-core path; 4: lfmq_chain_* (forecast_steps > 1), lfmq_window_index */
 
 enum { LFMQ_OK = 0, LFMQ_ERR_ARG = 1, LFMQ_ERR_CUDA = 2, LFMQ_ERR_UNSUPPORTED = 3, LFMQ_ERR_WORKSPACE = 4 };
 enum { LFMQ_OPT_ADADELTA = 0, LFMQ_OPT_ADAM = 1, LFMQ_OPT_RMSPROP = 2, LFMQ_OPT_SGD = 3 };
@@ -198,6 +198,32 @@ typedef struct lfmq_gather_args {
   double* seq_norm;
 } lfmq_gather_args;
 int32_t lfmq_gather_batch(const lfmq_gather_args* args, void* stream);
+
+/* Dataset._create_tf_dataset + _append_sequence_data (data_processing.py:170-305) on the device: the window index
+ * triples (start, end, pad) of every table row that yields a window, in row order.
+ *   key [n] int32: any code with key[i] == key[j] <=> same gvkey (rows of one company are consecutive, :203-219)
+ *   active [n] u8 (:211); date [n] int32 in any order-preserving encoding (yyyymmdd), compared with start_date,
+ *   end_date and last_train_date = end_date - stride months (:221-234); train selects the training rule (:221-225:
+ *   the target row forecast_n rows ahead must belong to the same key) or the prediction rule (:231-234)
+ *   min_unrollings / max_unrollings / stride / forecast_n as the flags of that name (:263-279)
+ * Outputs (device): inp_idx, tar_idx int32 [cap][3], rows int32 [cap] (table row of each window), count int32 [1]
+ * (the number of windows; entries beyond cap are dropped -- size cap = n to be safe).
+ * work: device ints, 4 * ceil(n / 1024) + n. */
+typedef struct lfmq_window_index_args {
+  int32_t struct_size;
+  int32_t n, train, stride, forecast_n, min_unrollings, max_unrollings;
+  int32_t start_date, end_date, last_train_date;
+  int32_t cap;
+  const int32_t* key;
+  const uint8_t* active;
+  const int32_t* date;
+  int32_t* inp_idx;
+  int32_t* tar_idx;
+  int32_t* rows;
+  int32_t* count;
+  int32_t* work;
+} lfmq_window_index_args;
+int32_t lfmq_window_index(const lfmq_window_index_args* args, void* stream);
 
 /* Train._unscale_preds (train.py:420-432) on the device, for the validation pass (train.py:268-336) without a host
  * round trip: out[r][k] = reverse_log_squasher(in[r][k] * scale[k] + center[k]) (data_processing.py:611-619), fp64

@@ -37,6 +37,14 @@ class LfmqGatherArgs(C.Structure):
                 ('x', C.c_void_p), ('y', C.c_void_p), ('seq_norm', C.c_void_p)]
 
 
+class LfmqWindowIndexArgs(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('n', C.c_int32), ('train', C.c_int32), ('stride', C.c_int32),
+                ('forecast_n', C.c_int32), ('min_unrollings', C.c_int32), ('max_unrollings', C.c_int32),
+                ('start_date', C.c_int32), ('end_date', C.c_int32), ('last_train_date', C.c_int32), ('cap', C.c_int32),
+                ('key', C.c_void_p), ('active', C.c_void_p), ('date', C.c_void_p), ('inp_idx', C.c_void_p),
+                ('tar_idx', C.c_void_p), ('rows', C.c_void_p), ('count', C.c_void_p), ('work', C.c_void_p)]
+
+
 # every symbol include/lfmq.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -65,6 +73,7 @@ SYMBOLS = {
     'lfmq_chain_loss': (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P]),
     'lfmq_chain_backward': (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),
     'lfmq_chain_apply': (C.c_int32, [_P, C.c_int32, C.c_float, C.c_int64, _P]),
+    'lfmq_window_index': (C.c_int32, [C.POINTER(LfmqWindowIndexArgs), _P]),
     'lfmq_gather_batch': (C.c_int32, [C.POINTER(LfmqGatherArgs), _P]),
     'lfmq_unscale': (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P]),
     'lfmq_launch_count': (C.c_int64, []),

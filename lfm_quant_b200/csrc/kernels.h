@@ -73,6 +73,17 @@ struct GatherArgs {
   double* seq_norm;
 };
 int gather_batch(cudaStream_t s, const GatherArgs& a);
+
+// window index on the device (data_processing.py:170-305); work: 4 * ceil(n / 1024) + n ints
+struct WindowIndexArgs {
+  int n, train, stride, forecast_n, min_steps, max_steps;
+  int32_t start_date, end_date, last_train_date;
+  const int32_t* key;
+  const uint8_t* active;
+  const int32_t* date;
+};
+int window_index(cudaStream_t s, const WindowIndexArgs& a, int cap, int32_t* inp, int32_t* tar, int32_t* rows,
+                 int32_t* count, int* work);
 int unscale(cudaStream_t s, const float* in, float* out, long n_rows, int O, const double* scale, const double* center,
             int log_squasher);
 

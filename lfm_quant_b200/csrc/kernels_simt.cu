@@ -463,6 +463,134 @@ int add_bias_rows(cudaStream_t s, long rows, int N, float* C, const float* bias)
   return 0;
 }
 
+// ---- window index on the device (data_processing.py:170-305: _create_tf_dataset + _append_sequence_data) -------------
+// One thread per table row.  cur_len[i] = i - (start of the row's key run) + 1 (:218-219,227) comes from an inclusive
+// max-scan of (key[i] != key[i-1] ? i : 0); the rows that yield a window (:221-234) are compacted in row order by an
+// exclusive sum-scan of their flags.  Both scans: per-block scan + one block over the block aggregates.
+constexpr int WI_THREADS = 1024;
+
+template <bool MAX>
+__device__ __forceinline__ int wi_block_scan(int v, int* total) {      // inclusive scan over the block's 1024 threads
+  __shared__ int warp_tot[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = MAX ? max(v, u) : v + u;
+  }
+  __syncthreads();                        // warp_tot may still be read by the previous call
+  if (lane == 31) warp_tot[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t = MAX ? max(t, u) : t + u;
+    }
+    warp_tot[lane] = t;
+  }
+  __syncthreads();
+  if (w > 0) v = MAX ? max(v, warp_tot[w - 1]) : v + warp_tot[w - 1];
+  if (total) *total = warp_tot[31];
+  return v;
+}
+
+// pass 1: block aggregate of the run-start candidates
+__global__ void __launch_bounds__(WI_THREADS) wi_runstart_agg_kernel(int n, const int32_t* __restrict__ key,
+                                                                     int* __restrict__ blk_max) {
+  const int i = blockIdx.x * WI_THREADS + threadIdx.x;
+  int v = 0;
+  if (i < n && i > 0 && key[i] != key[i - 1]) v = i;
+  int tot;
+  wi_block_scan<true>(v, &tot);
+  if (threadIdx.x == 0) blk_max[blockIdx.x] = tot;
+}
+
+// one block: exclusive scan of the nb block aggregates (element i combines in[0..i-1]); total (nullable) = all of them.
+// Thread k of a chunk loads in[i-1]: the inclusive scan of the shifted input is the exclusive scan.
+template <bool MAX>
+__global__ void __launch_bounds__(WI_THREADS) wi_scan_aggs_kernel(int nb, const int* __restrict__ in,
+                                                                  int* __restrict__ out_excl, int* __restrict__ total) {
+  int carry = 0;
+  for (int base = 0; base <= nb; base += WI_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = (i >= 1 && i <= nb) ? in[i - 1] : 0;
+    int tot;
+    const int inc = wi_block_scan<MAX>(v, &tot);
+    if (i < nb) out_excl[i] = MAX ? max(inc, carry) : inc + carry;
+    carry = MAX ? max(carry, tot) : carry + tot;
+  }
+  if (total && threadIdx.x == 0) *total = carry;
+}
+
+// pass 2: cur_len, the window test, per-row (seq_len, flag) and the block's window count
+__global__ void __launch_bounds__(WI_THREADS) wi_flags_kernel(WindowIndexArgs a, const int* __restrict__ blk_start_excl,
+                                                              int* __restrict__ seq_len_out, int* __restrict__ blk_cnt) {
+  const int i = blockIdx.x * WI_THREADS + threadIdx.x;
+  int v = 0;
+  if (i < a.n && i > 0 && a.key[i] != a.key[i - 1]) v = i;
+  int run_start = wi_block_scan<true>(v, nullptr);
+  run_start = max(run_start, blk_start_excl[blockIdx.x]);
+  int ok = 0, sl = 0;
+  if (i < a.n) {
+    const int cur_len = i - run_start + 1;
+    const int32_t d = a.date[i];
+    const bool same_tar = (i + a.forecast_n <= a.n - 1) && a.key[i + a.forecast_n] == a.key[i];       // :213-216
+    if (a.train)                                                                                          // :221-225
+      ok = cur_len >= a.min_steps && a.active[i] && d >= a.start_date && d <= a.last_train_date && same_tar;
+    else                                                                                                  // :231-234
+      ok = cur_len >= a.min_steps && a.active[i] && d >= a.start_date && d <= a.end_date;
+    sl = min(cur_len - (cur_len - 1) % a.stride, a.max_steps);                                            // :263
+    seq_len_out[i] = ok ? sl : 0;
+  }
+  int tot;
+  wi_block_scan<false>(ok, &tot);
+  if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
+}
+
+// pass 3: compaction in row order
+__global__ void __launch_bounds__(WI_THREADS) wi_scatter_kernel(WindowIndexArgs a, const int* __restrict__ seq_len_in,
+                                                                const int* __restrict__ blk_off, int cap,
+                                                                int32_t* __restrict__ inp, int32_t* __restrict__ tar,
+                                                                int32_t* __restrict__ rows) {
+  const int i = blockIdx.x * WI_THREADS + threadIdx.x;
+  const int sl = i < a.n ? seq_len_in[i] : 0;
+  const int ok = sl > 0;
+  const int pos = wi_block_scan<false>(ok, nullptr) - ok + blk_off[blockIdx.x];
+  if (!ok || pos >= cap) return;
+  const int pad = (a.max_steps - sl) / a.stride;                                                          // :264
+  const bool same_tar = (i + a.forecast_n <= a.n - 1) && a.key[i + a.forecast_n] == a.key[i];
+  inp[3 * pos + 0] = i - sl + 1;
+  inp[3 * pos + 1] = i;
+  inp[3 * pos + 2] = pad;
+  tar[3 * pos + 0] = i - sl + 1 + a.forecast_n;                                                           // :270-279
+  tar[3 * pos + 1] = same_tar ? i + a.forecast_n : i;
+  tar[3 * pos + 2] = pad;
+  rows[pos] = i;
+}
+
+int window_index(cudaStream_t s, const WindowIndexArgs& a, int cap, int32_t* inp, int32_t* tar, int32_t* rows,
+                 int32_t* count, int* work) {
+  const int nb = cdiv(a.n, WI_THREADS);
+  int* blk_max = work;                  // [nb]
+  int* blk_start = work + nb;           // [nb]
+  int* blk_cnt = work + 2 * nb;         // [nb]
+  int* blk_off = work + 3 * nb;         // [nb]
+  int* seq_len = work + 4 * nb;         // [n]
+  wi_runstart_agg_kernel<<<nb, WI_THREADS, 0, s>>>(a.n, a.key, blk_max);
+  LFMQ_LAUNCH_CHECK();
+  wi_scan_aggs_kernel<true><<<1, WI_THREADS, 0, s>>>(nb, blk_max, blk_start, nullptr);
+  LFMQ_LAUNCH_CHECK();
+  wi_flags_kernel<<<nb, WI_THREADS, 0, s>>>(a, blk_start, seq_len, blk_cnt);
+  LFMQ_LAUNCH_CHECK();
+  wi_scan_aggs_kernel<false><<<1, WI_THREADS, 0, s>>>(nb, blk_cnt, blk_off, count);
+  LFMQ_LAUNCH_CHECK();
+  wi_scatter_kernel<<<nb, WI_THREADS, 0, s>>>(a, seq_len, blk_off, cap, inp, tar, rows);
+  LFMQ_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- forecast_steps > 1: glue between the stages (rnn_point_estimate.py:109-124; model_base_class.py:18-51) ----
 // next[b, t, :] = prev[b, t + 1, :] for t < T-1 (Cropping1D((1,0)) of the concatenation), and the appended step
 // next[b, T-1, :] = [pred[b, T-1, 0:O], x0[b, T-1, O:F]] (latest prediction + the last AVAILABLE aux features).

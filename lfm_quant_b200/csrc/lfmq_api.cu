@@ -897,6 +897,29 @@ int32_t lfmq_profile_read(lfmq_handle h, int32_t region, float* total_ms, int32_
   return LFMQ_OK;
 }
 
+int32_t lfmq_window_index(const lfmq_window_index_args* a, void* stream) {
+  if (!a || a->struct_size != (int32_t)sizeof(lfmq_window_index_args)) {
+    LFMQ_SET_ERR("lfmq_window_index_args: struct_size mismatch");
+    return LFMQ_ERR_ARG;
+  }
+  if (!a->key || !a->active || !a->date || !a->inp_idx || !a->tar_idx || !a->rows || !a->count || !a->work) {
+    LFMQ_SET_ERR("lfmq_window_index: null pointer");
+    return LFMQ_ERR_ARG;
+  }
+  if (a->n <= 0 || a->cap <= 0 || a->stride <= 0 || a->forecast_n < 0 || a->min_unrollings <= 0 ||
+      a->max_unrollings < a->min_unrollings) {
+    LFMQ_SET_ERR("lfmq_window_index: bad dimensions");
+    return LFMQ_ERR_ARG;
+  }
+  WindowIndexArgs w;
+  w.n = a->n; w.train = a->train; w.stride = a->stride; w.forecast_n = a->forecast_n;
+  w.min_steps = a->stride * (a->min_unrollings - 1) + 1;        // data_processing.py:206-207
+  w.max_steps = a->stride * (a->max_unrollings - 1) + 1;
+  w.start_date = a->start_date; w.end_date = a->end_date; w.last_train_date = a->last_train_date;
+  w.key = a->key; w.active = a->active; w.date = a->date;
+  return window_index((cudaStream_t)stream, w, a->cap, a->inp_idx, a->tar_idx, a->rows, a->count, a->work);
+}
+
 int32_t lfmq_gather_batch(const lfmq_gather_args* a, void* stream) {
   if (!a || a->struct_size != (int32_t)sizeof(lfmq_gather_args)) {
     LFMQ_SET_ERR("lfmq_gather_args: struct_size mismatch");

@@ -145,7 +145,12 @@ struct GSmem {
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
   // one launch = one wave for the recurrence steps (<= 148 tiles: one CTA per SM, deep ring); the multi-wave GEMMs keep
   // two CTAs per SM
-  static constexpr int CTAS_PER_SM = (MT == 1 && (BN >= 256 || EPI == 2 || EPI == 4)) ? 2 : 1;      // (2 = EPI_STORE, 4 = EPI_HEAD)
+#ifndef LFMQ_GEN_BWD_2CTA
+#define LFMQ_GEN_BWD_2CTA 0
+#endif
+  // (LFMQ_GEN_BWD_2CTA: experiment -- two 64-unit backward CTAs per SM so that one's epilogue can overlap the other's mainloop)
+  static constexpr int CTAS_PER_SM =
+      (MT == 1 && (BN >= 256 || EPI == 2 || EPI == 4 || (LFMQ_GEN_BWD_2CTA && EPI == 1 && BN == 64))) ? 2 : 1;      // (2 = EPI_STORE, 4 = EPI_HEAD)
   static constexpr int NS = (int)((CTAS_PER_SM == 2 ? 98304u : 196608u) / STAGE);
   static constexpr uint32_t BARS = NS * STAGE;
   static constexpr uint32_t TOTAL = BARS + 256 + 1024;    // + alignment slack
@@ -237,7 +242,11 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
       const long hoff = ((long)(p.t + 1) * p.Bp + b) * p.H + j0;
       uint32_t w[8];
       pack16(hv, w);
+#ifndef LFMQ_EXP_NO_H       // timing experiment only
       st_global_v8(p.hseq + hoff, w);
+#else
+      if (w[0] == 0x12345678u && w[1] == 0x9abcdef0u) st_global_v8(p.hseq + hoff, w);
+#endif
       if (p.hseq_lo) {        // bf16x3: h = hi + lo with |lo| <= 2^-9 |h|
         float lo[16];
 #pragma unroll
@@ -371,10 +380,14 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
 #pragma unroll
     for (int e = 0; e < 8; ++e) zi[e] = zf[e] = zg[e] = zo[e] = 0u;
   }
+#ifndef LFMQ_EXP_NO_DZ      // timing experiment only (wrong results): how much of the epilogue the row-major stores cost
   st_global_v8(dzr, zi);
   st_global_v8(dzr + (long)p.H, zf);
   st_global_v8(dzr + 2L * p.H, zg);
   st_global_v8(dzr + 3L * p.H, zo);
+#else
+  if (zi[0] == 0x12345678u && zf[1] == 0x9abcdef0u && zg[2] == 0x1u && zo[3] == 0x2u) st_global_v8(dzr, zi);
+#endif
 }
 
 // `part` of `nparts` warps of this lane quadrant: blocks part, part + nparts, ...
@@ -1356,6 +1369,10 @@ void gen_layout(GenState& st, const lfmq_config& c, const GenLayerOff* lo, int64
   m.train_ws = !c.forward_only;
   m.oWo = oWo; m.obo = obo;
   m.BNU = (m.H % 128 == 0) ? 128 : 64;
+  {   // experiment (LFMQ_GEN_BWD_BN64=1): 64-unit backward tiles also when H % 128 == 0 -> twice the CTAs per step
+    static const char* e = getenv("LFMQ_GEN_BWD_BN64");
+    if (e && atoi(e)) m.BNU = 64;
+  }
   const size_t T = m.T, Bp = m.Bp, H = m.H;
   const bool rec = (c.train && c.recurrent_dropout > 0.f);
   m.layers.assign(m.L, GenLayer{});

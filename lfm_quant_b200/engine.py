@@ -446,3 +446,34 @@ def gather_batch(table, inp_idx, tar_idx, *, seq_len, stride, inp_cols, fin_cols
     a.x, a.y, a.seq_norm = x.data_ptr(), y.data_ptr(), sn.data_ptr()
     N.check(lib.lfmq_gather_batch(C.byref(a), _stream()))
     return x, y, sn
+
+
+def window_index(key_codes, active, dates, *, train, stride, forecast_n, min_unrollings, max_unrollings, start_date,
+                 end_date, last_train_date):
+    """Device window index: Dataset._create_tf_dataset + _append_sequence_data (scripts/data_processing.py:170-305).
+
+    key_codes int32 [n] (equal code <=> same gvkey), active uint8 [n], dates int32 [n] (yyyymmdd) -- CUDA tensors;
+    the three date bounds are ints in the same encoding.  Returns (inp_idx int32 [N,3], tar_idx int32 [N,3],
+    rows int32 [N]) as CUDA tensors, N = number of rows that yield a window, in row order.
+    """
+    lib = N.load()
+    n = key_codes.numel()
+    dev = key_codes.device
+    for name, t, dt in (('key', key_codes, torch.int32), ('active', active, torch.uint8), ('date', dates, torch.int32)):
+        assert t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() == n, name
+    inp = torch.empty(n, 3, dtype=torch.int32, device=dev)
+    tar = torch.empty(n, 3, dtype=torch.int32, device=dev)
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = torch.empty(4 * ((n + 1023) // 1024) + n, dtype=torch.int32, device=dev)
+    a = N.LfmqWindowIndexArgs()
+    a.struct_size = C.sizeof(N.LfmqWindowIndexArgs)
+    a.n, a.train, a.stride, a.forecast_n = n, int(bool(train)), int(stride), int(forecast_n)
+    a.min_unrollings, a.max_unrollings = int(min_unrollings), int(max_unrollings)
+    a.start_date, a.end_date, a.last_train_date, a.cap = int(start_date), int(end_date), int(last_train_date), n
+    a.key, a.active, a.date = key_codes.data_ptr(), active.data_ptr(), dates.data_ptr()
+    a.inp_idx, a.tar_idx, a.rows, a.count, a.work = (inp.data_ptr(), tar.data_ptr(), rows.data_ptr(), count.data_ptr(),
+                                                     work.data_ptr())
+    N.check(lib.lfmq_window_index(C.byref(a), _stream()))
+    k = int(count.item())
+    return inp[:k], tar[:k], rows[:k]

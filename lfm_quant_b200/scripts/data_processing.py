@@ -186,19 +186,23 @@ class Dataset(object):
         if fn < n:
             tar_key[:n - fn] = keys[fn:]                                # :213-216
         dates = pd.DatetimeIndex(self._dates)
-        if cfg.train:                                                   # :221-225
-            last = self.end_date - pd.DateOffset(months=stride)
-            ok = (cur_len >= min_steps) & active & (dates >= self.start_date) & (dates <= last) & (tar_key == keys)
-        else:                                                           # :231-234
-            ok = (cur_len >= min_steps) & active & (dates >= self.start_date) & (dates <= self.end_date)
-        sel = idx[ok]
-        cl = cur_len[sel]
-        seq_len = np.minimum(cl - (cl - 1) % stride, max_steps)        # :263
-        pad = (max_steps - seq_len) // stride                           # :264
-        inp = np.stack([sel - seq_len + 1, sel, pad], axis=1).astype(np.int32)
-        same = tar_key[sel] == keys[sel]
-        tar_end = np.where(same, sel + fn, sel)                         # :270-279
-        tar = np.stack([sel - seq_len + 1 + fn, tar_end, pad], axis=1).astype(np.int32)
+        last = self.end_date - pd.DateOffset(months=stride)             # :222
+        dev_idx = self._create_index_device(keys, active, dates, last) if self._use_device_index() else None
+        if dev_idx is not None:
+            inp, tar, sel = dev_idx
+        else:
+            if cfg.train:                                                   # :221-225
+                ok = (cur_len >= min_steps) & active & (dates >= self.start_date) & (dates <= last) & (tar_key == keys)
+            else:                                                           # :231-234
+                ok = (cur_len >= min_steps) & active & (dates >= self.start_date) & (dates <= self.end_date)
+            sel = idx[ok]
+            cl = cur_len[sel]
+            seq_len = np.minimum(cl - (cl - 1) % stride, max_steps)        # :263
+            pad = (max_steps - seq_len) // stride                           # :264
+            inp = np.stack([sel - seq_len + 1, sel, pad], axis=1).astype(np.int32)
+            same = tar_key[sel] == keys[sel]
+            tar_end = np.where(same, sel + fn, sel)                         # :270-279
+            tar = np.stack([sel - seq_len + 1 + fn, tar_end, pad], axis=1).astype(np.int32)
         meta = np.stack([dates[sel].strftime('%Y%m%d').values.astype('S'), keys[sel].astype('S'),
                          tar_key[sel].astype('S')], axis=1)
         in_train = np.isin(keys[sel], np.asarray(self._train_gvkeys, dtype=keys.dtype))
@@ -213,6 +217,34 @@ class Dataset(object):
             if not np.all(in_test):
                 raise ValueError("Mismatch between gvkey category (train/valid/test set) and run type (train/ pred)")
             self._dataset['test_X'], self._dataset['test_Y'], self._meta['test'] = inp, tar, meta
+
+    @staticmethod
+    def _use_device_index():
+        """The window index is built by the CUDA kernels (lfmq_window_index) whenever a GPU is present; the vectorised
+        NumPy form above serves GPU-less tooling and the CPU tests (LFMQ_HOST_INDEX=1 forces it)."""
+        if os.environ.get('LFMQ_HOST_INDEX') == '1':
+            return False
+        try:
+            import torch
+            return torch.cuda.is_available()
+        except Exception:
+            return False
+
+    def _create_index_device(self, keys, active, dates, last_train_date):
+        """data_processing.py:170-305 on the device.  String keys become integer codes (equal code <=> equal gvkey), dates
+        yyyymmdd ints; the triples come back once, at start-up."""
+        import torch
+        from ..engine import window_index
+        cfg = self.config
+        codes = np.unique(keys, return_inverse=True)[1].astype(np.int32)
+        ymd = (dates.year.values * 10000 + dates.month.values * 100 + dates.day.values).astype(np.int32)
+        as_int = lambda ts: int(pd.Timestamp(ts).strftime('%Y%m%d'))
+        cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        inp, tar, rows = window_index(cu(codes), cu(active.astype(np.uint8)), cu(ymd), train=bool(cfg.train),
+                                      stride=cfg.stride, forecast_n=cfg.forecast_n, min_unrollings=cfg.min_unrollings,
+                                      max_unrollings=cfg.max_unrollings, start_date=as_int(self.start_date),
+                                      end_date=as_int(self.end_date), last_train_date=as_int(last_train_date))
+        return inp.cpu().numpy(), tar.cpu().numpy(), rows.cpu().numpy().astype(np.int64)
 
     # ---- the tf.data-like views (data_processing.py:451-474) ------------------------------------------
     @property
