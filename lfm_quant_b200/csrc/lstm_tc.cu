@@ -218,6 +218,15 @@ struct FwdParams {
 
 constexpr int FWD_EPI_WARPS = 8;                          // 4 TMEM lane quadrants x 2 column halves
 constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS);     // producer + MMA + epilogue = 320
+#ifndef LFMQ_FWD_TMA_PUBLISH
+#define LFMQ_FWD_TMA_PUBLISH 0
+#endif
+// Publishing h_t: 0 = a 32-byte STG per thread and chunk followed by a release fence over all of them; 1 = the CTA's
+// [128 x 64] slice staged in shared memory (in the A-operand buffer, which no MMA reads any more once the step's last
+// chunk is committed) and sent as ONE TMA store whose completion is awaited before the peers are signalled.  Measured
+// (profiles/r02_time_c31_fwd_tma_publish.txt): the awaited TMA store takes ~2.5 K cycles under the kernel's own store
+// traffic (580 alone, profiles/r02_micro_tma_store_c30.txt): fwd 0.262 -> 0.315 ms, predict 3.67 -> 4.42 ms.  Off.
+constexpr bool TMA_PUBLISH = LFMQ_FWD_TMA_PUBLISH != 0;
 constexpr uint32_t SM_U = 0;                 // 4 k-blocks x [256 x 128 B]
 constexpr uint32_t SM_W = 131072;            // [256 x 64 B]
 constexpr uint32_t SM_H0 = 147456;           // 4 k-blocks x [128 x 128 B]
@@ -239,7 +248,8 @@ struct FwdBars {
 template <bool SAVE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
     lstm_fwd_tc_kernel(FwdParams p, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_x,
-                       const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w) {
+                       const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w,
+                       const __grid_constant__ CUtensorMap tm_hst) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + SM_BARS);
@@ -375,6 +385,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         const long wblk0 = (((long)t * p.n_tiles_cap + tile_c) * 8 + 2 * (int)rank) * 4 + q;      // jb = 0; jb = 1: + 4
         __nv_bfloat16* grow = SAVE ? p.gates + (wblk0 * 8 * 32 + lane) * 16 + half * 512 : nullptr;   // + gate*1024 (+ jb*4*8*512)
         __nv_bfloat16* crow = SAVE ? p.cst + (wblk0 * 2 * 32 + lane) * 16 + half * 512 : nullptr;     // (+ jb*4*2*512)
+        uint32_t phs[2][8];
 #pragma unroll
         for (int jb = 0; jb < 2; ++jb) {
           const int c = half + 2 * jb;            // 16-unit chunk of this CTA's 64 hidden units
@@ -414,7 +425,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             pg[jj / 2] = pack_bf16x2(gv[0], gv[1]);
             po[jj / 2] = pack_bf16x2(ov[0], ov[1]);
           }
-          if (valid) st_global_v8(hrow, ph);   // one full 32-byte sector per store (STG.256)
+          if (TMA_PUBLISH) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) phs[jb][e] = ph[e];
+          } else if (valid) {
+            st_global_v8(hrow, ph);   // one full 32-byte sector per store (STG.256)
+          }
           if (SAVE) {
             // Saved gates / cell states are not needed by the h exchange: park them in the idle accumulator
             // buffer (TMEM) and write them to HBM after the publish, off the per-step critical path.
@@ -429,6 +445,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
             tmem_st_32x32b_x8(tst + 32, cu);
           }
         }
+        if (TMA_PUBLISH) {
+          // all MMAs of the step are complete once chunk 3 is committed: the A-operand buffer is free to stage h_t in
+          // (the peers' multicast of h_t lands there only after every CTA, this one included, has signalled)
+          if (half == 0) mbar_wait(&bars->acc_full[g & 1][3], (g >> 1) & 1);
+          uint8_t* srow = smem + SM_H0 + m * 128;
+#pragma unroll
+          for (int jb = 0; jb < 2; ++jb) {
+            const int ch = (half + 2 * jb) * 2;            // 16-byte chunk of the 128-byte row, 128B-swizzled by row
+            *reinterpret_cast<uint4*>(srow + (((ch) ^ (m & 7)) << 4)) = make_uint4(phs[jb][0], phs[jb][1], phs[jb][2], phs[jb][3]);
+            *reinterpret_cast<uint4*>(srow + (((ch + 1) ^ (m & 7)) << 4)) = make_uint4(phs[jb][4], phs[jb][5], phs[jb][6], phs[jb][7]);
+          }
+          fence_proxy_async_smem();
+        }
         if (SAVE) tmem_st_wait();
         tcgen05_fence_before();
         if (leader) FWD_TRACE(2, t, 1);
@@ -437,6 +466,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         // Readers acquire at cluster scope and cross into the async proxy before their TMA loads.
         named_bar_sync(1, 32 * FWD_EPI_WARPS);
         if (leader) FWD_TRACE(2, t, 4);
+        if (TMA_PUBLISH && warp == 2) {
+          if (lane == 0) {
+            tma_store_2d(&tm_hst, smem + SM_H0, (t + 1) * TC_XH_LD + (int)rank * TC_HS, tile_c * 128);   // rows >= B clipped
+            bulk_commit_group();
+            bulk_wait_group0();                 // the slice is in global memory before anybody is told
+          }
+          __syncwarp();
+        }
         if (warp == 2 && lane < TC_NC)
           mbar_arrive_cluster(mapa_u32(smem_u32(&bars->h_written), (uint32_t)lane));
         if (SAVE) {
@@ -1400,11 +1437,11 @@ static int tc_run_recurrence(TcState& st, const float* x, int B, bool save, cuda
   p.trace = want_trace ? trace_dev : nullptr;
   if (save) {
     if (int rc = launch_pdl(lstm_fwd_tc_kernel<true>, dim3(TC_NC * p.n_clusters), dim3(FWD_THREADS), FWD_SMEM, s, TC_NC, p,
-                            m.tm_h, m.tm_x, m.tm_u, m.tm_w))
+                            m.tm_h, m.tm_x, m.tm_u, m.tm_w, m.tm_h128))
       return rc;
   } else {
     if (int rc = launch_pdl(lstm_fwd_tc_kernel<false>, dim3(TC_NC * p.n_clusters), dim3(FWD_THREADS), FWD_SMEM, s, TC_NC, p,
-                            m.tm_h, m.tm_x, m.tm_u, m.tm_w))
+                            m.tm_h, m.tm_x, m.tm_u, m.tm_w, m.tm_h128))
       return rc;
   }
   if (want_trace) {
