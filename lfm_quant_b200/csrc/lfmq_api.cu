@@ -216,7 +216,9 @@ size_t layout(lfmq_handle_s* h, char* base) {
       if (lfmq::gen_supported(c, why, sizeof(why)))      // lfmq_create reports unsupported configurations (gen_init)
         lfmq::gen_layout(h->gen, c, lo.data(), h->oWo, h->obo, cv.base, cv.off);
     } else {
-      lfmq::tc_layout(h->tc, c, cv.base, cv.off);
+      const LayerBuf& lb = h->layers[0];
+      lfmq::tc_layout(h->tc, c, lfmq::TcParamOff{lb.oW, lb.oU, lb.ob, lb.ogamma, lb.obeta, lb.omean, lb.ovar, h->oWo, h->obo},
+                      cv.base, cv.off);
     }
   }
   return cv.off;

@@ -1280,7 +1280,7 @@ bool tc_shape_supported(const lfmq_config& c) {
   return tc_supported(c, why, sizeof(why));
 }
 
-void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
+void tc_layout(TcState& st, const lfmq_config& c, const TcParamOff& po, char* base, size_t& off) {
   if (c.precision != LFMQ_PREC_BF16) return;
   char why[128];
   if (!tc_supported(c, why, sizeof(why))) return;   // tc_init reports the error
@@ -1324,9 +1324,9 @@ void tc_layout(TcState& st, const lfmq_config& c, char* base, size_t& off) {
     m.dpred = nullptr; m.head_wpart = nullptr; m.pexch = nullptr; m.dpb = nullptr;
     m.wg_part_elems = 0;
   }
-  const int64_t I = c.n_inputs, O = c.n_outputs;
-  m.oW = 0; m.oU = I * 4 * H; m.ob = m.oU + H * 4 * H; m.ogamma = m.ob + 4 * H; m.obeta = m.ogamma + H;
-  m.oWo = m.obeta + H; m.obo = m.oWo + H * O; m.omean = m.obo + O; m.ovar = m.omean + H;
+  // offsets of the tensors in the flat parameter vector: the API layer's layout() is the one place that defines them
+  m.oW = po.oW; m.oU = po.oU; m.ob = po.ob; m.ogamma = po.ogamma; m.obeta = po.obeta;
+  m.oWo = po.oWo; m.obo = po.obo; m.omean = po.omean; m.ovar = po.ovar;
 }
 
 int tc_init(TcState& st, const lfmq_config& c) {

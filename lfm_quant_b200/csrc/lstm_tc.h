@@ -21,7 +21,9 @@ struct TcState {
 // recurrent dropout.
 bool tc_shape_supported(const lfmq_config& cfg);
 // Extends the workspace carve (base may be null when only sizing); `off` is advanced.
-void tc_layout(TcState& st, const lfmq_config& cfg, char* base, size_t& off);
+// offsets (in floats) of the single layer's tensors and the head in the flat parameter vector, from lfmq_api.cu:layout()
+struct TcParamOff { int64_t oW, oU, ob, ogamma, obeta, omean, ovar, oWo, obo; };
+void tc_layout(TcState& st, const lfmq_config& cfg, const TcParamOff& po, char* base, size_t& off);
 int tc_init(TcState& st, const lfmq_config& cfg);
 void tc_destroy(TcState& st);
 // preds may be null (training: the head is fused with the loss in tc_backward)

@@ -79,6 +79,7 @@ inline long cdivl(long a, long b) { return (a + b - 1) / b; }
 // =============================================================================================
 // warp 0: TMA producer, warp 1: MMA issuer, then 4 epilogue warps (one TMEM lane quadrant each) per 128-row M tile
 constexpr int G_MAXSEG = 6;
+constexpr int GBAR_N = 4096;       // step-barrier counters per handle: one per (persistent launch, row-tile group)
 
 // One K segment: n_kb 64-wide k-blocks, A columns from a_col0 of map a_map, B columns from b_col0 of map b_map.
 struct GSeg {
@@ -90,6 +91,14 @@ struct GArgs {
   int a_row_base;      // A row coordinate = a_row_base + 128 * (MT * blockIdx.x + rt_off)
   int b_row_base;      // B row coordinate = b_row_base + BN * blockIdx.y
   int rt_off;          // first 128-row tile of this launch (the batch can be split over two concurrent launches)
+  // Persistent mode (n_steps > 1): one launch runs n_steps consecutive time steps of a layer; step i works on A rows
+  // a_row_base + i * row_step with EpiParams::t + i * t_step.  The A operand of a CTA's next step is written by the
+  // gridDim.y CTAs of its own row-tile group (same blockIdx.x, all column tiles), so the steps are separated by one
+  // barrier PER ROW-TILE GROUP (a counter in global memory; every CTA of the launch resident at once), not by a launch
+  // boundary: CTA dispatch, barrier init, TMEM allocation and the wait for the whole previous grid to retire are paid
+  // once, and the row-tile groups drift apart instead of hitting HBM in lockstep.
+  int n_steps, row_step, t_step;
+  unsigned int* gbar;  // [gridDim.x], zeroed before the launch; counts the group's CTAs that have finished a step
 };
 
 #ifndef LFMQ_GEN_BWD_EW
@@ -521,7 +530,8 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BARS);
   uint64_t* empty = full + S::NS;
   uint64_t* acc_full = empty + S::NS;
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* tmem_free = acc_full + 1;               // persistent mode: the epilogue has drained the accumulator
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_free + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t TMEM_COLS = (BN * MT < 32) ? 32 : BN * MT;
   __shared__ float red_s[EPI == EPI_HEAD ? GH_PART : 1];
@@ -538,6 +548,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(tmem_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
@@ -554,40 +565,61 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   // operand and every state the epilogue reads were written by the previous step, so all threads wait here first.
   // launch_dependents comes AFTER the wait: when the next grid starts, this one has seen its predecessor complete, so
   // by induction only the immediate predecessor can still be running.
+  const int n_steps = g.n_steps > 1 ? g.n_steps : 1;
+  const unsigned int n_cta = gridDim.y;             // CTAs of this row-tile group
   if (warp == 0) {
     if (lane == 0) {
-      const int arow = g.a_row_base + 128 * (MT * (int)blockIdx.x + g.rt_off);
       const int brow = g.b_row_base + BN * (int)blockIdx.y;
-      {   // B operand of the first NS stages, before the dependency wait
-        int i = 0;
-        for (int sg = 0; sg < g.n_seg && i < S::NS; ++sg) {
-          const GSeg sgm = g.seg[sg];
-          const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
-          for (int kb = 0; kb < sgm.n_kb && i < S::NS; ++kb, ++i) {
-            mbar_arrive_expect_tx(&full[i], S::STAGE);
-            tma_load_2d(smem + i * S::STAGE + S::A_BYTES, mb, &full[i], sgm.b_col0 + kb * 64, brow);
+      for (int it = 0; it < n_steps; ++it) {
+        const int arow = g.a_row_base + it * g.row_step + 128 * (MT * (int)blockIdx.x + g.rt_off);
+        const int gi0 = it * total_kb;               // ring position of this step's first k-block
+        {   // B operand (weights) of the first NS stages of the step, before the dependency wait
+          int i = 0;
+          for (int sg = 0; sg < g.n_seg && i < S::NS; ++sg) {
+            const GSeg sgm = g.seg[sg];
+            const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
+            for (int kb = 0; kb < sgm.n_kb && i < S::NS; ++kb, ++i) {
+              const int gi = gi0 + i, st_ = gi % S::NS;
+              if (gi >= S::NS) mbar_wait(&empty[st_], ((gi / S::NS) - 1) & 1);
+              mbar_arrive_expect_tx(&full[st_], S::STAGE);
+              tma_load_2d(smem + st_ * S::STAGE + S::A_BYTES, mb, &full[st_], sgm.b_col0 + kb * 64, brow);
+            }
           }
         }
-      }
-      griddep_wait();
-      griddep_launch_dependents();
-      if (tr) ep.trace[1] = clock64();
-      int i = 0;
-      for (int sg = 0; sg < g.n_seg; ++sg) {
-        const GSeg sgm = g.seg[sg];
-        const CUtensorMap* ma = sgm.a_map == 0 ? &tmA0 : (sgm.a_map == 1 ? &tmA1 : (sgm.a_map == 2 ? &tmA2 : &tmA3));
-        const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
-        for (int kb = 0; kb < sgm.n_kb; ++kb, ++i) {
-          const int s = i % S::NS;
-          uint8_t* st = smem + s * S::STAGE;
-          if (i >= S::NS) {
-            mbar_wait(&empty[s], ((i / S::NS) - 1) & 1);
-            mbar_arrive_expect_tx(&full[s], S::STAGE);
-            tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
+        long long* trc = tr ? ep.trace + (long)it * g.t_step * 8 : nullptr;     // trace entries are [t][8]
+        if (trc && it > 0) trc[0] = clock64();
+        if (it == 0) {
+          griddep_wait();
+          griddep_launch_dependents();
+          if (trc) trc[1] = clock64();
+        } else {
+          // every CTA of the row-tile group has published step it-1 (generic-proxy stores, fenced before the count went up)
+          const long long spin0 = clock64();
+          while (ld_acquire_gpu(g.gbar + blockIdx.x) < (unsigned int)it * n_cta) {
+            // the host only takes this mode when all CTAs fit on the machine at once; should a peer never arrive
+            // (SMs held by somebody else), fail the launch after ~2 s instead of hanging the device
+            if (clock64() - spin0 > 4000000000LL) __trap();
           }
+          fence_proxy_async_global();
+          if (trc) trc[1] = clock64();
+        }
+        int i = 0;
+        for (int sg = 0; sg < g.n_seg; ++sg) {
+          const GSeg sgm = g.seg[sg];
+          const CUtensorMap* ma = sgm.a_map == 0 ? &tmA0 : (sgm.a_map == 1 ? &tmA1 : (sgm.a_map == 2 ? &tmA2 : &tmA3));
+          const CUtensorMap* mb = sgm.b_map == 0 ? &tmB0 : &tmB1;
+          for (int kb = 0; kb < sgm.n_kb; ++kb, ++i) {
+            const int gi = gi0 + i, s = gi % S::NS;
+            uint8_t* st = smem + s * S::STAGE;
+            if (i >= S::NS) {
+              mbar_wait(&empty[s], ((gi / S::NS) - 1) & 1);
+              mbar_arrive_expect_tx(&full[s], S::STAGE);
+              tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
+            }
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
+          }
         }
       }
     } else {
@@ -599,25 +631,31 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     griddep_launch_dependents();
     if (lane == 0 && total_kb > 0) {
       const uint32_t idesc = make_idesc_bf16(128, BN, false, false);
-      for (int i = 0; i < total_kb; ++i) {
-        const int s = i % S::NS;
-        mbar_wait(&full[s], (i / S::NS) & 1);
-        if (tr && i == 0) ep.trace[2] = clock64();
-        tcgen05_fence_after();
-        uint8_t* st = smem + s * S::STAGE;
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          const uint64_t db = make_smem_desc(smem_u32(st + S::A_BYTES) + k16 * 32, 0, 1024, LAYOUT_SW128);
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t da = make_smem_desc(smem_u32(st + mt * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
-            umma_f16(tmem + mt * BN, da, db, idesc, (i | k16) != 0);
-          }
+      for (int it = 0; it < n_steps; ++it) {
+        if (it > 0) {                          // the epilogue of the previous step has read the accumulator
+          mbar_wait(tmem_free, (it - 1) & 1);
+          tcgen05_fence_after();
         }
-        umma_commit(&empty[s]);
+        for (int i = 0; i < total_kb; ++i) {
+          const int gi = it * total_kb + i, s = gi % S::NS;
+          mbar_wait(&full[s], (gi / S::NS) & 1);
+          if (tr && i == 0) ep.trace[(long)it * g.t_step * 8 + 2] = clock64();
+          tcgen05_fence_after();
+          uint8_t* st = smem + s * S::STAGE;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t db = make_smem_desc(smem_u32(st + S::A_BYTES) + k16 * 32, 0, 1024, LAYOUT_SW128);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t da = make_smem_desc(smem_u32(st + mt * 16384) + k16 * 32, 0, 1024, LAYOUT_SW128);
+              umma_f16(tmem + mt * BN, da, db, idesc, (i | k16) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(acc_full);
+        if (tr) ep.trace[(long)it * g.t_step * 8 + 3] = clock64();
       }
-      umma_commit(acc_full);
-      if (tr) ep.trace[3] = clock64();
     }
   } else {
     griddep_wait();
@@ -630,22 +668,37 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     // (An L2 prefetch of the epilogue's saved-state operands issued here, during the mainloop, was measured and lost:
     //  it delays the operand ring -- first stage 1.5 K -> 3 K cycles -- and the epilogue, which is issue-bound, not
     //  HBM-bound, got no shorter: 2.97 -> 3.25 ms for the backward steps of BASELINE configs[2].)
-    if (total_kb > 0) {
-      mbar_wait(acc_full, 0);
-      tcgen05_fence_after();
-    }
     const uint32_t tacc = tmem + mt * BN;
-    if (tr && warp == 2 && lane == 0) ep.trace[4] = clock64();
-    if constexpr (EPI == EPI_HEAD) {
-      epi_head(ep, tacc, q, lane, red_s);
-    } else if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
-      if constexpr (EPI == EPI_FWD) epi_fwd<BN, false>(ep, tacc, q, lane, rt, bias_s);
-      if constexpr (EPI == EPI_FWD_ACC) epi_fwd<BN, true>(ep, tacc, q, lane, rt, bias_s);
-      if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt, part, S::EW);
-      if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
+    const int t_first = ep.t;
+    for (int it = 0; it < n_steps; ++it) {
+      ep.t = t_first + it * g.t_step;
+      if (total_kb > 0) {
+        mbar_wait(acc_full, it & 1);
+        tcgen05_fence_after();
+      }
+      if (tr && warp == 2 && lane == 0) ep.trace[(long)it * g.t_step * 8 + 4] = clock64();
+      if constexpr (EPI == EPI_HEAD) {
+        epi_head(ep, tacc, q, lane, red_s);
+      } else if ((long)rt * 128 < ep.Bp || EPI == EPI_STORE) {      // (a 256-row CTA tile may hang over the last row tile)
+        if constexpr (EPI == EPI_FWD) epi_fwd<BN, false>(ep, tacc, q, lane, rt, bias_s);
+        if constexpr (EPI == EPI_FWD_ACC) epi_fwd<BN, true>(ep, tacc, q, lane, rt, bias_s);
+        if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt, part, S::EW);
+        if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
+      }
+      if (tr && warp == 2 && lane == 0) ep.trace[(long)it * g.t_step * 8 + 5] = clock64();
+      if (n_steps > 1) {
+        // end of a step: all epilogue warps of the CTA are done with the accumulator and have issued their stores; one
+        // thread makes them visible device-wide and counts the CTA in (the pattern of a cooperative grid sync)
+        tcgen05_fence_before();
+        named_bar_sync(2, S::THREADS - 64);
+        if (warp == 2 && lane == 0) {
+          mbar_arrive(tmem_free);
+          __threadfence();
+          atomicAdd(g.gbar + blockIdx.x, 1u);
+        }
+      }
     }
     (void)part;
-    if (tr && warp == 2 && lane == 0) ep.trace[5] = clock64();
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -1313,6 +1366,9 @@ struct GenLayer {
 
 struct GenImpl {
   bool enabled = false;
+  unsigned int* gbar = nullptr;         // grid-barrier counters of the persistent step launches (GBAR_N, zeroed per call)
+  int gbar_next = 0;
+  int n_sms = 0;
   cudaStream_t side = nullptr;          // second half of the batch in the backward recurrence (see gen_backward)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   long long* trace = nullptr;      // LFMQ_TRACE_GEN=1: [phase 0 fwd / 1 bwd][layer][t][8] clock64 stamps of CTA (0,0)
@@ -1510,9 +1566,25 @@ int gen_init(GenState& st, const lfmq_config& c) {
     LFMQ_CUDA_CHECK(cudaMalloc(&m.trace, (size_t)2 * m.L * T * 8 * sizeof(long long)));
     LFMQ_CUDA_CHECK(cudaMemset(m.trace, 0, (size_t)2 * m.L * T * 8 * sizeof(long long)));
   }
+  LFMQ_CUDA_CHECK(cudaMalloc(&m.gbar, GBAR_N * sizeof(unsigned int)));
+  LFMQ_CUDA_CHECK(cudaMemset(m.gbar, 0, GBAR_N * sizeof(unsigned int)));
+  {
+    int dev = 0;
+    LFMQ_CUDA_CHECK(cudaGetDevice(&dev));
+    LFMQ_CUDA_CHECK(cudaDeviceGetAttribute(&m.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   m.enabled = true;
   st.weights_dirty = 1;
   return 0;
+}
+
+// Persistent step launches need every CTA of the launch(es) running at once (they meet at a grid-wide barrier).
+// `n_concurrent` launches of `ctas` CTAs each, `per_sm` resident CTAs of that instantiation per SM.  LFMQ_GEN_PERSIST=0
+// turns the mode off (one launch per time step, chained with programmatic dependent launch).
+static bool gen_can_persist(const GenImpl& m, long ctas, int n_concurrent, int per_sm, int n_steps) {
+  static const bool on = !(getenv("LFMQ_GEN_PERSIST") && atoi(getenv("LFMQ_GEN_PERSIST")) == 0);
+  return on && n_steps > 1 && m.gbar != nullptr && ctas * n_concurrent <= (long)m.n_sms * per_sm &&
+         m.gbar_next + ctas * n_concurrent <= GBAR_N;
 }
 
 static void gen_print_trace(GenImpl& m, cudaStream_t s) {
@@ -1539,6 +1611,7 @@ void gen_destroy(GenState& st) {
     cudaStreamDestroy(st.impl->side);
   }
   if (st.impl && st.impl->trace) cudaFree(st.impl->trace);
+  if (st.impl && st.impl->gbar) cudaFree(st.impl->gbar);
   delete st.impl;
   st.impl = nullptr;
 }
@@ -1615,6 +1688,8 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
   const bool drop = c.train && c.dropout > 0.f;
   static const char* dual_env = getenv("LFMQ_GEN_DUAL");      // 0 / 1 force, unset: by tile count
   const bool dual = dual_env ? atoi(dual_env) != 0 : ((long)((nrt + 1) / 2) * (4 * H / 256) >= 96);
+  LFMQ_CUDA_CHECK(cudaMemsetAsync(m.gbar, 0, GBAR_N * sizeof(unsigned int), s));
+  m.gbar_next = 0;
   {
     const GenLayer& l0 = m.layers[0];
     const long n = (long)B * T * (l0.Ipad / 8);
@@ -1633,12 +1708,22 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
     ep.use_rec = rec ? 1 : 0;
     ep.rkey = gkey(c, 2 * l + 1, step, c.recurrent_dropout);
     const CUtensorMap& th = rec ? ly.tm_hm : ly.tm_h;
+    // steps 1 .. T-1 as ONE persistent launch when all its CTAs fit on the machine at once (see GArgs::n_steps)
+    const long fwd_ctas = dual ? (long)((nrt + 1) / 2) * (4 * H / 256) : (long)nrt * (4 * H / 256);
+    const bool persist = gen_can_persist(m, fwd_ctas, 1, dual ? 1 : 2, T - 1);
     for (int t = 0; t < T; ++t) {
       ep.t = t;
       ep.trace = m.trace ? m.trace + (((size_t)0 * m.L + l) * T + t) * 8 : nullptr;
       GArgs g = {};
       g.a_row_base = t * Bp;
       g.b_row_base = 0;
+      if (persist && t == 1) {
+        g.n_steps = T - 1;
+        g.row_step = Bp;
+        g.t_step = 1;
+        g.gbar = m.gbar + m.gbar_next;
+        m.gbar_next += dual ? (nrt + 1) / 2 : nrt;
+      }
       const int nkb_h = (t > 0) ? H / 64 : 0, nkb_x = ly.Ipad / 64;
       int ns = 0;
       // maps: A0 = h (or masked h), A1 = input, A2 = h low halves, A3 = input low halves; B0 = weights, B1 = their low halves
@@ -1667,6 +1752,7 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
       }
 #undef LFMQ_FWD_LAUNCH
       if (rc) return rc;
+      if (persist && t == 1) break;              // that launch ran steps 1 .. T-1
     }
     const bool last = (l == m.L - 1);
     __nv_bfloat16* yo = last ? m.head_in : m.layers[l + 1].in;
@@ -1889,6 +1975,9 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       LFMQ_CUDA_CHECK(cudaEventRecord(m.ev_fork, s));
       LFMQ_CUDA_CHECK(cudaStreamWaitEvent(m.side, m.ev_fork, 0));
     }
+    // steps T-2 .. 0 of each chain as ONE persistent launch when all CTAs of both chains fit on the machine at once
+    const long bwd_ctas = (long)n_a * (H / m.BNU);
+    const bool persist = gen_can_persist(m, bwd_ctas, split ? 2 : 1, 1, T - 1);
     for (int t = T - 1; t >= 0; --t) {
       for (int half = 0; half < (split ? 2 : 1); ++half) {       // launches interleaved: neither chain lags the other
         cudaStream_t hs = half ? m.side : s;
@@ -1902,6 +1991,13 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
         g.rt_off = rt_off;
         g.n_seg = ep.has_rec ? 1 : 0;
         g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
+        if (persist && t == T - 2) {
+          g.n_steps = T - 1;
+          g.row_step = -Bp;
+          g.t_step = -1;
+          g.gbar = m.gbar + m.gbar_next;
+          m.gbar_next += n_rt;
+        }
         if (m.BNU == 128)
           rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(n_rt, H / 128), hs, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz,
                                                  m.tm_dz, ly.tm_ub, ly.tm_ub);
@@ -1910,6 +2006,7 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
                                                 m.tm_dz, ly.tm_ub, ly.tm_ub);
         if (rc) return rc;
       }
+      if (persist && t == T - 2) break;          // those launches ran steps T-2 .. 0
     }
     if (split) {
       LFMQ_CUDA_CHECK(cudaEventRecord(m.ev_join, m.side));
