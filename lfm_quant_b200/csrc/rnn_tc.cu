@@ -98,6 +98,8 @@ struct GArgs {
   // boundary: CTA dispatch, barrier init, TMEM allocation and the wait for the whole previous grid to retire are paid
   // once, and the row-tile groups drift apart instead of hitting HBM in lockstep.
   int n_steps, row_step, t_step;
+  int lin_cols;        // > 0: 1-D grid, CTA i = (row tile i / lin_cols, column tile i % lin_cols): the column tiles of a row
+                       // tile are dispatched together and share its A tile in L2 (multi-wave GEMMs: EPI_STORE)
   unsigned int* gbar;  // [gridDim.x], zeroed before the launch; counts the group's CTAs that have finished a step
 };
 
@@ -425,9 +427,9 @@ __device__ __forceinline__ void epi_bwd(const EpiParams& p, uint32_t tmem, int q
 
 // ---- EPI_STORE: accumulator -> bf16 row-major ---------------------------------------------------------------------
 template <int BN>
-__device__ __forceinline__ void epi_store(const EpiParams& p, uint32_t tmem, int q, int lane, long row) {
+__device__ __forceinline__ void epi_store(const EpiParams& p, uint32_t tmem, int q, int lane, long row, int by) {
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  __nv_bfloat16* o = p.out + row * p.ldc + (long)blockIdx.y * BN;
+  __nv_bfloat16* o = p.out + row * p.ldc + (long)by * BN;
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
@@ -556,6 +558,8 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_base_s;
+  const int bx = g.lin_cols > 0 ? (int)blockIdx.x / g.lin_cols : (int)blockIdx.x;      // row-tile / column-tile coordinates
+  const int by = g.lin_cols > 0 ? (int)blockIdx.x % g.lin_cols : (int)blockIdx.y;
   const bool tr = ep.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (tr && tid == 0) ep.trace[0] = clock64();
 
@@ -569,9 +573,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   const unsigned int n_cta = gridDim.y;             // CTAs of this row-tile group
   if (warp == 0) {
     if (lane == 0) {
-      const int brow = g.b_row_base + BN * (int)blockIdx.y;
+      const int brow = g.b_row_base + BN * by;
       for (int it = 0; it < n_steps; ++it) {
-        const int arow = g.a_row_base + it * g.row_step + 128 * (MT * (int)blockIdx.x + g.rt_off);
+        const int arow = g.a_row_base + it * g.row_step + 128 * (MT * bx + g.rt_off);
         const int gi0 = it * total_kb;               // ring position of this step's first k-block
         {   // B operand (weights) of the first NS stages of the step, before the dependency wait
           int i = 0;
@@ -664,7 +668,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
     const int grp = (warp - 2) >> 2;                 // group of four warps = one pass over the four TMEM lane quadrants
     const int mt = grp / S::EW;                      // which 128-row M tile of the CTA this group works on
     const int part = grp % S::EW;                    // ... and which share of its column blocks
-    const int rt = MT * (int)blockIdx.x + mt + g.rt_off;        // 128-row tile index
+    const int rt = MT * bx + mt + g.rt_off;        // 128-row tile index
     // (An L2 prefetch of the epilogue's saved-state operands issued here, during the mainloop, was measured and lost:
     //  it delays the operand ring -- first stage 1.5 K -> 3 K cycles -- and the epilogue, which is issue-bound, not
     //  HBM-bound, got no shorter: 2.97 -> 3.25 ms for the backward steps of BASELINE configs[2].)
@@ -683,7 +687,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
         if constexpr (EPI == EPI_FWD) epi_fwd<BN, false>(ep, tacc, q, lane, rt, bias_s);
         if constexpr (EPI == EPI_FWD_ACC) epi_fwd<BN, true>(ep, tacc, q, lane, rt, bias_s);
         if constexpr (EPI == EPI_BWD) epi_bwd<BN>(ep, tacc, q, lane, rt, part, S::EW);
-        if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane);
+        if constexpr (EPI == EPI_STORE) epi_store<BN>(ep, tacc, q, lane, (long)g.a_row_base + 128L * rt + q * 32 + lane, by);
       }
       if (tr && warp == 2 && lane == 0) ep.trace[(long)it * g.t_step * 8 + 5] = clock64();
       if (n_steps > 1) {
@@ -1851,11 +1855,12 @@ static int gen_run_head(GenState& st, const lfmq_config& c, const float* params,
       gd.n_seg = 1;
       gd.seg[0] = GSeg{0, 0, 1, 0, 0};
       const int row_tiles = m.T * m.Bp / 128;
+      gd.lin_cols = (m.H % 128 == 0) ? m.H / 128 : m.H / 64;
       if (m.H % 128 == 0)
-        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles, m.H / 128), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
+        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles * (m.H / 128)), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
                                                  m.tm_dpb, m.tm_wos, m.tm_wos);
       else
-        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles, m.H / 64), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
+        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles * (m.H / 64)), s, false, gd, es, m.tm_dpb, m.tm_dpb, m.tm_dpb,
                                                 m.tm_dpb, m.tm_wos, m.tm_wos);
       if (rc) return rc;
       int S = 0, Mpad = 0;
@@ -2035,11 +2040,12 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
       g.n_seg = 1;
       g.seg[0] = GSeg{0, 0, 4 * H / 64, 0, 0};
       const int row_tiles = T * Bp / 128;
+      g.lin_cols = (H % 128 == 0) ? H / 128 : H / 64;
       if (H % 128 == 0)
-        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles, H / 128), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
+        rc = launch_tile_gemm<128, EPI_STORE, 1>(dim3(row_tiles * (H / 128)), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
                                                  m.tm_dz, ly.tm_wb, ly.tm_wb);
       else
-        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles, H / 64), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
+        rc = launch_tile_gemm<64, EPI_STORE, 1>(dim3(row_tiles * (H / 64)), s, false, g, es, m.tm_dz, m.tm_dz, m.tm_dz,
                                                 m.tm_dz, ly.tm_wb, ly.tm_wb);
       if (rc) return rc;
     }
