@@ -252,6 +252,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// the same arrive on the barrier at this offset in every CTA of `cta_mask` (multicast operand rings: a stage is free
+// only when all CTAs that received it have consumed it)
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---- TMEM loads ---------------------------------------------------------------------------------
 // 32x32b: thread i of the warp reads TMEM lane (lane_base + i), `n` consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t v[32]) {
