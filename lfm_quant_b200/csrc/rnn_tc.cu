@@ -98,9 +98,6 @@ struct GArgs {
   // boundary: CTA dispatch, barrier init, TMEM allocation and the wait for the whole previous grid to retire are paid
   // once, and the row-tile groups drift apart instead of hitting HBM in lockstep.
   int n_steps, row_step, t_step;
-  int mcast;           // > 1: the CTAs (x, y .. y + mcast - 1) form a thread-block cluster and share their A tile: each loads
-                       // 128 / mcast rows of it (map A1, a box of that height) and multicasts them to all, which cuts the
-                       // L2 -> SM traffic of the mainloop by (mcast - 1) / (2 mcast) (EPI_BWD: 128 x 128 tiles, MT = 1)
   int lin_cols;        // > 0: 1-D grid, CTA i = (row tile i / lin_cols, column tile i % lin_cols): the column tiles of a row
                        // tile are dispatched together and share its A tile in L2 (multi-wave GEMMs: EPI_STORE)
   unsigned int* gbar;  // [gridDim.x], zeroed before the launch; counts the group's CTAs that have finished a step
@@ -547,13 +544,10 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   int total_kb = 0;
   for (int i = 0; i < g.n_seg; ++i) total_kb += g.seg[i].n_kb;
 
-  const int CL = (MT == 1 && g.mcast > 1) ? g.mcast : 1;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   if (tid == 0) {
     for (int s = 0; s < S::NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);            // multicast ring: every CTA of the cluster has consumed the stage
+      mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     mbar_init(tmem_free, 1);
@@ -562,7 +556,6 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   if (warp == 1) tmem_alloc(tmem_base_s, TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before anyone multicasts into / arrives on them
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_base_s;
   const int bx = g.lin_cols > 0 ? (int)blockIdx.x / g.lin_cols : (int)blockIdx.x;      // row-tile / column-tile coordinates
@@ -627,15 +620,9 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
               mbar_arrive_expect_tx(&full[s], S::STAGE);
               tma_load_2d(st + S::A_BYTES, mb, &full[s], sgm.b_col0 + kb * 64, brow);
             }
-            if (CL > 1) {
-              const int rows_q = 128 / CL;
-              tma_load_2d_mcast(st + crank * rows_q * 128, &tmA1, &full[s], sgm.a_col0 + kb * 64, arow + rows_q * (int)crank,
-                                cmask);
-            } else {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt)
-                tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
-            }
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_2d(st + mt * 16384, ma, &full[s], sgm.a_col0 + kb * 64, arow + 128 * mt);
           }
         }
       }
@@ -668,8 +655,7 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
               umma_f16(tmem + mt * BN, da, db, idesc, (i | k16) != 0);
             }
           }
-          if (CL > 1) umma_commit_mcast(&empty[s], cmask);
-          else umma_commit(&empty[s]);
+          umma_commit(&empty[s]);
         }
         umma_commit(acc_full);
         if (tr) ep.trace[(long)it * g.t_step * 8 + 3] = clock64();
@@ -721,7 +707,6 @@ __global__ void __launch_bounds__(GSmem<BN, MT, EPI>::THREADS, GSmem<BN, MT, EPI
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // nobody leaves while peers may still multicast into / arrive on this CTA
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -1404,9 +1389,6 @@ struct GenImpl {
   float *cstate = nullptr, *dcstate = nullptr;
   __nv_bfloat16 *dz = nullptr, *dy = nullptr, *dhout = nullptr;
   CUtensorMap tm_dz, tm_dz_mn;
-  CUtensorMap tm_dz_q;                  // dz as A operand in 128 / bwd_mcast-row boxes (multicast pieces)
-  int bwd_mcast = 0;                    // cluster size of the backward step kernel along the column tiles (0: off)
-  int bwd_max_clusters = 0;             // how many such clusters the device can run at once
   float *dpred = nullptr, *head_part = nullptr, *head_wpart = nullptr, *bn_part = nullptr, *cs_part = nullptr;
   float* wg_part = nullptr;
   size_t wg_part_elems = 0;
@@ -1561,17 +1543,6 @@ int gen_init(GenState& st, const lfmq_config& c) {
     LFMQ_CUDA_CHECK(cudaMemset(m.dpred, 0, T * Bp * GH_O * 4));
     if ((rc = gmap_2d(&m.tm_dz, m.dz, 4 * H, T * Bp, 64, 128))) return rc;
     if ((rc = gmap_2d(&m.tm_dz_mn, m.dz, 4 * H, T * Bp, 64, 64))) return rc;
-    // A-operand multicast of the backward step (GArgs::mcast): the column tiles of a row tile form a cluster
-    const int ncol = (int)(H / m.BNU);
-    // Off by default (LFMQ_GEN_MCAST=1 turns it on): measured neutral, 2.602 vs 2.611 ms of backward steps on BASELINE
-    // configs[2] with 535 cycles per 32 KB k-block either way (profiles/r02_summary.md, c39/c40).  The mainloop is bound
-    // by what one SM can RECEIVE (~64 B/clk), and a multicast tile still arrives in full at every SM of the cluster; it
-    // only spares the L2, which was not the limit.
-    static const bool mc_on = getenv("LFMQ_GEN_MCAST") && atoi(getenv("LFMQ_GEN_MCAST")) != 0;
-    if (mc_on && m.BNU == 128 && (ncol == 2 || ncol == 4)) {
-      m.bwd_mcast = ncol;
-      if ((rc = gmap_2d(&m.tm_dz_q, m.dz, 4 * H, T * Bp, 64, 128 / ncol))) return rc;
-    }
   }
 #define LFMQ_GEMM_ATTR(BN_, EPI_, MT_)                                                                         \
   LFMQ_CUDA_CHECK(cudaFuncSetAttribute(tile_gemm_kernel<BN_, EPI_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1598,26 +1569,6 @@ int gen_init(GenState& st, const lfmq_config& c) {
   if (getenv("LFMQ_TRACE_GEN")) {
     LFMQ_CUDA_CHECK(cudaMalloc(&m.trace, (size_t)2 * m.L * T * 8 * sizeof(long long)));
     LFMQ_CUDA_CHECK(cudaMemset(m.trace, 0, (size_t)2 * m.L * T * 8 * sizeof(long long)));
-  }
-  if (m.bwd_mcast > 1) {
-    cudaLaunchConfig_t oc = {};
-    oc.gridDim = dim3(1, m.bwd_mcast);
-    oc.blockDim = dim3(GSmem<128, 1, EPI_BWD>::THREADS);
-    oc.dynamicSmemBytes = GSmem<128, 1, EPI_BWD>::TOTAL;
-    cudaLaunchAttribute oa[1];
-    oa[0].id = cudaLaunchAttributeClusterDimension;
-    oa[0].val.clusterDim.x = 1;
-    oa[0].val.clusterDim.y = (unsigned)m.bwd_mcast;
-    oa[0].val.clusterDim.z = 1;
-    oc.attrs = oa;
-    oc.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, tile_gemm_kernel<128, EPI_BWD, 1>, &oc) != cudaSuccess) {
-      cudaGetLastError();
-      nc = 0;
-    }
-    m.bwd_max_clusters = nc;
-    if (nc <= 0) m.bwd_mcast = 0;
   }
   LFMQ_CUDA_CHECK(cudaMalloc(&m.gbar, GBAR_N * sizeof(unsigned int)));
   LFMQ_CUDA_CHECK(cudaMemset(m.gbar, 0, GBAR_N * sizeof(unsigned int)));
@@ -1681,22 +1632,11 @@ static int launch_tile_gemm(dim3 grid, cudaStream_t s, bool pdl, const GArgs& g,
   cfg.blockDim = dim3(GSmem<BN, MT, EPI>::THREADS);
   cfg.dynamicSmemBytes = GSmem<BN, MT, EPI>::TOTAL;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (pdl && pdl_on) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (g.mcast > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
-    attr[na].val.clusterDim.y = (unsigned)g.mcast;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = na;
+  cfg.numAttrs = (pdl && pdl_on) ? 1 : 0;
   LFMQ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<BN, EPI, MT>, g, ep, a0, a1, a2, a3, b0, b1));
   g_launches++;
   if (debug_sync_on()) {
@@ -2063,15 +2003,9 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
           g.gbar = m.gbar + m.gbar_next;
           m.gbar_next += n_rt;
         }
-        // clusters over the column tiles with the A tile multicast; in persistent mode only if all clusters of both
-        // chains can run at once
-        if (ep.has_rec && m.bwd_mcast > 1 && (!persist || nrt <= m.bwd_max_clusters)) g.mcast = m.bwd_mcast;
-        if (m.trace && t == T - 2 && half == 0 && l == m.L - 1)
-          fprintf(stderr, "[gen bwd] persist %d split %d mcast %d (cluster size %d, device runs %d such clusters at once, %d needed)\n",
-                  (int)persist, (int)split, g.mcast, m.bwd_mcast, m.bwd_max_clusters, nrt);
         if (m.BNU == 128)
-          rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(n_rt, H / 128), hs, t < T - 1, g, ep, m.tm_dz,
-                                                 g.mcast > 1 ? m.tm_dz_q : m.tm_dz, m.tm_dz, m.tm_dz, ly.tm_ub, ly.tm_ub);
+          rc = launch_tile_gemm<128, EPI_BWD, 1>(dim3(n_rt, H / 128), hs, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz,
+                                                 m.tm_dz, ly.tm_ub, ly.tm_ub);
         else
           rc = launch_tile_gemm<64, EPI_BWD, 1>(dim3(n_rt, H / 64), hs, t < T - 1, g, ep, m.tm_dz, m.tm_dz, m.tm_dz,
                                                 m.tm_dz, ly.tm_ub, ly.tm_ub);
