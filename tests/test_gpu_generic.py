@@ -161,3 +161,36 @@ def test_tensor_core_paths_refuse_unsupported_shapes_loudly():
         make_engine(8, 4, 32, 16, 96, 1, precision='bf16')       # H not a multiple of 64
     with pytest.raises(LfmqError):
         make_engine(8, 4, 32, 17, 128, 1, precision='bf16')      # n_outputs > 16
+
+
+def test_persistent_steps_equal_one_launch_per_step():
+    """The persistent step launches (GArgs::n_steps, one barrier per row-tile group) run the same arithmetic in the same
+    order as one launch per time step: gradients and outputs must agree bit for bit (LFMQ_GEN_PERSIST is read once per
+    process, hence the two subprocesses)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/oracle'); sys.path.insert(0, %r + '/tests')
+from util import make_engine, make_problem
+B, T, F, O, H, L = 200, 12, 16, 8, 128, 2
+params, x, y = make_problem(B, T, F, O, H, L, seed=4)
+eng = make_engine(B, T, F, O, H, L, target_idx=1, precision='bf16', train=True, dropout=0.2, recurrent_dropout=0.1, seed=9)
+eng.set_weights(params)
+xc, yc = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+eng.backward(xc, yc, step=3, row0=7)
+torch.cuda.synchronize()
+np.save(sys.argv[1], eng.grads.detach().cpu().numpy())
+''' % (root, root, root)
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ('1', '0'):
+            path = os.path.join(d, 'g%s.npy' % mode)
+            env = dict(os.environ, LFMQ_GEN_PERSIST=mode)
+            subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=120)
+            outs.append(np.load(path))
+    assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
+    np.testing.assert_array_equal(outs[0], outs[1])
