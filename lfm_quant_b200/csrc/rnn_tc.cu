@@ -253,11 +253,7 @@ __device__ __forceinline__ void epi_fwd(const EpiParams& p, uint32_t tmem, int q
       const long hoff = ((long)(p.t + 1) * p.Bp + b) * p.H + j0;
       uint32_t w[8];
       pack16(hv, w);
-#ifndef LFMQ_EXP_NO_H       // timing experiment only
       st_global_v8(p.hseq + hoff, w);
-#else
-      if (w[0] == 0x12345678u && w[1] == 0x9abcdef0u) st_global_v8(p.hseq + hoff, w);
-#endif
       if (p.hseq_lo) {        // bf16x3: h = hi + lo with |lo| <= 2^-9 |h|
         float lo[16];
 #pragma unroll
@@ -391,14 +387,12 @@ __device__ __forceinline__ void bwd_block(const EpiParams& p, uint32_t tmem_blk,
 #pragma unroll
     for (int e = 0; e < 8; ++e) zi[e] = zf[e] = zg[e] = zo[e] = 0u;
   }
-#ifndef LFMQ_EXP_NO_DZ      // timing experiment only (wrong results): how much of the epilogue the row-major stores cost
+  // (row-major 32-byte pieces, one line per lane: a store-free timing run put their cost at up to 0.44 ms per train step of
+  //  BASELINE configs[2], profiles/r02_summary.md c27; they stay row-major because dz is a TMA-loaded GEMM operand)
   st_global_v8(dzr, zi);
   st_global_v8(dzr + (long)p.H, zf);
   st_global_v8(dzr + 2L * p.H, zg);
   st_global_v8(dzr + 3L * p.H, zo);
-#else
-  if (zi[0] == 0x12345678u && zf[1] == 0x9abcdef0u && zg[2] == 0x1u && zo[3] == 0x2u) st_global_v8(dzr, zi);
-#endif
 }
 
 // `part` of `nparts` warps of this lane quadrant: blocks part, part + nparts, ...
