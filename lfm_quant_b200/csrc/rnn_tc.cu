@@ -814,13 +814,14 @@ __global__ void __launch_bounds__(GWCfg<MT>::THREADS, 1)
 }
 
 // dst[row][n] = sum_z partial[z][row][n] for row < Mvalid (dst row-major [Mvalid][Ntot])
+// (rows row_first .. row_first + Mvalid - 1 of the partials)
 __global__ void gwgrad_reduce_kernel(int S, int Mvalid, int Mpad, int Ntot, const float* __restrict__ partial,
-                                     float* __restrict__ dst) {
+                                     float* __restrict__ dst, int row_first) {
   const long idx = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (idx >= (long)Mvalid * Ntot) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z = 0; z < S; ++z) {
-    const float4 v = *reinterpret_cast<const float4*>(partial + (long)z * Mpad * Ntot + idx);
+    const float4 v = *reinterpret_cast<const float4*>(partial + (long)z * Mpad * Ntot + (long)row_first * Ntot + idx);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   *reinterpret_cast<float4*>(dst + idx) = s;
@@ -830,8 +831,10 @@ __global__ void gwgrad_reduce_kernel(int S, int Mvalid, int Mpad, int Ntot, cons
 // Small streaming kernels
 // =============================================================================================
 // x f32 [B][T][F] -> in0 bf16 [T][Bp][Ipad] (+ low halves for bf16x3); 8 columns per thread, padding columns zero.
+// `ones`: column F (the first padding column) is set to 1 -- the weights of the padding rows are zero, so the forward GEMM
+// does not see it, and the weight-gradient GEMM in0^T dz then delivers db = colsum(dz) of the first layer as its row F.
 __global__ void gcast_x_kernel(int B, int T, int F, int Bp, int Ipad, const float* __restrict__ x,
-                               __nv_bfloat16* __restrict__ o, __nv_bfloat16* __restrict__ o_lo) {
+                               __nv_bfloat16* __restrict__ o, __nv_bfloat16* __restrict__ o_lo, int ones) {
   const int c8 = Ipad / 8;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * T * c8) return;
@@ -843,7 +846,7 @@ __global__ void gcast_x_kernel(int B, int T, int F, int Bp, int Ipad, const floa
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int f = c * 8 + e;
-    v[e] = (f < F) ? x[(b * T + t) * F + f] : 0.f;
+    v[e] = (f < F) ? x[(b * T + t) * F + f] : ((ones && f == F) ? 1.f : 0.f);
   }
   uint4 w;
   w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]); w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
@@ -1691,7 +1694,8 @@ static int gen_run_trunk(GenState& st, const lfmq_config& c, const float* params
   {
     const GenLayer& l0 = m.layers[0];
     const long n = (long)B * T * (l0.Ipad / 8);
-    gcast_x_kernel<<<(int)cdivl(n, 256), 256, 0, s>>>(B, T, m.F, Bp, l0.Ipad, x, l0.in, l0.in_lo);
+    gcast_x_kernel<<<(int)cdivl(n, 256), 256, 0, s>>>(B, T, m.F, Bp, l0.Ipad, x, l0.in, l0.in_lo,
+                                                      (save && !m.x3 && l0.Ipad > m.F) ? 1 : 0);
     LFMQ_LAUNCH_CHECK();
   }
   for (int l = 0; l < m.L; ++l) {
@@ -1800,13 +1804,18 @@ static int gen_wgrad_gemm(GenImpl& m, const CUtensorMap& tm_a, const CUtensorMap
   return 0;
 }
 
-static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst, cudaStream_t s) {
+// `db` (nullable): row Mvalid of the product (A's constant-one column, see gcast_x_kernel) = colsum(dz)
+static int gen_wgrad(GenImpl& m, const CUtensorMap& tm_a, int Mvalid, float* dst, cudaStream_t s, float* db = nullptr) {
   const int Ntot = 4 * m.H;
   int S = 0, Mpad = 0, rc;
-  if ((rc = gen_wgrad_gemm(m, tm_a, m.tm_dz_mn, Mvalid, Ntot, &S, &Mpad, s))) return rc;
+  if ((rc = gen_wgrad_gemm(m, tm_a, m.tm_dz_mn, db ? Mvalid + 1 : Mvalid, Ntot, &S, &Mpad, s))) return rc;
   const long n4 = (long)Mvalid * Ntot / 4;
-  gwgrad_reduce_kernel<<<(int)cdivl(n4, 256), 256, 0, s>>>(S, Mvalid, Mpad, Ntot, m.wg_part, dst);
+  gwgrad_reduce_kernel<<<(int)cdivl(n4, 256), 256, 0, s>>>(S, Mvalid, Mpad, Ntot, m.wg_part, dst, 0);
   LFMQ_LAUNCH_CHECK();
+  if (db) {
+    gwgrad_reduce_kernel<<<(int)cdivl(Ntot / 4, 256), 256, 0, s>>>(S, 1, Mpad, Ntot, m.wg_part, db, Mvalid);
+    LFMQ_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -2014,8 +2023,10 @@ int gen_backward(GenState& st, const lfmq_config& c, const float* params, float*
     st.prof->end(LFMQ_REGION_BWD, s);
     st.prof->begin(LFMQ_REGION_WGRAD, s);
     if ((rc = gen_wgrad(m, ly.tm_hA_mn, H, grads + ly.off.oU, s))) return rc;
-    if ((rc = gen_wgrad(m, ly.tm_in_mn, ly.I, grads + ly.off.oW, s))) return rc;
-    {   // db = column sums of dz over the T*Bp rows (rows beyond the batch are zero)
+    // first layer: the input buffer's first padding column is constant one (gcast_x_kernel), so db falls out of the dW GEMM
+    const bool ones_db = (l == 0) && !m.x3 && ly.Ipad > ly.I;
+    if ((rc = gen_wgrad(m, ly.tm_in_mn, ly.I, grads + ly.off.oW, s, ones_db ? grads + ly.off.ob : nullptr))) return rc;
+    if (!ones_db) {   // db = column sums of dz over the T*Bp rows (rows beyond the batch are zero)
       const long rows = (long)T * Bp;
       const long rpc = cdivl(rows, m.cs_chunks);
       gcolsum_kernel<<<dim3((4 * H / 8 + 127) / 128, m.cs_chunks), 128, 0, s>>>(rows, 4 * H, rpc, m.dz, m.cs_part);

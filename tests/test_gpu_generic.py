@@ -165,8 +165,9 @@ def test_tensor_core_paths_refuse_unsupported_shapes_loudly():
 
 def test_persistent_steps_equal_one_launch_per_step():
     """The persistent step launches (GArgs::n_steps, one barrier per row-tile group) run the same arithmetic in the same
-    order as one launch per time step: gradients and outputs must agree bit for bit (LFMQ_GEN_PERSIST is read once per
-    process, hence the two subprocesses)."""
+    order as one launch per time step: the gradients must agree to fp32 rounding (the head's loss / bias-gradient sums
+    go through shared-memory atomics, so a last-bit difference between two runs is possible whatever the mode).
+    LFMQ_GEN_PERSIST is read once per process, hence the two subprocesses."""
     import os
     import subprocess
     import sys
@@ -193,4 +194,4 @@ np.save(sys.argv[1], eng.grads.detach().cpu().numpy())
             subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=120)
             outs.append(np.load(path))
     assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
-    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-6, atol=1e-9)
