@@ -88,3 +88,30 @@ def test_keras_keys_follow_the_reference_layer_stack(tmp_path, L, cell, uq):
     assert b'layer_with_weights-0' in graph and b'VARIABLE_VALUE' in graph and b'cell' in graph
     with pytest.raises(KeyError, match='layer_with_weights'):
         tfc.read_keras_checkpoint(prefix, names + ['lstm_9/kernel'])
+
+
+def test_construction_order_keys_for_the_multi_step_graph(tmp_path):
+    """forecast_steps > 1 (rnn_point_estimate.py:109-150): heads and extra recurrent layers interleave, so the
+    layer_with_weights numbering follows construction order; round trip through the TF-format container."""
+    from lfm_quant_b200 import tf_checkpoint as tfc
+    names = ['lstm_1/kernel', 'lstm_1/recurrent_kernel', 'lstm_1/bias', 'batch_normalization/gamma',
+             'batch_normalization/beta', 'OUTPUT_1/kernel', 'OUTPUT_1/bias', 'batch_normalization/moving_mean',
+             'batch_normalization/moving_variance', 'lstm_2/kernel', 'lstm_2/recurrent_kernel', 'lstm_2/bias',
+             'batch_normalization_1/gamma', 'batch_normalization_1/beta', 'OUTPUT_2/kernel', 'OUTPUT_2/bias',
+             'batch_normalization_1/moving_mean', 'batch_normalization_1/moving_variance']
+    keys = tfc.keras_keys(names, construction_order=True)
+    assert keys['lstm_1/kernel'].startswith('layer_with_weights-0/cell/kernel')
+    assert keys['batch_normalization/moving_mean'].startswith('layer_with_weights-1/moving_mean')
+    assert keys['OUTPUT_1/bias'].startswith('layer_with_weights-2/bias')
+    assert keys['lstm_2/recurrent_kernel'].startswith('layer_with_weights-3/cell/recurrent_kernel')
+    assert keys['batch_normalization_1/gamma'].startswith('layer_with_weights-4/gamma')
+    assert keys['OUTPUT_2/kernel'].startswith('layer_with_weights-5/kernel')
+    # the default (forecast_steps = 1) numbering puts every recurrent layer before the heads
+    assert tfc.keras_keys(names)['OUTPUT_1/bias'].startswith('layer_with_weights-4/')
+    rng = np.random.RandomState(0)
+    arrs = {n: rng.normal(size=(3, 4) if n.endswith('kernel') else (4,)).astype(np.float32) for n in names}
+    prefix = str(tmp_path / 'chkpt')
+    tfc.write_keras_checkpoint(prefix, arrs, construction_order=True)
+    back = tfc.read_keras_checkpoint(prefix, names, {n: a.shape for n, a in arrs.items()}, construction_order=True)
+    for n in names:
+        np.testing.assert_array_equal(back[n], arrs[n])
