@@ -96,7 +96,7 @@ def oracle_cfg(w):
                 optimizer='Adadelta', max_norm=3.0, train=True, dropout=w['dropout'], recurrent_dropout=0.0, seed=SEED)
 
 
-def cpu_port_seq_per_s(w, rows, steps, threads):
+def cpu_port_seq_per_s(w, rows, steps, threads, warm=1):
     """Times oracle.train_step (fp32 NumPy; oracle.forward for the predict workload) on `rows` windows per step.  The
     BLAS thread count is scanned on a small sample (per-step matmuls this small do not scale to 128 threads) and the
     best one is kept; returns (windows/s, seconds/step, threads used)."""
@@ -126,7 +126,7 @@ def cpu_port_seq_per_s(w, rows, steps, threads):
 
     cands = sorted({min(threads, c) for c in (4, 8, 16, 32, threads)})
     best = min(cands, key=lambda c: run(c, min(rows, 256), 1, 1))
-    per_step = run(best, rows, steps, 1)
+    per_step = run(best, rows, steps, warm)
     return rows / per_step, per_step, best
 
 
@@ -190,7 +190,7 @@ def run_reference(args, w, rank, world):
         return
     cores = os.cpu_count() or 1
     rows = args.cpu_rows or (w['B'] if w['mode'] == 'train' else 4096)
-    v, s_per_step, used = cpu_port_seq_per_s(w, rows, max(1, args.steps), cores)
+    v, s_per_step, used = cpu_port_seq_per_s(w, rows, max(1, args.steps), cores, warm=args.warmup)   # W untimed steps, as asked
     full = rows == w['B']
     line = {
         'impl': 'reference', 'metric': w['metric'], 'value': v, 'unit': 'sequences/s', 'n_gpus': args.gpus,
@@ -200,10 +200,10 @@ def run_reference(args, w, rank, world):
                                                               ' (bounded sample of %d windows per step)' % rows),
                    'same_config': bool(full)},
         'cpu_baseline': {'value': v, 'unit': 'sequences/s', 'cores': used, 'kind': 'port',
-                         'sample': '%d of %d windows per step, %d steps after 1 warm-up; NumPy fp32 restatement (oracle/) '
+                         'sample': '%d of %d windows per step, %d steps after %d warm-up; NumPy fp32 restatement (oracle/) '
                                    '-- TensorFlow (the reference runtime) is not installable in this image; host has %d '
                                    'cores, `cores` = the BLAS thread count that was fastest and was used'
-                                   % (rows, w['B'], args.steps, cores)},
+                                   % (rows, w['B'], args.steps, args.warmup, cores)},
         'e2e': {'value': v, 'unit': 'sequences/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
